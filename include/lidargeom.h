@@ -1,0 +1,133 @@
+/*
+ * lidargeom.h -- C ABI of liblidargeom.so: B200 (sm_100a) rotated 3D-box geometry ops.
+ *
+ * This is the drop-in boundary for the reference's two pybind11/torch extensions
+ *   iou3d_nms_cuda        (pcdet/ops/iou3d_nms/src/iou3d_nms_api.cpp:11-17, iou3d_nms.h:9-12)
+ *   roiaware_pool3d_cuda  (pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp:172-177; points_in_boxes_* only)
+ * Each entry point below cites the reference function it replaces.  There are no torch / pybind
+ * types in any signature: plain device pointers, sizes, and a CUDA stream passed as void*.
+ *
+ * Conventions
+ *   - boxes are float32 rows of 7: (x, y, z, dx, dy, dz, heading), contiguous, 4-byte aligned
+ *     (28-byte rows are NOT 16-byte aligned; the library never assumes they are).
+ *   - points are float32 rows of 3: (x, y, z).
+ *   - every pointer is a DEVICE pointer unless its name ends in _host.
+ *   - the library never allocates, never synchronises and keeps no global state: outputs and the
+ *     scratch `ws` are caller-owned (query the size with lg_*_workspace_bytes), work is enqueued on
+ *     `stream` (a cudaStream_t; NULL = legacy default stream) and is stream-ordered.
+ *   - return value: LG_OK (0), a positive cudaError_t from the launch, or a negative LG_ERR_* code.
+ *     lg_last_error_string() describes the last failure on the calling thread.
+ *     (The reference prints to stderr and calls exit(-1): iou3d_nms.cpp:14-38.)
+ *   - empty inputs (n == 0, m == 0, ...) return LG_OK without launching anything.
+ *
+ * Arithmetic contract (DESIGN.md "arithmetic contract"): by default every IoU is computed with the
+ * operation order AND the FMA contraction of the reference CUDA kernels as nvcc 12.9 builds them for
+ * sm_100a, so results agree with the reference GPU path to the last bits (polygon-vertex ordering
+ * ties aside).  LG_FLAG_STRICT_FP32 switches to the un-contracted arithmetic of the reference CPU
+ * build (iou3d_cpu.cpp compiled by g++ -O2 on x86-64).
+ */
+#ifndef LIDARGEOM_H_
+#define LIDARGEOM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LG_API __attribute__((visibility("default")))
+#else
+#define LG_API
+#endif
+
+#define LG_VERSION 100 /* 0.1.0 */
+
+#define LG_OK 0
+#define LG_ERR_INVALID_ARG (-1)   /* null pointer, negative size, ld_out < m, ... */
+#define LG_ERR_WORKSPACE (-2)     /* ws == NULL or ws_bytes too small */
+#define LG_ERR_TOO_LARGE (-3)     /* size exceeds a documented limit */
+#define LG_ERR_NO_DEVICE (-4)     /* no usable CUDA device / wrong architecture */
+
+/* flags */
+#define LG_FLAG_NONE 0u
+#define LG_FLAG_STRICT_FP32 1u /* un-contracted FP32 (reference CPU build's rounding) instead of the reference CUDA build's */
+
+/* limits */
+#define LG_NMS_MAX_BOXES 65536 /* per NMS problem */
+#define LG_PIB_MAX_BOXES 4096  /* boxes per frame for lg_points_in_boxes (shared-memory resident) */
+
+LG_API int lg_version(void);
+LG_API const char *lg_last_error_string(void);
+/* 0 if a CUDA device of compute capability 10.x is current, else LG_ERR_NO_DEVICE. */
+LG_API int lg_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * N x M rotated BEV overlap / IoU / 3D IoU.   out[i * ld_out + j], 64-bit offsets (the reference
+ * indexes with 32-bit int and is wrong beyond 2^31 pairs: iou3d_nms_kernel.cu:248,264).
+ *
+ *   lg_boxes_overlap_bev  <- boxes_overlap_bev_gpu   (iou3d_nms.cpp:49-68,  kernel.cu:236-249)
+ *   lg_boxes_iou_bev      <- boxes_iou_bev_gpu       (iou3d_nms.cpp:70-88,  kernel.cu:251-265)
+ *   lg_boxes_iou3d        <- boxes_iou3d_gpu, the whole Python function fused into one pass
+ *                            (iou3d_nms_utils.py:48-81: ~12 elementwise torch kernels + 6 temporaries)
+ *
+ * ws must hold lg_iou_workspace_bytes(n, m) bytes (per-box records).  Unlike the reference, `out`
+ * does not have to be zero-filled beforehand: every element is written.
+ */
+LG_API size_t lg_iou_workspace_bytes(int64_t n, int64_t m);
+LG_API int lg_boxes_overlap_bev(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, float *out, int64_t ld_out,
+                         void *ws, size_t ws_bytes, unsigned flags, void *stream);
+LG_API int lg_boxes_iou_bev(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, float *out, int64_t ld_out,
+                     void *ws, size_t ws_bytes, unsigned flags, void *stream);
+LG_API int lg_boxes_iou3d(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, float *out, int64_t ld_out,
+                   void *ws, size_t ws_bytes, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NMS, rotated (nms_gpu: iou3d_nms.cpp:90-136, kernel.cu:267-311) and axis-aligned
+ * (nms_normal_gpu: iou3d_nms.cpp:139-186, kernel.cu:314-372), batched over P independent problems.
+ *
+ * Problem p owns rows boxes[p * nmax .. p * nmax + counts[p]) (counts == NULL: all nmax rows).
+ * The i-th box of a problem IN DESCENDING SCORE ORDER is
+ *     order == NULL :  boxes[p*nmax + i]                       (caller already sorted and gathered)
+ *     order != NULL :  boxes[p*nmax + order[p*nmax + i]]       (order = the wrapper's scores.sort()[1])
+ * Box i is kept iff no kept k < i has iou(box_k, box_i) > thresh (strict, argument order (k, i)).
+ * Output, entirely on the device (no host sweep, no D2H of the mask, no hidden sync):
+ *     num_keep[p]            number of kept boxes
+ *     keep[p*nmax + 0..num)  order == NULL: positions i; order != NULL: order[...] i.e. indices into
+ *                            the caller's unsorted boxes -- exactly what the Python wrapper returns
+ *                            (iou3d_nms_utils.py:99).  Entries beyond num_keep[p] are set to -1.
+ * nmax <= LG_NMS_MAX_BOXES.
+ */
+LG_API size_t lg_nms_workspace_bytes(int num_problems, int nmax);
+LG_API int lg_nms_rotated_batched(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
+                           float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,
+                           void *stream);
+LG_API int lg_nms_normal_batched(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
+                          float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,
+                          void *stream);
+/* single problem == batched with num_problems = 1, counts = NULL */
+LG_API int lg_nms_rotated(const float *boxes, const int64_t *order, int n, float thresh, void *ws, size_t ws_bytes,
+                   int64_t *keep, int32_t *num_keep, unsigned flags, void *stream);
+LG_API int lg_nms_normal(const float *boxes, const int64_t *order, int n, float thresh, void *ws, size_t ws_bytes,
+                  int64_t *keep, int32_t *num_keep, unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * points in boxes.
+ *   lg_points_in_boxes      <- points_in_boxes_gpu (roiaware_pool3d.cpp:98-118, kernel.cu:16-36,313-359)
+ *       boxes (B, T, 7), pts (B, M, 3) -> out (B, M) int32: lowest box index containing the point,
+ *       else -1 (written by the library; the reference needs the wrapper to pre-fill -1).
+ *       MARGIN 1e-5 on x/y compared in double, z extent closed.  T <= LG_PIB_MAX_BOXES.
+ *   lg_points_in_boxes_mask <- the all-pairs form of points_in_boxes_cpu (roiaware_pool3d.cpp:121-168)
+ *       boxes (N, 7), pts (M, 3) -> out (N, M) int32 0/1 with the caller's margin (reference CPU: 1e-2).
+ */
+LG_API size_t lg_points_in_boxes_workspace_bytes(int batch, int num_boxes, int64_t num_points);
+LG_API int lg_points_in_boxes(const float *boxes, const float *pts, int32_t *out, int batch, int num_boxes, int64_t num_points,
+                       void *ws, size_t ws_bytes, unsigned flags, void *stream);
+LG_API int lg_points_in_boxes_mask(const float *boxes, int64_t n, const float *pts, int64_t m, int32_t *out, float margin,
+                            unsigned flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDARGEOM_H_ */

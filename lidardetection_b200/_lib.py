@@ -1,0 +1,82 @@
+"""ctypes binding of liblidargeom.so (include/lidargeom.h).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblidargeom.so")
+
+LG_FLAG_NONE = 0
+LG_FLAG_STRICT_FP32 = 1
+LG_NMS_MAX_BOXES = 65536
+LG_PIB_MAX_BOXES = 4096
+
+_lib = None
+
+
+class LidarGeomError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python lidardetection_b200/csrc/build.py` "
+            "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for these ops."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, sz, u32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_uint, C.c_float
+    L.lg_version.restype = C.c_int
+    L.lg_last_error_string.restype = C.c_char_p
+    L.lg_check_device.restype = C.c_int
+    L.lg_iou_workspace_bytes.restype = sz
+    L.lg_iou_workspace_bytes.argtypes = [i64, i64]
+    for name in ("lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, i64, vp, i64, vp, i64, vp, sz, u32, vp]
+    L.lg_nms_workspace_bytes.restype = sz
+    L.lg_nms_workspace_bytes.argtypes = [i32, i32]
+    for name in ("lg_nms_rotated_batched", "lg_nms_normal_batched"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp]
+    for name in ("lg_nms_rotated", "lg_nms_normal"):
+        f = getattr(L, name)
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, i32, f32, vp, sz, vp, vp, u32, vp]
+    L.lg_points_in_boxes_workspace_bytes.restype = sz
+    L.lg_points_in_boxes_workspace_bytes.argtypes = [i32, i32, i64]
+    L.lg_points_in_boxes.restype = C.c_int
+    L.lg_points_in_boxes.argtypes = [vp, vp, vp, i32, i32, i64, vp, sz, u32, vp]
+    L.lg_points_in_boxes_mask.restype = C.c_int
+    L.lg_points_in_boxes_mask.argtypes = [vp, i64, vp, i64, vp, f32, u32, vp]
+    _lib = L
+    return L
+
+
+EXPORTS = [
+    "lg_version", "lg_last_error_string", "lg_check_device",
+    "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d",
+    "lg_nms_workspace_bytes", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_rotated", "lg_nms_normal",
+    "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
+]
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().lg_last_error_string().decode("utf-8", "replace")
+        raise LidarGeomError(f"{what} failed with status {rc}: {msg}")
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (None -> NULL)"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

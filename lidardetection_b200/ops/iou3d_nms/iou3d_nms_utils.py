@@ -1,0 +1,168 @@
+"""Drop-in for pcdet/ops/iou3d_nms/iou3d_nms_utils.py (reference lines cited per function).
+
+Same names, signatures, return types and devices; the computation goes through the C ABI of
+liblidargeom.so (include/lidargeom.h) on the caller's current CUDA stream.  The *_batched functions
+are additions for callers that want to drop the reference's per-frame / per-class Python loops.
+"""
+import torch
+
+from ... import _lib
+from ...utils import common_utils
+
+
+def _cuda_f32(x, cols):
+    assert x.is_cuda, "expected a CUDA tensor"
+    assert x.dim() == 2 and x.shape[1] == cols
+    return x.contiguous().float() if x.dtype != torch.float32 else x.contiguous()
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _iou_call(fn_name, boxes_a, boxes_b, flags=_lib.LG_FLAG_NONE, out=None):
+    a, b = _cuda_f32(boxes_a, 7), _cuda_f32(boxes_b, 7)
+    n, m = a.shape[0], b.shape[0]
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=a.device)
+    if n == 0 or m == 0:
+        return out
+    L = _lib.lib()
+    with torch.cuda.device(a.device):
+        ws_bytes = L.lg_iou_workspace_bytes(n, m)
+        ws = _workspace(ws_bytes, a.device)
+        rc = getattr(L, fn_name)(_lib.ptr(a), n, _lib.ptr(b), m, _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws.numel(),
+                                 flags, _lib.stream_ptr(a.device))
+    _lib.check(rc, fn_name)
+    return out
+
+
+def boxes_bev_iou_cpu(boxes_a, boxes_b):
+    """iou3d_nms_utils.py:12-28.  CPU tensors / numpy in, same kind out.
+
+    The reference runs a single-threaded double loop on the host (iou3d_cpu.cpp:232-252).  Here the
+    matrix is computed on the B200 with the un-contracted arithmetic of that CPU build
+    (LG_FLAG_STRICT_FP32) and copied back; there is no host fallback.
+    Args:
+        boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]
+        boxes_b: (M, 7) [x, y, z, dx, dy, dz, heading]
+    Returns:
+        ans_iou: (N, M)
+    """
+    boxes_a, is_numpy = common_utils.check_numpy_to_torch(boxes_a)
+    boxes_b, is_numpy = common_utils.check_numpy_to_torch(boxes_b)
+    assert not (boxes_a.is_cuda or boxes_b.is_cuda), 'Only support CPU tensors'
+    assert boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
+    dev = torch.device('cuda', torch.cuda.current_device())
+    ans = _iou_call('lg_boxes_iou_bev', boxes_a.to(dev), boxes_b.to(dev), flags=_lib.LG_FLAG_STRICT_FP32)
+    ans_iou = ans.cpu().to(boxes_a.dtype)
+    return ans_iou.numpy() if is_numpy else ans_iou
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    """iou3d_nms_utils.py:31-45.
+    Args:
+        boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]
+        boxes_b: (M, 7) [x, y, z, dx, dy, dz, heading]
+    Returns:
+        ans_iou: (N, M)
+    """
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    return _iou_call('lg_boxes_iou_bev', boxes_a, boxes_b)
+
+
+def boxes_overlap_bev(boxes_a, boxes_b):
+    """The extension entry boxes_overlap_bev_gpu (iou3d_nms.cpp:49-68) as a function: (N, M) overlap areas."""
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    return _iou_call('lg_boxes_overlap_bev', boxes_a, boxes_b)
+
+
+def boxes_iou3d_gpu(boxes_a, boxes_b):
+    """iou3d_nms_utils.py:48-81, fused into one pass (height overlap, volumes and the quotient are
+    evaluated in the pair kernel with the same individually-rounded operations as the torch ops).
+    Args:
+        boxes_a: (N, 7) [x, y, z, dx, dy, dz, heading]
+        boxes_b: (M, 7) [x, y, z, dx, dy, dz, heading]
+    Returns:
+        ans_iou: (N, M)
+    """
+    assert boxes_a.shape[1] == boxes_b.shape[1] == 7
+    return _iou_call('lg_boxes_iou3d', boxes_a, boxes_b)
+
+
+def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE):
+    """boxes (P, N, 7) cuda f32 contiguous; order (P, N) int64 or None; counts (P,) int32 or None."""
+    P, N = boxes.shape[0], boxes.shape[1]
+    dev = boxes.device
+    keep = torch.empty((P, N), dtype=torch.int64, device=dev)
+    num = torch.zeros((P,), dtype=torch.int32, device=dev)
+    if P == 0 or N == 0:
+        return keep, num
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws_bytes = L.lg_nms_workspace_bytes(P, N)
+        ws = _workspace(ws_bytes, dev)
+        rc = getattr(L, fn_name)(_lib.ptr(boxes), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), _lib.ptr(ws),
+                                 ws.numel(), _lib.ptr(keep), _lib.ptr(num), flags, _lib.stream_ptr(dev))
+    _lib.check(rc, fn_name)
+    return keep, num
+
+
+def _nms_single(fn_name, boxes, scores, thresh, pre_maxsize):
+    assert boxes.shape[1] == 7
+    order = scores.sort(0, descending=True)[1]
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    if pre_maxsize is not None and order.shape[0] < boxes.shape[0]:
+        # reference path: gather first, map back afterwards (iou3d_nms_utils.py:93-99)
+        b = _cuda_f32(boxes[order], 7).unsqueeze(0)
+        keep, num = _nms_call(fn_name, b, None, None, thresh)
+        return order[keep[0, :int(num.item())]].contiguous(), None
+    b = _cuda_f32(boxes, 7).unsqueeze(0)
+    keep, num = _nms_call(fn_name, b, order.contiguous().unsqueeze(0), None, thresh)
+    return keep[0, :int(num.item())].contiguous(), None
+
+
+def nms_gpu(boxes, scores, thresh, pre_maxsize=None, **kwargs):
+    """iou3d_nms_utils.py:84-99.
+    :param boxes: (N, 7) [x, y, z, dx, dy, dz, heading]
+    :param scores: (N)
+    :param thresh:
+    :return: (LongTensor[cuda] of kept indices into `boxes`, descending score; None)
+    """
+    return _nms_single('lg_nms_rotated_batched', boxes, scores, thresh, pre_maxsize)
+
+
+def nms_normal_gpu(boxes, scores, thresh, **kwargs):
+    """iou3d_nms_utils.py:102-116 (axis-aligned BEV IoU, heading ignored; no pre_maxsize).
+    :param boxes: (N, 7) [x, y, z, dx, dy, dz, heading]
+    :param scores: (N)
+    :param thresh:
+    :return: (LongTensor[cuda] of kept indices into `boxes`, descending score; None)
+    """
+    return _nms_single('lg_nms_normal_batched', boxes, scores, thresh, None)
+
+
+def _nms_batched(fn_name, boxes, scores, thresh, counts):
+    assert boxes.dim() == 3 and boxes.shape[2] == 7 and scores.shape == boxes.shape[:2]
+    b = boxes.contiguous().float()
+    if counts is not None:
+        # invalid (padding) rows sort last
+        idx = torch.arange(b.shape[1], device=b.device).unsqueeze(0)
+        scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
+        counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
+    order = scores.sort(1, descending=True)[1].contiguous()
+    return _nms_call(fn_name, b, order, counts, thresh)
+
+
+def nms_gpu_batched(boxes, scores, thresh, counts=None):
+    """P independent rotated-NMS problems in three launches and no host sync.
+    :param boxes: (P, N, 7), :param scores: (P, N), :param counts: optional (P,) valid boxes per problem
+    :return: keep (P, N) int64 indices into each problem's boxes, padded with -1; num_keep (P,) int32
+    """
+    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts)
+
+
+def nms_normal_gpu_batched(boxes, scores, thresh, counts=None):
+    """Batched axis-aligned NMS; see nms_gpu_batched."""
+    return _nms_batched('lg_nms_normal_batched', boxes, scores, thresh, counts)

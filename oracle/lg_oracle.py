@@ -31,7 +31,7 @@ def lib():
         L.lgo_box_overlap_cnt.restype = C.c_int
         L.lgo_box_overlap_cnt.argtypes = [fp, fp, C.c_int]
         L.lgo_iou_normal.restype = C.c_float
-        L.lgo_iou_normal.argtypes = [fp, fp]
+        L.lgo_iou_normal.argtypes = [fp, fp, C.c_int]
         for name in ("lgo_boxes_overlap_bev", "lgo_boxes_iou_bev", "lgo_boxes_iou3d"):
             f = getattr(L, name)
             f.restype = None
@@ -95,9 +95,9 @@ def iou_bev_pair(a, b, flavor=FLAVOR_CUDA):
     return lib().lgo_iou_bev(_p(a, C.c_float), _p(b, C.c_float), flavor)
 
 
-def iou_normal_pair(a, b):
+def iou_normal_pair(a, b, flavor=FLAVOR_CUDA):
     a, b = _f32(np.reshape(a, (1, 7)), 7), _f32(np.reshape(b, (1, 7)), 7)
-    return lib().lgo_iou_normal(_p(a, C.c_float), _p(b, C.c_float))
+    return lib().lgo_iou_normal(_p(a, C.c_float), _p(b, C.c_float), flavor)
 
 
 def overlap_cnt_pair(a, b, flavor=FLAVOR_CUDA):
