@@ -1,0 +1,583 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json on N B200s of one node; prints ONE JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workloads (BASELINE.json `configs`; a "step" is one pass of the op over one resident batch of synthetic input):
+    nms_cfg2  (default) SECOND KITTI post-processing: rotated nms_gpu, 4096 boxes/frame, thresh 0.01,
+              64 frames per GPU (weak scaling: frames are independent problems, no data-path collective;
+              keep lists are all-gathered over NCCL inside the timed region when N > 1).  metric: frames/s.
+    nms_cfg5  NuScenes CBGS multi-head: 1000 boxes x 10 classes x 256 frames, thresh 0.2.  metric: problems/s.
+    iou_dense FP32-roofline microbench: 16384 x 16384 all-overlapping pairs.  metric: Gpairs/s.
+    iou_cfg1  PointPillars anchors x GT, 321,408 x 20 boxes_iou_bev.  metric: Gpairs/s.
+    iou_cfg4  Waymo-scale boxes_iou3d, 200k x 200k row-sharded (each rank owns 200k/8 = 25,000 rows
+              = 20 GB of output whatever N is: weak scaling; strong-scaling numbers follow by division).
+    pib_cfg3  PV-RCNN points_in_boxes_gpu, 16,384 points x 100 ROIs, 4096 frames per GPU.  metric: frames/s.
+
+JSON keys follow the driver's contract: value = whole-job throughput with inputs resident in HBM (CUDA
+events per step, summed, max over ranks); e2e = same metric through the public Python API from pinned
+HOST buffers with H2D and D2H inside the timed region; roofline = dominant kernel's algorithmic work /
+its own CUDA-event duration against a measured peak; cpu_baseline = the reference's CPU path on this
+box's host cores over a bounded sample.  `--impl reference` times only that CPU path (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)", 1965.0
+
+
+def fp32_peak_tflops(torch):
+    """unrolled-FFMA microbenchmark (tools/peak_fp32.cu): measured non-tensor FP32 peak of this GPU"""
+    import ctypes as C
+
+    path = os.path.join(ROOT, "tools", "libpeakfp32.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.peakfp32_launch.restype = C.c_double
+    lib.peakfp32_launch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    sink = torch.zeros(148 * 16 * 256, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    best = 0.0
+    for chains in (8, 4):
+        for _ in range(4):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            flops = lib.peakfp32_launch(C.c_void_p(sink.data_ptr()), 2048, 148 * 16, chains, st)
+            e.record()
+            e.synchronize()
+            if flops > 0:
+                best = max(best, flops / (s.elapsed_time(e) * 1e-3) / 1e12)
+    return best
+
+
+# ------------------------------------------------------------------------------------------------
+class Workload:
+    """inputs resident on the device + pinned host copies; step() = device hot path; e2e_step() = host->host"""
+    name = metric = unit = dtype = ""
+    launches_per_step = 0
+
+    def host_inputs(self):  # numpy arrays (for the CPU baseline sample)
+        raise NotImplementedError
+
+
+class NmsWorkload(Workload):
+    dtype = "f32"
+
+    def __init__(self, torch, which, rank):
+        from lidardetection_b200 import synth
+
+        self.torch = torch
+        self.which = which
+        if which == "nms_cfg2":
+            self.boxes_np, self.scores_np = synth.cfg2(64, 4096, seed=synth.SEEDS["cfg2"] + 1000 * rank)
+            self.thresh, self.name = 0.01, "SECOND KITTI post-processing: rotated nms_gpu 4096 boxes/frame, thresh 0.01, 64 frames per GPU"
+            self.metric, self.unit = "rotated NMS frames/s (4096 boxes/frame)", "frames/s"
+        else:
+            b, s = synth.cfg5(256, 10, 1000, seed=synth.SEEDS["cfg5"] + 1000 * rank)
+            self.boxes_np, self.scores_np = b.reshape(-1, 1000, 7), s.reshape(-1, 1000)
+            self.thresh, self.name = 0.2, "NuScenes CBGS multi-head NMS: 10 classes x 1000 boxes x 256 frames per GPU, thresh 0.2"
+            self.metric, self.unit = "rotated NMS problems/s (1000 boxes/problem)", "problems/s"
+        self.units = self.boxes_np.shape[0]
+        self.boxes = torch.from_numpy(self.boxes_np).cuda()
+        self.scores = torch.from_numpy(self.scores_np).cuda()
+        self.h_boxes = torch.from_numpy(self.boxes_np).pin_memory()
+        self.h_scores = torch.from_numpy(self.scores_np).pin_memory()
+        self.launches_per_step = 3  # nms_prep_kernel, nms_mask_kernel, nms_sweep_kernel (torch.sort is not ours)
+        self.h2d = self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
+        self.d2h = self.scores.numel() * 8 + self.units * 4
+
+    def step(self):
+        from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+
+        return U.nms_gpu_batched(self.boxes, self.scores, self.thresh)
+
+    def e2e_step(self):
+        from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+
+        b = self.h_boxes.cuda(non_blocking=True)
+        s = self.h_scores.cuda(non_blocking=True)
+        keep, num = U.nms_gpu_batched(b, s, self.thresh)
+        return keep.cpu(), num.cpu()
+
+    def result_for_gather(self, out):
+        return list(out)
+
+    def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
+        """dominant kernel = nms_mask_kernel (rotated IoU on the upper triangle): FP32-pipe bound.
+        algorithmic flops = pairs * (307 (1-p) + 818 p), p = fraction of pairs with non-zero overlap."""
+        torch = self.torch
+        from lidardetection_b200 import _lib
+        from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+
+        P, N = self.scores.shape
+        nz = tot = 0
+        for f in range(0, P, max(1, P // 8)):  # p from a sample of problems (exact counts, our IoU == reference bits)
+            order = self.scores[f].sort(0, descending=True)[1]
+            ov = U.boxes_overlap_bev(self.boxes[f][order], self.boxes[f][order])
+            nz += int((torch.triu(ov, 1) > 0).sum())
+            tot += N * (N - 1) // 2
+        p = nz / max(tot, 1)
+        pairs = P * N * (N - 1) // 2
+        flops = pairs * (307.0 * (1 - p) + 818.0 * p)
+        L = _lib.lib()
+        order = self.scores.sort(1, descending=True)[1].contiguous()
+        keep = torch.empty((P, N), dtype=torch.int64, device="cuda")
+        num = torch.zeros((P,), dtype=torch.int32, device="cuda")
+        ws = torch.empty(L.lg_nms_workspace_bytes(P, N), dtype=torch.uint8, device="cuda")
+        st = _lib.stream_ptr(self.boxes.device)
+
+        def phases(ph):
+            rc = L.lg_nms_batched_phases(_lib.ptr(self.boxes), _lib.ptr(order), None, P, N, self.thresh, _lib.ptr(ws), ws.numel(),
+                                         _lib.ptr(keep), _lib.ptr(num), 0, st, 0, ph)
+            _lib.check(rc, "lg_nms_batched_phases")
+
+        phases(7)
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        times = {1: [], 2: [], 4: []}
+        for _ in range(max(3, steps)):
+            for ph in (1, 2, 4):
+                if ph == 2:
+                    flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                phases(ph)
+                e.record()
+                e.synchronize()
+                times[ph].append(s.elapsed_time(e))
+        t_mask = float(np.mean(times[2])) * 1e-3
+        achieved = flops / t_mask / 1e12
+        peak = fp32_peak or 74.4
+        return {"bound": "fp32", "kernel": "nms_mask_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": "tools/peak_fp32.cu unrolled-FFMA microbenchmark measured live (MEASURED_PEAKS.json has no FP32 figure)"
+                if fp32_peak else "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz",
+                "algorithmic": {"pairs_per_launch": pairs, "nonzero_fraction": p, "flops_per_pair": 307.0 * (1 - p) + 818.0 * p,
+                                "gpairs_per_s": pairs / t_mask / 1e9},
+                "kernel_ms": {"nms_prep_kernel": float(np.mean(times[1])), "nms_mask_kernel": float(np.mean(times[2])),
+                              "nms_sweep_kernel": float(np.mean(times[4]))}}
+
+    def cpu_sample(self, pool):
+        keep, dt = pool.nms_frame(self.boxes_np[0], self.scores_np[0], self.thresh)
+        return 1.0 / dt, f"1 {'frame' if self.which == 'nms_cfg2' else 'problem'} of {self.boxes_np.shape[1]} boxes: boxes_iou_bev_cpu on the upper block-triangle in row blocks + host sweep (iou3d_nms.cpp:116-132)"
+
+
+class IouWorkload(Workload):
+    dtype = "f32"
+
+    def __init__(self, torch, which, rank, world):
+        from lidardetection_b200 import synth
+
+        self.torch, self.which = torch, which
+        self.metric, self.unit = "rotated-IoU Gpairs/s", "Gpairs/s"
+        if which == "iou_dense":
+            a, b = synth.dense_overlap(16384, 16384, seed=synth.SEEDS["dense"] + rank)
+            self.fn, self.name = "boxes_iou_bev", "dense-overlap microbench: boxes_iou_bev 16384 x 16384, all pairs overlapping, per GPU"
+        elif which == "iou_cfg1":
+            a, b = synth.cfg1(seed=synth.SEEDS["cfg1"] + rank)
+            self.fn, self.name = "boxes_iou_bev", "PointPillars KITTI anchor-target IoU: boxes_iou_bev 321,408 anchors x 20 GT, per GPU"
+        else:
+            a, b = synth.cfg4(200_000)
+            rows = 25_000  # one eighth of the 200k rows per GPU (20 GB of output), whatever N is
+            r0 = (rank % 8) * rows
+            a = a[r0:r0 + rows]
+            self.fn, self.name = "boxes_iou3d_gpu", "Waymo-scale evaluation IoU: boxes_iou3d 25,000-row shard x 200,000 boxes per GPU (200k x 200k over 8 shards)"
+        self.a_np, self.b_np = a, b
+        self.a, self.b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        self.h_a, self.h_b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+        self.pairs = a.shape[0] * b.shape[0]
+        self.units = self.pairs / 1e9
+        self.out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device="cuda")
+        self.launches_per_step = 2  # prep_kernel, iou_tile_kernel
+        self.h2d = (a.size + b.size) * 4
+        self.e2e_d2h_full = self.pairs * 4 <= (1 << 30)
+        self.d2h = self.pairs * 4 if self.e2e_d2h_full else a.shape[0] * 8
+        self.h_out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32).pin_memory() if self.e2e_d2h_full else None
+
+    def _call(self, a, b):
+        from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+
+        name = {"boxes_iou_bev": "lg_boxes_iou_bev", "boxes_iou3d_gpu": "lg_boxes_iou3d"}[self.fn]
+        return U._iou_call(name, a, b, out=self.out)  # same C-ABI call as U.<fn>, output buffer reused
+
+    def step(self):
+        return self._call(self.a, self.b)
+
+    def e2e_step(self):
+        a, b = self.h_a.cuda(non_blocking=True), self.h_b.cuda(non_blocking=True)
+        out = self._call(a, b)
+        if self.e2e_d2h_full:
+            self.h_out.copy_(out, non_blocking=False)
+            return self.h_out
+        # 20 GB result: what the evaluation consumes is the per-row best match (max, argmax), read back
+        mx, am = out.max(1)
+        return mx.cpu(), am.cpu()
+
+    def result_for_gather(self, out):
+        return []  # row blocks stay sharded (160 GB is never gathered)
+
+    def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
+        torch = self.torch
+        from lidardetection_b200 import _lib
+        from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+
+        n, m = self.a.shape[0], self.b.shape[0]
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        ts = []
+        for _ in range(max(3, steps)):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.step()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = float(np.mean(ts)) * 1e-3
+        if self.which == "iou_dense":
+            nz = float((self.out[:2048] > 0).float().mean())
+            flops = self.pairs * (307.0 * (1 - nz) + 818.0 * nz)
+            ach, peak = flops / t / 1e12, (fp32_peak or 74.4)
+            return {"bound": "fp32", "kernel": "iou_tile_kernel (+prep_kernel, <1%)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": "tools/peak_fp32.cu FFMA microbenchmark, measured live",
+                    "algorithmic": {"pairs_per_launch": self.pairs, "nonzero_fraction": nz, "flops_per_pair": 307.0 * (1 - nz) + 818.0 * nz}}
+        byts = 4.0 * n * m + 28.0 * (n + m)
+        ach = byts / t / 1e9
+        return {"bound": "hbm", "kernel": "iou_tile_kernel (+prep_kernel)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "4*N*M + 28*(N+M)"}}
+
+    def cpu_sample(self, pool):
+        rows = {"iou_dense": 2048, "iou_cfg1": 321408, "iou_cfg4": 2000}[self.which]
+        cols = {"iou_dense": 2048}.get(self.which, self.b_np.shape[0])
+        a, b = self.a_np[:rows], self.b_np[:cols]
+        dt = pool.iou_matrix(a, b)
+        return a.shape[0] * b.shape[0] / dt / 1e9, f"boxes_iou_bev_cpu on a {a.shape[0]} x {b.shape[0]} slice in row blocks (rows are independent: linear extrapolation)"
+
+
+class PibWorkload(Workload):
+    dtype = "f32"
+
+    def __init__(self, torch, rank):
+        from lidardetection_b200 import synth
+
+        self.torch = torch
+        B = 4096
+        base_p, base_r = synth.cfg3(n_frames=64, seed=synth.SEEDS["cfg3"] + rank)
+        rep = B // 64
+        self.pts_np, self.rois_np = np.tile(base_p, (rep, 1, 1)), np.tile(base_r, (rep, 1, 1))
+        self.name = "PV-RCNN KITTI points_in_boxes_gpu: 16,384 points x 100 ROIs per frame, 4096 frames per GPU (64 distinct, tiled)"
+        self.metric, self.unit = "points-in-boxes frames/s (16,384 pts x 100 ROIs)", "frames/s"
+        self.units = B
+        self.pts, self.rois = torch.from_numpy(self.pts_np).cuda(), torch.from_numpy(self.rois_np).cuda()
+        self.h_pts, self.h_rois = torch.from_numpy(self.pts_np).pin_memory(), torch.from_numpy(self.rois_np).pin_memory()
+        self.launches_per_step = 1
+        self.h2d = (self.pts_np.size + self.rois_np.size) * 4
+        self.d2h = B * 16384 * 4
+
+    def step(self):
+        from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU
+
+        return PU.points_in_boxes_gpu(self.pts, self.rois)
+
+    def e2e_step(self):
+        from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU
+
+        return PU.points_in_boxes_gpu(self.h_pts.cuda(non_blocking=True), self.h_rois.cuda(non_blocking=True)).cpu()
+
+    def result_for_gather(self, out):
+        return []
+
+    def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
+        torch = self.torch
+        ts = []
+        for _ in range(max(3, steps)):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.step()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = float(np.mean(ts)) * 1e-3
+        byts = self.units * (12.0 * 16384 + 28.0 * 100 + 4.0 * 16384)
+        ach = byts / t / 1e9
+        return {"bound": "hbm", "kernel": "pib_idx_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "B*(12*M + 28*T + 4*M)", "bytes_per_frame": 264944}}
+
+    def cpu_sample(self, pool):
+        n = 4 * pool.workers
+        dt = pool.points_mask(self.pts_np[:n], self.rois_np[:n])
+        return n / dt, f"points_in_boxes_cpu on {n} frames of 16,384 points x 100 boxes (one frame per task)"
+
+
+def make_workload(torch, which, rank, world):
+    if which in ("nms_cfg2", "nms_cfg5"):
+        return NmsWorkload(torch, which, rank)
+    if which in ("iou_dense", "iou_cfg1", "iou_cfg4"):
+        return IouWorkload(torch, which, rank, world)
+    if which == "pib_cfg3":
+        return PibWorkload(torch, rank)
+    raise SystemExit(f"unknown workload {which}")
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import CpuPool
+
+    pool = CpuPool(prefer_reference=True)
+
+
+    from lidardetection_b200 import synth
+
+    which = args.workload
+    if which in ("nms_cfg2", "nms_cfg5"):
+        if which == "nms_cfg2":
+            b, s = synth.cfg2(2, 4096)
+            thr, name, metric, unit, n = 0.01, "SECOND KITTI post-processing: rotated nms_gpu 4096 boxes/frame, thresh 0.01, 64 frames per GPU", "rotated NMS frames/s (4096 boxes/frame)", "frames/s", 4096
+        else:
+            b5, s5 = synth.cfg5(1, 10, 1000)
+            b, s = b5.reshape(-1, 1000, 7), s5.reshape(-1, 1000)
+            thr, name, metric, unit, n = 0.2, "NuScenes CBGS multi-head NMS: 10 classes x 1000 boxes x 256 frames per GPU, thresh 0.2", "rotated NMS problems/s (1000 boxes/problem)", "problems/s", 1000
+        sample = f"1 problem of {n} boxes per step: boxes_iou_bev_cpu on the upper block-triangle in row blocks + host sweep"
+
+        def one(i):
+            return pool.nms_frame(b[i % b.shape[0]], s[i % b.shape[0]], thr)[1], 1.0
+    elif which in ("iou_dense", "iou_cfg1", "iou_cfg4"):
+        metric, unit = "rotated-IoU Gpairs/s", "Gpairs/s"
+        if which == "iou_dense":
+            a, bb = synth.dense_overlap(2048, 2048)
+            name = "dense-overlap microbench: boxes_iou_bev 16384 x 16384, all pairs overlapping, per GPU"
+        elif which == "iou_cfg1":
+            a, bb = synth.cfg1()
+            name = "PointPillars KITTI anchor-target IoU: boxes_iou_bev 321,408 anchors x 20 GT, per GPU"
+        else:
+            a, bb = synth.cfg4(200_000)
+            a = a[:2000]
+            name = "Waymo-scale evaluation IoU: boxes_iou3d 25,000-row shard x 200,000 boxes per GPU (200k x 200k over 8 shards)"
+        sample = f"boxes_iou_bev_cpu {a.shape[0]} x {bb.shape[0]} per step in row blocks"
+
+        def one(i):
+            return pool.iou_matrix(a, bb), a.shape[0] * bb.shape[0] / 1e9
+    else:
+        p, r = synth.cfg3(n_frames=4 * pool.workers)
+        metric, unit = "points-in-boxes frames/s (16,384 pts x 100 ROIs)", "frames/s"
+        name = "PV-RCNN KITTI points_in_boxes_gpu: 16,384 points x 100 ROIs per frame, 4096 frames per GPU (64 distinct, tiled)"
+        sample = f"points_in_boxes_cpu on {p.shape[0]} frames per step"
+
+        def one(i):
+            return pool.points_mask(p, r), float(p.shape[0])
+    for i in range(args.warmup):
+        one(i)
+    tot_t = tot_u = 0.0
+    for i in range(args.steps):
+        dt, u = one(i)
+        tot_t += dt
+        tot_u += u
+    pool.close()
+    val = tot_u / tot_t
+    line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded, SURVEY.md 8d shapes)", "config": {"workload": name},
+            "cpu_baseline": {"value": val, "unit": unit, "cores": pool.workers, "kind": pool.kind, "sample": sample},
+            "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="nms_cfg2", choices=["nms_cfg2", "nms_cfg5", "iou_dense", "iou_cfg1", "iou_cfg4", "pib_cfg3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    # CPU baseline first: its worker pool forks, which must happen before CUDA is initialised
+    cpu_pool = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_baseline import CpuPool
+
+        cpu_pool = CpuPool(prefer_reference=True)
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from lidardetection_b200 import _lib
+
+    _lib.check(_lib.lib().lg_check_device(), "lg_check_device")
+    wl = make_workload(torch, args.workload, rank, world)
+
+    cpu_baseline = None
+    if cpu_pool is not None:
+        v, sample = wl.cpu_sample(cpu_pool)
+        cpu_baseline = {"value": v, "unit": wl.unit, "cores": cpu_pool.workers, "kind": cpu_pool.kind, "sample": sample}
+        cpu_pool.close()
+        log("cpu_baseline", cpu_baseline)
+
+    hbm_peak, hbm_src, _ = measured_peaks()
+    fp32_peak = fp32_peak_tflops(torch)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather(out):
+        if world > 1:
+            for t in wl.result_for_gather(out):
+                buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(buf, t.contiguous())
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        gather(wl.step())
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations (outside the events)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        gather(wl.step())
+        e.record()
+        e.synchronize()
+        dev_ms += s.elapsed_time(e)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    # keep the GPU under load a little longer if the region was too short for a clock sample
+    t_end = time.perf_counter() + max(0.0, 0.6 - t_wall)
+    while time.perf_counter() < t_end:
+        wl.step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end through the public API from pinned host memory --------------------------------
+    for _ in range(2):
+        wl.e2e_step()
+    barrier()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gather_out = wl.e2e_step()
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+        del gather_out
+    barrier()
+
+    tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(tt[0]), float(tt[1])
+
+    roofline = wl.roofline(args.steps, hbm_peak, hbm_src, fp32_peak) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    total_units = wl.units * world
+    line = {
+        "metric": wl.metric, "value": total_units * args.steps / (dev_ms * 1e-3), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": wl.dtype, "data": "synthetic (seeded, SURVEY.md 8d shapes; no datasets offline)",
+        "config": {"workload": wl.name, "units_per_step_per_gpu": wl.units, "l2": "256 MB L2 flush between timed iterations",
+                   "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
+                   "multi_gpu": "independent problems per rank; results all-gathered over NCCL inside the timed region" if world > 1 else "single GPU"},
+        "e2e": {"value": total_units * args.steps / e2e_s, "unit": wl.unit, "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h)},
+        "gpu_launches": wl.launches_per_step * args.steps,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "fp32_peak_tflops_measured": fp32_peak, "hbm_peak_gbs": hbm_peak,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

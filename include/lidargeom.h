@@ -106,6 +106,14 @@ LG_API int lg_nms_rotated_batched(const float *boxes, const int64_t *order, cons
 LG_API int lg_nms_normal_batched(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
                           float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,
                           void *stream);
+/* The same pipeline one phase at a time, for profiling (bench.py times the mask kernel alone for its
+ * roofline line): phases is a bit-or of LG_NMS_PHASE_*; ws carries the records and the mask between calls. */
+#define LG_NMS_PHASE_RECORDS 1u
+#define LG_NMS_PHASE_MASK 2u
+#define LG_NMS_PHASE_SWEEP 4u
+LG_API int lg_nms_batched_phases(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
+                                 float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,
+                                 void *stream, int normal, unsigned phases);
 /* single problem == batched with num_problems = 1, counts = NULL */
 LG_API int lg_nms_rotated(const float *boxes, const int64_t *order, int n, float thresh, void *ws, size_t ws_bytes,
                    int64_t *keep, int32_t *num_keep, unsigned flags, void *stream);

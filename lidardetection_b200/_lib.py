@@ -43,6 +43,8 @@ def lib():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp]
+    L.lg_nms_batched_phases.restype = C.c_int
+    L.lg_nms_batched_phases.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp, i32, u32]
     for name in ("lg_nms_rotated", "lg_nms_normal"):
         f = getattr(L, name)
         f.restype = C.c_int
@@ -60,7 +62,7 @@ def lib():
 EXPORTS = [
     "lg_version", "lg_last_error_string", "lg_check_device",
     "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d",
-    "lg_nms_workspace_bytes", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_rotated", "lg_nms_normal",
+    "lg_nms_workspace_bytes", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
 ]
 

@@ -256,8 +256,11 @@ __global__ void __launch_bounds__(32)
     for (int i = nk + lane; i < nmax; i += 32) keep[base + i] = -1;
 }
 
+enum { PHASE_RECORDS = 1, PHASE_MASK = 2, PHASE_SWEEP = 4, PHASE_ALL = 7 };
+
 static int nms_entry(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax, float thresh, void* ws,
-                     size_t ws_bytes, int64_t* keep, int32_t* num_keep, unsigned flags, void* stream, bool normal) {
+                     size_t ws_bytes, int64_t* keep, int32_t* num_keep, unsigned flags, void* stream, bool normal,
+                     unsigned phases = PHASE_ALL) {
     if (P < 0 || nmax < 0) {
         set_error("negative size num_problems=%d nmax=%d", P, nmax);
         return LG_ERR_INVALID_ARG;
@@ -297,10 +300,13 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
     const bool strict = (flags & LG_FLAG_STRICT_FP32) != 0;
     int rc;
     if (!normal) {
-        dim3 pg((nmax + 255) / 256, P);
-        if (strict) nms_prep_kernel<0><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
-        else nms_prep_kernel<1><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
-        if ((rc = check_launch("nms_prep_kernel"))) return rc;
+        if (phases & PHASE_RECORDS) {
+            dim3 pg((nmax + 255) / 256, P);
+            if (strict) nms_prep_kernel<0><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
+            else nms_prep_kernel<1><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
+            if ((rc = check_launch("nms_prep_kernel"))) return rc;
+        }
+        if (!(phases & PHASE_MASK)) goto sweep;
         dim3 mg(tri, P);
         if (strict) {
             if ((rc = set_smem(nms_mask_kernel<0>, NmsSmem::total))) return rc;
@@ -310,12 +316,14 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
             nms_mask_kernel<1><<<mg, NMS_THREADS, NmsSmem::total, st>>>(rec, counts, nmax, cbk, thresh, mask);
         }
         if ((rc = check_launch("nms_mask_kernel"))) return rc;
-    } else {
+    } else if (phases & PHASE_MASK) {
         dim3 mg(tri, P);
         if (strict) nms_normal_mask_kernel<0><<<mg, NMS_TILE, 0, st>>>(boxes, order, counts, nmax, cbk, thresh, mask);
         else nms_normal_mask_kernel<1><<<mg, NMS_TILE, 0, st>>>(boxes, order, counts, nmax, cbk, thresh, mask);
         if ((rc = check_launch("nms_normal_mask_kernel"))) return rc;
     }
+sweep:
+    if (!(phases & PHASE_SWEEP)) return LG_OK;
     nms_sweep_kernel<<<P, 32, (size_t)cbk * sizeof(unsigned long long), st>>>(mask, order, counts, nmax, cbk, keep, num_keep);
     return check_launch("nms_sweep_kernel");
 }
@@ -338,6 +346,13 @@ extern "C" int lg_nms_normal_batched(const float* boxes, const int64_t* order, c
                                      float thresh, void* ws, size_t ws_bytes, int64_t* keep, int32_t* num_keep,
                                      unsigned flags, void* stream) {
     return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, num_keep, flags, stream, true);
+}
+
+extern "C" int lg_nms_batched_phases(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax,
+                                     float thresh, void* ws, size_t ws_bytes, int64_t* keep, int32_t* num_keep,
+                                     unsigned flags, void* stream, int normal, unsigned phases) {
+    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, num_keep, flags, stream, normal != 0,
+                         phases & lg::PHASE_ALL);
 }
 
 extern "C" int lg_nms_rotated(const float* boxes, const int64_t* order, int n, float thresh, void* ws, size_t ws_bytes,

@@ -1,0 +1,96 @@
+"""One-process-per-GPU drivers for the parts of the hot path that shard naturally.
+
+    IoU matrices        rows of boxes_a split into contiguous blocks, boxes_b replicated; no data-path
+                        collective.  The (N, M) result is all-gathered only on request -- at 200k x 200k
+                        it is 160 GB and stays row-sharded.
+    batched NMS         problems (frames x classes) dealt in contiguous blocks; keep lists gathered.
+    points in boxes     frames dealt in contiguous blocks; (B, M) indices gathered.
+
+The reference has no multi-GPU code on this path (its only distributed code is DDP and a pickle-file
+merge, pcdet/utils/common_utils.py:146-227).  Collectives go through torch.distributed (NCCL over
+NVLink on the B200 box, gloo in the CPU unit tests); the `compute` callables default to the CUDA ops
+and are injectable so that the partition / gather logic is testable without a GPU.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world_size):
+    """Contiguous block [start, stop) of n items for `rank`: blocks of ceil(n / world) (last ones short/empty)."""
+    per = (n + world_size - 1) // world_size if world_size > 0 else n
+    start = min(rank * per, n)
+    return start, min(start + per, n)
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _gather_rows(local, n_total, group):
+    """all-gather row blocks produced with shard_range (equal-size padded blocks) -> (n_total, ...)."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    return out[:n_total]
+
+
+def boxes_iou_sharded(boxes_a, boxes_b, kind="iou3d", gather=False, group=None, compute=None):
+    """Row-sharded N x M IoU.  Every rank passes the SAME boxes_a / boxes_b (replicated inputs, KBs-MBs).
+
+    Returns (block, (start, stop)) with block = rows [start, stop) of the matrix computed by this rank,
+    or, with gather=True, the full (N, M) matrix on every rank.
+    kind: 'iou3d' | 'iou_bev' | 'overlap_bev'.
+    """
+    if compute is None:
+        from .ops.iou3d_nms import iou3d_nms_utils as U
+
+        compute = {"iou3d": U.boxes_iou3d_gpu, "iou_bev": U.boxes_iou_bev, "overlap_bev": U.boxes_overlap_bev}[kind]
+    rank, world = _world(group)
+    n = boxes_a.shape[0]
+    start, stop = shard_range(n, rank, world)
+    block = compute(boxes_a[start:stop], boxes_b)
+    if gather:
+        return _gather_rows(block, n, group)
+    return block, (start, stop)
+
+
+def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather=True, group=None, compute=None):
+    """Frame-sharded batched NMS.  boxes (P, N, 7), scores (P, N) replicated on every rank.
+
+    Returns keep (P, N) int64 (-1 padded) and num_keep (P,) int32 for all problems (gather=True), or this
+    rank's block plus its (start, stop).
+    """
+    if compute is None:
+        from .ops.iou3d_nms import iou3d_nms_utils as U
+
+        compute = U.nms_normal_gpu_batched if normal else U.nms_gpu_batched
+    rank, world = _world(group)
+    P = boxes.shape[0]
+    start, stop = shard_range(P, rank, world)
+    c = None if counts is None else counts[start:stop]
+    keep, num = compute(boxes[start:stop], scores[start:stop], thresh, c)
+    if gather:
+        return _gather_rows(keep, P, group), _gather_rows(num, P, group)
+    return (keep, num), (start, stop)
+
+
+def points_in_boxes_sharded(points, boxes, gather=True, group=None, compute=None):
+    """Frame-sharded points_in_boxes_gpu.  points (B, M, 3), boxes (B, T, 7) replicated on every rank."""
+    if compute is None:
+        from .ops.roiaware_pool3d import roiaware_pool3d_utils as PU
+
+        compute = PU.points_in_boxes_gpu
+    rank, world = _world(group)
+    B = points.shape[0]
+    start, stop = shard_range(B, rank, world)
+    idx = compute(points[start:stop], boxes[start:stop])
+    if gather:
+        return _gather_rows(idx, B, group)
+    return idx, (start, stop)

@@ -1,0 +1,274 @@
+"""GPU parity tests proper: liblidargeom (through the Python drop-in modules -> ctypes -> C ABI) against
+  (1) the oracle restatement (oracle/lg_oracle.c, CUDA flavor) on the same seeded inputs,
+  (2) the committed golden vectors of the reference CUDA kernels (tests/golden/golden_gpu.npz),
+  (3) when oracle/_ref travelled with the snapshot, the reference CUDA kernels run live on this GPU.
+Tolerances (north_star): IoU <= 1e-5 absolute; NMS keep indices and point-in-box results bit-exact, except
+documented ties where the deciding comparison is within 1e-6 of its threshold (none occur on these inputs:
+the tests assert exact equality and would report the deciding value otherwise).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lidardetection_b200 import _lib, synth
+from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU
+from oracle import lg_oracle as O
+from oracle import ref_loader as R
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+IOU_ATOL = 1e-5
+IOU_SETS = ["kat", "kat_t", "kat_sq", "car35", "ped70", "mix150", "dense", "cfg3iou", "cfg1sub"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev())
+
+
+def bits(x):
+    return np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+
+
+def assert_iou_close(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    assert d.max() <= IOU_ATOL, f"{what}: max |diff| {d.max():.3g} > {IOU_ATOL}"
+    # exact zeros must stay exact zeros (database_sampler.py:220 tests == 0)
+    assert np.array_equal(got == 0, want == 0), f"{what}: zero pattern differs"
+    return int((bits(got) != bits(want)).sum())
+
+
+def explain_nms_mismatch(boxes_sorted, got_pos, want_pos, thresh, normal):
+    """documented-tie rule: find the first differing decision and recompute its deciding IoU with the oracle"""
+    for k in range(min(len(got_pos), len(want_pos))):
+        if got_pos[k] != want_pos[k]:
+            j = min(got_pos[k], want_pos[k])
+            kept = want_pos[:k]
+            vals = [O.iou_normal_pair(boxes_sorted[i], boxes_sorted[j]) if normal else O.iou_bev_pair(boxes_sorted[i], boxes_sorted[j])
+                    for i in kept]
+            near = [v for v in vals if abs(v - thresh) < 1e-6]
+            return f"first difference at output {k} (box {j}); deciding IoUs within 1e-6 of {thresh}: {near}"
+    return "length differs"
+
+
+@pytest.fixture(scope="module")
+def ggpu():
+    p = os.path.join(HERE, "golden", "golden_gpu.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden_gpu.npz not generated yet")
+    return np.load(p)
+
+
+def test_library_sees_a_blackwell_device():
+    assert _lib.lib().lg_check_device() == 0, _lib.lib().lg_last_error_string()
+
+
+# ------------------------------------------------------------------------------------------ IoU
+@pytest.mark.parametrize("seed,centre,pri,n,m", [
+    (1, (35, 17.5), synth.KITTI_PRIORS[:1], 300, 257),
+    (2, (70, 35), synth.KITTI_PRIORS[1:2], 300, 129),   # pedestrians at range: the FP32-conditioning stress case
+    (3, (150, 75), synth.KITTI_PRIORS, 200, 300),
+    (4, (-75, 75), synth.WAYMO_PRIORS, 130, 33),
+    (5, (0.2, -0.1), synth.KITTI_PRIORS, 64, 20),
+])
+def test_iou_family_vs_oracle(seed, centre, pri, n, m):
+    a, b = synth.clustered_pairs(n, m, seed, centre, pri)
+    ta, tb = cu(a), cu(b)
+    nb = assert_iou_close(U.boxes_iou_bev(ta, tb).cpu().numpy(), O.boxes_iou_bev(a, b, O.FLAVOR_CUDA), "iou_bev")
+    no = assert_iou_close(U.boxes_overlap_bev(ta, tb).cpu().numpy(), O.boxes_overlap_bev(a, b, O.FLAVOR_CUDA), "overlap_bev")
+    n3 = assert_iou_close(U.boxes_iou3d_gpu(ta, tb).cpu().numpy(), O.boxes_iou3d(a, b, O.FLAVOR_CUDA), "iou3d")
+    # the arithmetic contract is mirrored exactly; only vertex-order ties may move last bits
+    assert max(nb, no, n3) <= max(1, n * m // 2000)
+    # strict (CPU-build) arithmetic vs the CPU flavor: differs only through libdevice vs glibc trig
+    strict = U._iou_call("lg_boxes_iou_bev", ta, tb, flags=_lib.LG_FLAG_STRICT_FP32).cpu().numpy()
+    d = np.abs(strict - O.boxes_iou_bev(a, b, O.FLAVOR_CPU))
+    assert d.max() <= 5e-5  # reference CPU vs reference GPU disagree at this level themselves
+
+
+@pytest.mark.parametrize("name", IOU_SETS)
+def test_iou_family_vs_golden_reference_cuda(ggpu, name):
+    ta, tb = cu(ggpu[f"iou_{name}_a"]), cu(ggpu[f"iou_{name}_b"])
+    for key, fn in (("bev", U.boxes_iou_bev), ("overlap", U.boxes_overlap_bev), ("iou3d", U.boxes_iou3d_gpu)):
+        assert_iou_close(fn(ta, tb).cpu().numpy(), ggpu[f"iou_{name}_{key}"], f"{name}/{key}")
+
+
+def test_iou_shapes_strides_and_empties():
+    a, b = synth.clustered_pairs(70, 45, 7)
+    ta, tb = cu(a), cu(b)
+    want = O.boxes_iou_bev(a, b, O.FLAVOR_CUDA)
+    # callers pass boxes[:, 0:7] slices of wider tensors (non-contiguous)
+    wide_a = torch.cat([ta, torch.randn(70, 3, device=dev())], 1)
+    wide_b = torch.cat([tb, torch.randn(45, 2, device=dev())], 1)
+    assert_iou_close(U.boxes_iou_bev(wide_a[:, 0:7], wide_b[:, 0:7]).cpu().numpy(), want, "sliced")
+    for n, m in ((0, 5), (5, 0), (0, 0)):
+        out = U.boxes_iou3d_gpu(ta[:n], tb[:m])
+        assert out.shape == (n, m) and out.dtype == torch.float32 and out.is_cuda
+    # every tile-width variant and ragged edges: m = 1, 31, 32, 33, 64, 65, 127, 128, 129
+    big_a, big_b = synth.clustered_pairs(140, 129, 8)
+    wantb = O.boxes_iou_bev(big_a, big_b, O.FLAVOR_CUDA)
+    for m in (1, 31, 32, 33, 64, 65, 127, 128, 129):
+        got = U.boxes_iou_bev(cu(big_a), cu(big_b[:m])).cpu().numpy()
+        assert_iou_close(got, wantb[:, :m], f"m={m}")
+    # unaligned output pitch goes through the scalar store path
+    out = torch.empty((140, 131), device=dev())[:, :129]
+    got = U._iou_call("lg_boxes_iou_bev", cu(big_a), cu(big_b), out=out).cpu().numpy()
+    assert_iou_close(got, wantb, "pitched")
+
+
+def test_iou_cfg1_shape_sampled_against_oracle():
+    """PointPillars anchors x GT at full size (321,408 x 20); the oracle checks a row sample."""
+    a, gt = synth.cfg1()
+    got = U.boxes_iou_bev(cu(a), cu(gt)).cpu().numpy()
+    assert got.shape == (321408, 20)
+    rows = np.unique(np.concatenate([np.arange(0, 321408, 53), np.nonzero(got.max(1) > 0)[0][:4000]]))
+    assert_iou_close(got[rows], O.boxes_iou_bev(a[rows], gt, O.FLAVOR_CUDA), "cfg1 sample")
+    frac = (got > 0).mean()
+    assert 0.0005 < frac < 0.02
+
+
+# ------------------------------------------------------------------------------------------ NMS
+@pytest.mark.parametrize("n,thresh", [(1, 0.1), (63, 0.1), (64, 0.3), (65, 0.01), (300, 0.7), (1024, 0.01), (1000, 0.2), (4096, 0.01)])
+@pytest.mark.parametrize("normal", [False, True])
+def test_nms_vs_oracle(n, thresh, normal):
+    boxes, scores = synth.nms_frames(1, n, seed=100 + n)
+    tb, ts = cu(boxes[0]), cu(scores[0])
+    fn = U.nms_normal_gpu if normal else U.nms_gpu
+    keep, none = fn(tb, ts, thresh, NMS_TYPE="nms_gpu", NMS_THRESH=thresh)  # the whole NMS config is splatted in
+    assert none is None and keep.dtype == torch.int64 and keep.is_cuda and keep.is_contiguous()
+    order = ts.sort(0, descending=True)[1].cpu().numpy()
+    want = O.nms(boxes[0], scores[0], thresh, normal=normal, flavor=O.FLAVOR_CUDA, order=order)
+    got = keep.cpu().numpy()
+    if not np.array_equal(got, want):
+        inv = np.empty(n, np.int64)
+        inv[order] = np.arange(n)
+        pytest.fail(explain_nms_mismatch(boxes[0][order], inv[got], inv[want], thresh, normal))
+
+
+def test_nms_vs_golden_reference_cuda(ggpu):
+    boxes, scores = ggpu["nms_boxes"], ggpu["nms_scores"]
+    for f in range(boxes.shape[0]):
+        tb, ts = cu(boxes[f]), cu(scores[f])
+        assert np.array_equal(ts.sort(0, descending=True)[1].cpu().numpy(), ggpu[f"nms_order_{f}"])
+        for thr in (0.01, 0.1, 0.7):
+            assert np.array_equal(U.nms_gpu(tb, ts, thr)[0].cpu().numpy(), ggpu[f"nms_keep_{f}_{thr}_0"]), (f, thr)
+            assert np.array_equal(U.nms_normal_gpu(tb, ts, thr)[0].cpu().numpy(), ggpu[f"nms_keep_{f}_{thr}_1"]), (f, thr)
+
+
+def test_nms_pre_maxsize_empty_and_duplicates():
+    boxes, scores = synth.nms_frames(1, 500, seed=9)
+    tb, ts = cu(boxes[0]), cu(scores[0])
+    order = ts.sort(0, descending=True)[1].cpu().numpy()
+    got = U.nms_gpu(tb, ts, 0.1, pre_maxsize=200)[0].cpu().numpy()
+    assert np.array_equal(got, O.nms(boxes[0], scores[0], 0.1, pre_maxsize=200, order=order))
+    k, _ = U.nms_gpu(tb[:0], ts[:0], 0.1)
+    assert k.shape == (0,) and k.dtype == torch.int64
+    one = np.array([[1, 2, 0, 4, 2, 1, 0.3]], np.float32)
+    dup = cu(np.repeat(one, 130, 0))
+    s = cu(np.linspace(1, 0.1, 130).astype(np.float32))
+    assert U.nms_gpu(dup, s, 0.5)[0].cpu().tolist() == [0]
+    assert U.nms_gpu(dup, s, 1.0)[0].cpu().tolist() == list(range(130))  # strict >
+    assert U.nms_normal_gpu(dup, s, 0.5)[0].cpu().tolist() == [0]
+
+
+def test_nms_batched_with_ragged_counts():
+    boxes, scores = synth.nms_frames(6, 700, seed=12)
+    counts = torch.tensor([700, 1, 0, 64, 65, 333], dtype=torch.int32)
+    tb, ts = cu(boxes), cu(scores)
+    for fn, single, normal in ((U.nms_gpu_batched, U.nms_gpu, False), (U.nms_normal_gpu_batched, U.nms_normal_gpu, True)):
+        keep, num = fn(tb, ts, 0.1, counts)
+        assert keep.shape == (6, 700) and num.dtype == torch.int32
+        for p in range(6):
+            c = int(counts[p])
+            want = single(tb[p, :c], ts[p, :c], 0.1)[0]
+            assert int(num[p]) == want.numel()
+            assert torch.equal(keep[p, : want.numel()], want)
+            assert bool((keep[p, want.numel():] == -1).all())
+            order = ts[p, :c].sort(0, descending=True)[1].cpu().numpy()
+            assert np.array_equal(want.cpu().numpy(), O.nms(boxes[p, :c], scores[p, :c], 0.1, normal=normal, order=order))
+
+
+# ------------------------------------------------------------------------------------------ points
+def test_points_in_boxes_vs_oracle_and_golden(ggpu):
+    pts, rois = synth.cfg3(n_frames=3, n_points=16384, n_rois=100, seed=5)
+    got = PU.points_in_boxes_gpu(cu(pts), cu(rois))
+    assert got.dtype == torch.int32 and got.shape == (3, 16384)
+    want = O.points_in_boxes_idx(pts, rois, O.FLAVOR_CUDA)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert 0.2 < (want >= 0).mean() < 0.5
+    g = PU.points_in_boxes_gpu(cu(ggpu["pib_pts"]), cu(ggpu["pib_boxes"])).cpu().numpy()
+    assert np.array_equal(g, ggpu["pib_idx"])
+
+
+def test_points_edge_cases():
+    # ragged sizes, padded all-zero boxes (dataset.py:172-177 pads GT with zeros; they are NOT skipped)
+    pts = np.zeros((2, 1001, 3), np.float32)
+    pts[:, 1:] = np.random.default_rng(3).uniform(-5, 5, (2, 1000, 3))
+    boxes = np.zeros((2, 7, 7), np.float32)
+    boxes[:, :3] = synth.gt_boxes(6, 2, x_range=(-4, 4), y_range=(-4, 4), z=0.0).reshape(2, 3, 7)
+    got = PU.points_in_boxes_gpu(cu(pts), cu(boxes)).cpu().numpy()
+    want = O.points_in_boxes_idx(pts, boxes, O.FLAVOR_CUDA)
+    assert np.array_equal(got, want)
+    assert got[0, 0] >= 0  # the origin matches a zero-size padded box (or an earlier real one)
+    assert PU.points_in_boxes_gpu(cu(pts[:, :0]), cu(boxes)).shape == (2, 0)
+    none = PU.points_in_boxes_gpu(cu(pts), cu(boxes[:, :0])).cpu().numpy()
+    assert (none == -1).all()
+    # x/y open with 1e-5 margin evaluated in double, z closed
+    box = np.array([[[0, 0, 0, 4, 2, 1.5, 0.0], [0, 0, 0, 4, 2, 1.5, 0.0]]], np.float32)
+    p = np.array([[[0, 0, 0], [2.000005, 0, 0], [2.00002, 0, 0], [0, 0, 0.75], [0, 0, 0.7500001], [2.005, 0, 0]]], np.float32)
+    assert PU.points_in_boxes_gpu(cu(p), cu(box)).cpu().tolist() == [[0, 0, -1, 0, -1, -1]]
+
+
+def test_cpu_named_functions_run_on_the_gpu_with_cpu_semantics():
+    g = np.load(os.path.join(HERE, "golden", "golden_cpu.npz"))
+    for f in range(2):
+        m = PU.points_in_boxes_cpu(g["pib_pts"][f], g["pib_boxes"][f])
+        assert isinstance(m, np.ndarray) and m.dtype == np.int32
+        assert np.array_equal(m, g["pib_ref_mask"][f])  # bit-exact vs the reference's own CPU output
+    t = PU.points_in_boxes_cpu(torch.from_numpy(g["pib_pts"][0]), torch.from_numpy(g["pib_boxes"][0]))
+    assert isinstance(t, torch.Tensor) and not t.is_cuda
+    for name in ("kat_sq", "car35", "cfg3iou"):
+        a, b, ref = g[f"iou_{name}_a"], g[f"iou_{name}_b"], g[f"iou_{name}_ref"]
+        got = U.boxes_bev_iou_cpu(a, b)
+        assert isinstance(got, np.ndarray) and got.shape == ref.shape
+        assert np.abs(got - ref).max() <= IOU_ATOL
+        assert np.array_equal(got == 0, ref == 0)
+
+
+# ------------------------------------------------------------------------------------------ tier A, live
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref (compiled reference) did not travel with this snapshot")
+def test_live_against_reference_cuda_kernels():
+    ref, roi = R.iou3d_nms_cuda(), R.roiaware_pool3d_cuda()
+    tot = bad = 0
+    for seed, centre, pri in [(21, (35, 17.5), synth.KITTI_PRIORS), (22, (70, 35), synth.KITTI_PRIORS[1:2]),
+                              (23, (150, 75), synth.KITTI_PRIORS), (24, (-60, 40), synth.WAYMO_PRIORS)]:
+        a, b = synth.clustered_pairs(1000, 1000, seed, centre, pri)
+        ta, tb = cu(a), cu(b)
+        want = torch.zeros((1000, 1000), device=dev())
+        ref.boxes_iou_bev_gpu(ta, tb, want)
+        got = U.boxes_iou_bev(ta, tb)
+        bad += assert_iou_close(got.cpu().numpy(), want.cpu().numpy(), "tier A iou_bev")
+        tot += 1000 * 1000
+    assert bad <= tot // 2000, f"{bad} of {tot} pairs not bit-identical to the reference CUDA kernel"
+    boxes, scores = synth.cfg2(n_frames=3, n_boxes=4096)
+    for f in range(3):
+        tb, ts = cu(boxes[f]), cu(scores[f])
+        order = ts.sort(0, descending=True)[1]
+        b = tb[order].contiguous()
+        for thr, normal in ((0.01, False), (0.5, False), (0.01, True)):
+            keep = torch.LongTensor(b.size(0))
+            n = (ref.nms_normal_gpu if normal else ref.nms_gpu)(b, keep, thr)
+            want = order[keep[:n].to(dev())]
+            got = (U.nms_normal_gpu if normal else U.nms_gpu)(tb, ts, thr)[0]
+            assert torch.equal(got, want), (f, thr, normal)
+    pts, rois = synth.cfg3(n_frames=4, seed=9)
+    want = torch.full((4, 16384), -1, dtype=torch.int32, device=dev())
+    roi.points_in_boxes_gpu(cu(rois), cu(pts), want)
+    assert torch.equal(PU.points_in_boxes_gpu(cu(pts), cu(rois)), want)

@@ -1,0 +1,81 @@
+"""CPU-only, world_size 2 over gloo: the row / frame partition + gather logic of lidardetection_b200.sharded,
+with the oracle standing in for the CUDA ops (the partitioning code is device-agnostic)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lidardetection_b200 import sharded, synth
+from oracle import lg_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _iou_cpu(a, b):
+    return torch.from_numpy(O.boxes_iou3d(a.numpy(), b.numpy(), O.FLAVOR_CUDA))
+
+
+def _nms_cpu(boxes, scores, thresh, counts):
+    P, N = scores.shape
+    keep = torch.full((P, N), -1, dtype=torch.int64)
+    num = torch.zeros((P,), dtype=torch.int32)
+    for p in range(P):
+        k = O.nms(boxes[p].numpy(), scores[p].numpy(), thresh)
+        keep[p, : len(k)] = torch.from_numpy(k)
+        num[p] = len(k)
+    return keep, num
+
+
+def _pib_cpu(points, boxes):
+    return torch.from_numpy(O.points_in_boxes_idx(points.numpy(), boxes.numpy(), O.FLAVOR_CUDA))
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = synth.clustered_pairs(37, 11, 3)
+        ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+        full = sharded.boxes_iou_sharded(ta, tb, gather=True, compute=_iou_cpu)
+        block, (s, e) = sharded.boxes_iou_sharded(ta, tb, gather=False, compute=_iou_cpu)
+        ok = torch.equal(full, _iou_cpu(ta, tb)) and torch.equal(block, full[s:e]) and (s, e) == sharded.shard_range(37, rank, world)
+        boxes, scores = synth.nms_frames(5, 60, seed=8)
+        keep, num = sharded.nms_batched_sharded(torch.from_numpy(boxes), torch.from_numpy(scores), 0.1, compute=_nms_cpu)
+        k1, n1 = _nms_cpu(torch.from_numpy(boxes), torch.from_numpy(scores), 0.1, None)
+        ok = ok and torch.equal(keep, k1) and torch.equal(num, n1)
+        pts, rois = synth.cfg3(n_frames=3, n_points=200, n_rois=12, seed=4)
+        idx = sharded.points_in_boxes_sharded(torch.from_numpy(pts), torch.from_numpy(rois), compute=_pib_cpu)
+        ok = ok and torch.equal(idx, _pib_cpu(torch.from_numpy(pts), torch.from_numpy(rois)))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_world_size_2_partition_and_gather():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(170)
+        assert p.exitcode == 0
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_single_process_path_needs_no_process_group():
+    a, b = synth.clustered_pairs(9, 4, 2)
+    full = sharded.boxes_iou_sharded(torch.from_numpy(a), torch.from_numpy(b), gather=True, compute=_iou_cpu)
+    assert np.array_equal(full.numpy(), O.boxes_iou3d(a, b, O.FLAVOR_CUDA))
