@@ -109,7 +109,7 @@ def test_cuda_flavor_bit_exact_vs_reference_cuda_kernels(ggpu, name):
         # whose polygon has coincident vertices.  The hand-made kat_sq set is built from coincident boxes
         # (identical, swapped-extent, 1e-4 rad apart: 10-12 vertices), so ties are the rule there; the seeded
         # random sets must be bit-identical up to a stray tie.
-        allowed = ref.size // 20 if name.startswith("kat") else max(1, ref.size // 2000)
+        allowed = max(2, ref.size // 20) if name.startswith("kat") else max(1, ref.size // 2000)
         assert nbad <= allowed, f"{key}: {nbad} of {ref.size} differ"
         assert np.abs(got - ref).max() <= 1e-6
 
