@@ -7,23 +7,21 @@
 // Design (B200: 148 SMs, 228 KB smem/SM, HBM3e):
 //   1. prep kernel: one thread per box builds an 80-byte record (lg_geom.cuh) -- all trigonometry,
 //      corner rotation and margin arithmetic happens N+M times instead of N*M times.
-//   2. tile kernel: a CTA owns a TA x TB tile (4096 pairs) of the output.
+//   2. strip kernel (lg_strip.cuh): a CTA owns 64 rows x up to 512 columns (flat variant for M <= 64:
+//      256 rows x M columns, linear pair index so that stores stay coalesced for 20-column matrices).
 //        cull   -- lanes run along columns; |ca - cb|^2 > (ra + rb)^2 proves the reference would
-//                  return exactly +0.0; survivors are compacted (ballot + popc) into a smem queue;
-//        heavy  -- the queue is drained by ALL threads, so the divergent polygon code runs at full
-//                  lane occupancy whatever the survivor density (0.3 % for anchors x GT, 100 % for
-//                  the dense microbench);
-//        store  -- the tile is staged in smem and streamed out once, coalesced (float4, st.global.cs):
-//                  DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+80*(N+M) record round trip).
-//      Sparse workloads are therefore HBM-write bound, dense ones FP32-issue bound.
+//                  return exactly +0.0, which is stored at once (coalesced st.global.cs, one full
+//                  128-byte line per warp instruction); survivors are compacted into a smem queue;
+//        drain  -- the queue, filled by up to 8 tiles, is drained by ALL threads, so the divergent
+//                  polygon code runs with full warps whatever the survivor density (0.3 % for
+//                  anchors x GT, 100 % for the dense microbench); results are stored directly.
+//      DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+ the 80*(N+M)-byte record round trip).
+//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.
 //   3. 64-bit output offsets (the reference's int32 index overflows at 2^31 pairs).
 #include "lg_common.cuh"
-#include "lg_geom.cuh"
+#include "lg_strip.cuh"
 
 namespace lg {
-
-constexpr int IOU_THREADS = 256;
-constexpr int IOU_TILE_PAIRS = 4096;
 
 template <int FL>
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ a, int64_t n, const float* __restrict__ b,
@@ -39,108 +37,166 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ a, 
 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
-template <int TB>
-struct IouSmem {
-    static constexpr int TA = IOU_TILE_PAIRS / TB;
-    static constexpr size_t rec_bytes = (size_t)(TA + TB) * REC_F4 * sizeof(float4);
-    static constexpr size_t out_bytes = (size_t)IOU_TILE_PAIRS * sizeof(float);
-    static constexpr size_t slab_bytes = (size_t)16 * IOU_THREADS * sizeof(float2);
-    static constexpr size_t queue_bytes = (size_t)IOU_TILE_PAIRS * sizeof(uint16_t);
-    static constexpr size_t total = rec_bytes + out_bytes + slab_bytes + queue_bytes;
-};
+__device__ __forceinline__ float finish_pair(const int mode, const float ov, const float4* A, const float4* B) {
+    if (mode == MODE_IOU_BEV) return iou_from_overlap(ov, A[2].w, B[2].w);
+    if (mode == MODE_IOU3D) return iou3d_from_overlap(ov, A[4], B[4]);
+    return ov;
+}
 
-template <int FL, int TB>
-__global__ void __launch_bounds__(IOU_THREADS, 2)
-    iou_tile_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int64_t m,
-                    float* __restrict__ out, const int64_t ld, const int mode, const int64_t tiles_m) {
-    constexpr int TA = IOU_TILE_PAIRS / TB;
-    constexpr int NT = IOU_THREADS;
+// ---- wide matrices: a CTA owns 64 rows x up to 512 columns --------------------------------------
+template <int FL>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+    iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int64_t m,
+                     float* __restrict__ out, const int64_t ld, const int mode, const int64_t strips_m) {
+    constexpr int NT = ST_THREADS;
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
-    float4* sB = sA + TA * REC_F4;
-    float* sOut = reinterpret_cast<float*>(sB + TB * REC_F4);
-    float2* slab = reinterpret_cast<float2*>(sOut + IOU_TILE_PAIRS);
+    float4* sB = sA + ST_ROWS * REC_F4;
+    float2* slab = reinterpret_cast<float2*>(sB + ST_COLS * REC_F4);
     uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 16 * NT);
     __shared__ int qcount;
 
-    const int tid = threadIdx.x;
-    const int64_t tile = blockIdx.x;
-    const int64_t tn = tile / tiles_m, tm = tile - tn * tiles_m;
-    const int64_t row0 = tn * TA, col0 = tm * TB;
-    const int na = (int)min((int64_t)TA, n - row0), nb = (int)min((int64_t)TB, m - col0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t strip = blockIdx.x;
+    const int64_t sn = strip / strips_m, sm = strip - sn * strips_m;
+    const int64_t row0 = sn * ST_ROWS, col0 = sm * ST_COLS;
+    const int na = (int)min((int64_t)ST_ROWS, n - row0), nb = (int)min((int64_t)ST_COLS, m - col0);
+    const int ntiles = (nb + ST_TILE - 1) / ST_TILE;
 
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
     for (int e = tid; e < nb * REC_F4; e += NT) sB[e] = __ldg(rec_b + col0 * REC_F4 + e);
-    for (int e = tid; e < IOU_TILE_PAIRS / 4; e += NT) reinterpret_cast<float4*>(sOut)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) qcount = 0;
-    __syncthreads();
 
-    // ---- cull: lanes along columns, rows broadcast from smem
-    {
-        const int col = tid % TB;
-        const int lane = tid & 31;
-        float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col < nb) bc = sB[col * REC_F4 + 2];
-#pragma unroll 4
-        for (int r = tid / TB; r < TA; r += NT / TB) {
-            bool surv = false;
-            if (r < na && col < nb) {
-                const float4 ac = sA[r * REC_F4 + 2];
-                const float dx = ac.x - bc.x, dy = ac.y - bc.y, rr = ac.z + bc.z;
-                surv = !(dx * dx + dy * dy > rr * rr);  // NaN => keep
-            }
-            const unsigned msk = __ballot_sync(0xffffffffu, surv);
-            if (msk) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&qcount, __popc(msk));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (surv) queue[base + __popc(msk & ((1u << lane) - 1u))] = (uint16_t)((r << 8) | col);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- heavy: drain the queue with every thread
-    {
-        const int qn = qcount;
+    auto drain = [&](const int qn) {
         for (int q = tid; q < qn; q += NT) {
             const int e = queue[q];
-            const int r = e >> 8, c = e & 255;
+            const int r = e >> 9, c = e & 511;
             const float4* A = sA + r * REC_F4;
             const float4* B = sB + c * REC_F4;
             const float ov = overlap_area<FL>(A, B, slab + tid, NT);
-            float res = ov;
-            if (mode == MODE_IOU_BEV) res = iou_from_overlap(ov, A[2].w, B[2].w);
-            else if (mode == MODE_IOU3D) res = iou3d_from_overlap(ov, A[4], B[4]);
-            sOut[r * TB + c] = res;
+            __stcs(out + (row0 + r) * ld + col0 + c, finish_pair(mode, ov, A, B));
         }
+    };
+
+    const int rbase = warp >> 1, cbase = (warp & 1) * 32;
+    for (int t = 0; t < ntiles; t++) {
+        __syncthreads();
+        const int qn = qcount;
+        __syncthreads();
+        if (qn > ST_QCAP - ST_TILE * ST_TILE) {  // the next tile could overflow the queue: drain first
+            drain(qn);
+            __syncthreads();
+            if (tid == 0) qcount = 0;
+            __syncthreads();
+        }
+        const int c = t * ST_TILE + cbase + lane;
+        const bool cvalid = c < nb;
+        const float4 bc = cvalid ? sB[c * REC_F4 + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* outp = out + (row0 + rbase) * ld + col0 + c;
+        unsigned mk[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int r = rbase + 4 * k;
+            bool surv = false;
+            if (cvalid && r < na) {
+                surv = cull_survives(sA[r * REC_F4 + 2], bc);
+                if (!surv) __stcs(outp + (int64_t)(4 * k) * ld, 0.f);  // culled: exactly +0.0, written once, coalesced
+            }
+            mk[k] = __ballot_sync(0xffffffffu, surv);
+        }
+        push_survivors<9>(mk, lane, rbase, 4, c, &qcount, queue);
     }
     __syncthreads();
+    drain(qcount);
+}
 
-    // ---- store: one coalesced streaming pass over the tile
-    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    if (vec) {
-        constexpr int C4 = TB / 4;
-        for (int e = tid; e < TA * C4; e += NT) {
-            const int r = e / C4, c = (e % C4) * 4;
-            if (r < na && c < nb) {
-                const float4 v = *reinterpret_cast<const float4*>(sOut + r * TB + c);
-                float* dst = out + (row0 + r) * ld + col0 + c;
-                if (c + 3 < nb) {
-                    __stcs(reinterpret_cast<float4*>(dst), v);
-                } else {
-                    __stcs(dst, v.x);
-                    if (c + 1 < nb) __stcs(dst + 1, v.y);
-                    if (c + 2 < nb) __stcs(dst + 2, v.z);
+// ---- narrow matrices (M <= 64, e.g. anchors x GT): a CTA owns 256 rows x all M columns, flat pair index ----
+constexpr int FLAT_ROWS = 256;
+constexpr int FLAT_COLS = 64;
+
+struct FlatSmem {
+    static constexpr size_t a_bytes = (size_t)FLAT_ROWS * REC_F4 * sizeof(float4);
+    static constexpr size_t b_bytes = (size_t)FLAT_COLS * REC_F4 * sizeof(float4);
+    static constexpr size_t slab_bytes = (size_t)16 * ST_THREADS * sizeof(float2);
+    static constexpr size_t queue_bytes = (size_t)ST_QCAP * sizeof(uint16_t);
+    static constexpr size_t total = a_bytes + b_bytes + slab_bytes + queue_bytes;
+};
+
+template <int FL>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+    iou_flat_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int m,
+                    float* __restrict__ out, const int64_t ld, const int mode, const unsigned inv_m /* ceil(2^20 / m) */) {
+    constexpr int NT = ST_THREADS;
+    extern __shared__ float4 smem4[];
+    float4* sA = smem4;
+    float4* sB = sA + FLAT_ROWS * REC_F4;
+    float2* slab = reinterpret_cast<float2*>(sB + FLAT_COLS * REC_F4);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 16 * NT);
+    __shared__ int qcount;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * FLAT_ROWS;
+    const int na = (int)min((int64_t)FLAT_ROWS, n - row0);
+    for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
+    for (int e = tid; e < m * REC_F4; e += NT) sB[e] = __ldg(rec_b + e);
+    if (tid == 0) qcount = 0;
+
+    auto drain = [&](const int qn) {
+        for (int q = tid; q < qn; q += NT) {
+            const int e = queue[q];
+            const int r = e >> 6, c = e & 63;
+            const float4* A = sA + r * REC_F4;
+            const float4* B = sB + c * REC_F4;
+            const float ov = overlap_area<FL>(A, B, slab + tid, NT);
+            __stcs(out + (row0 + r) * ld + c, finish_pair(mode, ov, A, B));
+        }
+    };
+
+    const int npairs = na * m;  // <= 16384
+    for (int chunk = 0; chunk < npairs; chunk += 16 * NT) {
+        __syncthreads();
+        const int qn = qcount;
+        __syncthreads();
+        if (qn > ST_QCAP - 16 * NT) {
+            drain(qn);
+            __syncthreads();
+            if (tid == 0) qcount = 0;
+            __syncthreads();
+        }
+        unsigned mk[16];
+        int codes[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int e = chunk + k * NT + tid;  // consecutive lanes -> consecutive pairs -> consecutive addresses
+            bool surv = false;
+            codes[k] = 0;
+            if (e < npairs) {
+                const int r = (int)(((unsigned)e * inv_m) >> 20), c = e - r * m;  // exact for e < 2^14, m <= 64
+                codes[k] = (r << 6) | c;
+                surv = cull_survives(sA[r * REC_F4 + 2], sB[c * REC_F4 + 2]);
+                if (!surv) __stcs(out + (row0 + r) * ld + c, 0.f);
+            }
+            mk[k] = __ballot_sync(0xffffffffu, surv);
+        }
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) total += __popc(mk[k]);
+        if (total) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&qcount, total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (mk[k]) {
+                    if ((mk[k] >> lane) & 1u) queue[base + __popc(mk[k] & lt)] = (uint16_t)codes[k];
+                    base += __popc(mk[k]);
                 }
             }
         }
-    } else {
-        for (int e = tid; e < TA * TB; e += NT) {
-            const int r = e / TB, c = e % TB;
-            if (r < na && c < nb) __stcs(out + (row0 + r) * ld + col0 + c, sOut[e]);
-        }
     }
+    __syncthreads();
+    drain(qcount);
 }
 
 static int check_args(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, size_t ws_bytes) {
@@ -164,23 +220,6 @@ static int check_args(const float* a, int64_t n, const float* b, int64_t m, floa
     return LG_OK;
 }
 
-template <int FL, int TB>
-static int launch_tiles(const float4* ra, int64_t n, const float4* rb, int64_t m, float* out, int64_t ld, int mode,
-                        cudaStream_t st) {
-    constexpr int TA = IOU_TILE_PAIRS / TB;
-    const int64_t tiles_n = (n + TA - 1) / TA, tiles_m = (m + TB - 1) / TB;
-    const int64_t tiles = tiles_n * tiles_m;
-    if (tiles > 0x7fffffffLL) {
-        set_error("%lld tiles exceed the 1-D grid limit; split the call by row blocks", (long long)tiles);
-        return LG_ERR_TOO_LARGE;
-    }
-    auto kern = iou_tile_kernel<FL, TB>;
-    int rc = set_smem(kern, IouSmem<TB>::total);
-    if (rc) return rc;
-    kern<<<(unsigned)tiles, IOU_THREADS, IouSmem<TB>::total, st>>>(ra, n, rb, m, out, ld, mode, tiles_m);
-    return check_launch("iou_tile_kernel");
-}
-
 template <int FL>
 static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, int mode,
                    cudaStream_t st) {
@@ -190,9 +229,28 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
     prep_kernel<FL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb);
     int rc = check_launch("prep_kernel");
     if (rc) return rc;
-    if (m <= 32) return launch_tiles<FL, 32>(ra, n, rb, m, out, ld, mode, st);
-    if (m <= 64) return launch_tiles<FL, 64>(ra, n, rb, m, out, ld, mode, st);
-    return launch_tiles<FL, 128>(ra, n, rb, m, out, ld, mode, st);
+    if (m <= FLAT_COLS) {
+        const int64_t ctas = (n + FLAT_ROWS - 1) / FLAT_ROWS;
+        if (ctas > 0x7fffffffLL) {
+            set_error("%lld row blocks exceed the 1-D grid limit; split the call by row blocks", (long long)ctas);
+            return LG_ERR_TOO_LARGE;
+        }
+        auto kern = iou_flat_kernel<FL>;
+        if ((rc = set_smem(kern, FlatSmem::total))) return rc;
+        const unsigned inv_m = (unsigned)(((1u << 20) + (unsigned)m - 1u) / (unsigned)m);
+        kern<<<(unsigned)ctas, ST_THREADS, FlatSmem::total, st>>>(ra, n, rb, (int)m, out, ld, mode, inv_m);
+        return check_launch("iou_flat_kernel");
+    }
+    const int64_t strips_n = (n + ST_ROWS - 1) / ST_ROWS, strips_m = (m + ST_COLS - 1) / ST_COLS;
+    const int64_t strips = strips_n * strips_m;
+    if (strips > 0x7fffffffLL) {
+        set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
+        return LG_ERR_TOO_LARGE;
+    }
+    auto kern = iou_strip_kernel<FL>;
+    if ((rc = set_smem(kern, StripSmem::total))) return rc;
+    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, m, out, ld, mode, strips_m);
+    return check_launch("iou_strip_kernel");
 }
 
 static int iou_entry(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, size_t ws_bytes,

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Small, short-running targets for `ncu --set full` (≈40 replays per launch): one op, a few launches."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lidardetection_b200 import synth  # noqa: E402
+from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U  # noqa: E402
+from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU  # noqa: E402
+
+op = sys.argv[1] if len(sys.argv) > 1 else "nms"
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+cu = lambda x: torch.from_numpy(x).cuda()
+if op == "nms":
+    b, s = synth.cfg2(16, 4096)
+    tb, ts = cu(b), cu(s)
+    for _ in range(iters):
+        U.nms_gpu_batched(tb, ts, 0.01)
+elif op == "iou_dense":
+    a, b = synth.dense_overlap(4096, 4096)
+    ta, tb = cu(a), cu(b)
+    for _ in range(iters):
+        U.boxes_iou_bev(ta, tb)
+elif op == "iou_sparse":
+    a, b = synth.cfg4(32768)
+    ta, tb = cu(a), cu(b)
+    for _ in range(iters):
+        U.boxes_iou3d_gpu(ta, tb)
+elif op == "pib":
+    p, r = synth.cfg3(256)
+    tp, tr = cu(p), cu(r)
+    for _ in range(iters):
+        PU.points_in_boxes_gpu(tp, tr)
+torch.cuda.synchronize()
+print("ok", op)
