@@ -53,6 +53,8 @@ extern "C" {
 /* flags */
 #define LG_FLAG_NONE 0u
 #define LG_FLAG_STRICT_FP32 1u /* un-contracted FP32 (reference CPU build's rounding) instead of the reference CUDA build's */
+#define LG_FLAG_NMS_FULL_MASK 2u /* rotated NMS: materialise the reference's N x N/64 suppression mask (upper triangle) and sweep
+                                    it, instead of the default lazy evaluation of kept rows only; same keep list either way */
 
 /* limits */
 #define LG_NMS_MAX_BOXES 65536 /* per NMS problem */
@@ -98,8 +100,17 @@ LG_API int lg_boxes_iou3d(const float *boxes_a, int64_t n, const float *boxes_b,
  *                            the caller's unsorted boxes -- exactly what the Python wrapper returns
  *                            (iou3d_nms_utils.py:99).  Entries beyond num_keep[p] are set to -1.
  * nmax <= LG_NMS_MAX_BOXES.
+ *
+ * Rotated NMS evaluates, by default, only the mask rows the sweep would read (rows of kept boxes): the
+ * reference computes N x N IoUs per problem of which its sweep (iou3d_nms.cpp:121-132) consumes kept rows
+ * only.  LG_FLAG_NMS_FULL_MASK selects the mask + sweep formulation; both give the identical keep list.
  */
-LG_API size_t lg_nms_workspace_bytes(int num_problems, int nmax);
+LG_API size_t lg_nms_workspace_bytes(int num_problems, int nmax); /* enough for every variant and flag */
+/* exact size for one variant: normal = 0 rotated / 1 axis-aligned; flags as passed to the NMS call */
+LG_API size_t lg_nms_workspace_bytes_ex(int num_problems, int nmax, int normal, unsigned flags);
+/* byte offset inside ws of two uint64 work counters the lazy rotated NMS leaves behind: [0] pairs put to the
+ * exact-zero cull test, [1] pairs evaluated by the polygon path (bench.py's roofline accounting reads them) */
+LG_API size_t lg_nms_stats_offset(int num_problems, int nmax);
 LG_API int lg_nms_rotated_batched(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
                            float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,
                            void *stream);

@@ -7,6 +7,7 @@ LIB_PATH = os.path.join(_HERE, "liblidargeom.so")
 
 LG_FLAG_NONE = 0
 LG_FLAG_STRICT_FP32 = 1
+LG_FLAG_NMS_FULL_MASK = 2
 LG_NMS_MAX_BOXES = 65536
 LG_PIB_MAX_BOXES = 4096
 
@@ -39,6 +40,10 @@ def lib():
         f.argtypes = [vp, i64, vp, i64, vp, i64, vp, sz, u32, vp]
     L.lg_nms_workspace_bytes.restype = sz
     L.lg_nms_workspace_bytes.argtypes = [i32, i32]
+    L.lg_nms_workspace_bytes_ex.restype = sz
+    L.lg_nms_workspace_bytes_ex.argtypes = [i32, i32, i32, u32]
+    L.lg_nms_stats_offset.restype = sz
+    L.lg_nms_stats_offset.argtypes = [i32, i32]
     for name in ("lg_nms_rotated_batched", "lg_nms_normal_batched"):
         f = getattr(L, name)
         f.restype = C.c_int
@@ -62,7 +67,7 @@ def lib():
 EXPORTS = [
     "lg_version", "lg_last_error_string", "lg_check_device",
     "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d",
-    "lg_nms_workspace_bytes", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
+    "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
 ]
 

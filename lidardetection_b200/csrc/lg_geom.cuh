@@ -8,15 +8,21 @@
 // sm_100a; DESIGN.md lists every decoded site) of each value that reaches the result: corner
 // coordinates, the four straddle determinants, the crossing point, the margin test, the fan area,
 // the IoU quotient.  Everything else is re-designed for the B200:
-//   * all per-box work (4 sincos, corners, margin-expanded half extents, areas, z-range, volume,
-//     a conservative cull radius) is hoisted into an 80-byte record computed once per box instead
-//     of once per pair (the reference re-evaluates 20 sinf/cosf per pair);
-//   * polygon vertices live in a per-thread shared-memory slab, not in local memory;
+//   * all per-box work (4 sincos, corners, edge vectors, margin-expanded half extents, areas, z-range,
+//     volume, a conservative cull radius) is hoisted into a 112-byte record computed once per box
+//     instead of once per pair (the reference re-evaluates 20 sinf/cosf per pair);
+//   * the 16 corner-difference vectors q_j - p_i are formed once and every determinant is written on
+//     them (negations are exact and free as operand modifiers), sharing the products the reference
+//     arithmetic shares: 10 FP32 instructions per edge pair;
 //   * the 16 straddle tests and 8 margin tests run uniformly into bit masks; only accepted crossings
-//     are expanded, in a compact loop, so warps do not serialise over 16 divergent branch bodies;
+//     are expanded, in a compact loop, and the warp is re-converged explicitly after each such loop;
+//   * polygon vertices live in a per-thread shared-memory column (8 slots), not in local memory;
 //   * the angular order comes from a monotone pseudo-angle packed with the vertex index into one
-//     32-bit key and an 8- (or, rarely, 16-) input min/max sorting network (the reference: ~24 atan2f
-//     + bubble sort).
+//     32-bit key and a 19-comparator min/max network (the reference: ~24 atan2f + bubble sort);
+//   * pairs with more than 8 polygon vertices (near-coincident boxes, < 1 %), and pairs in which two
+//     vertices are so close in polar angle that the reference's order hangs on the last bits of atan2f,
+//     are deferred by the caller to overlap_area_slow -- a literal atan2f + stable-sort evaluation -- so
+//     that they neither stall the other 31 lanes of a warp nor depart from the reference's vertex order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,21 +33,21 @@
 #define LG_SINF(x) sinf(x)
 #define LG_COSF(x) cosf(x)
 #endif
+#ifndef LG_ATAN2F
+#define LG_ATAN2F(y, x) atan2f((y), (x))
+#endif
 
 namespace lg {
 
-// ---- record layout (20 floats = 5 x float4 = 80 B) -------------------------------------------
-//  [0..7]   rotated corners x0,y0,x1,y1,x2,y2,x3,y3   order (-,-),(+,-),(+,+),(-,+)
-//  [8,9]    centre x, y
-//  [10]     cull radius (conservative)                -- rec[2] alone feeds the cull phase
-//  [11]     dx*dy
-//  [12,13]  cos(-heading), sin(-heading)              (check_in_box2d recomputes trig of the negated angle)
-//  [14,15]  dx/2 + 1e-2, dy/2 + 1e-2                  (MARGIN = 1e-2, kernel.cu:53)
-//  [16,17]  z + dz/2, z - dz/2                        (iou3d_nms_utils.py:60-63)
-//  [18]     dx*dy*dz
-//  [19]     unused
-constexpr int REC_FLOATS = 20;
-constexpr int REC_F4 = 5;
+// ---- record layout (28 floats = 7 x float4 = 112 B) -------------------------------------------
+//  rec[k], k = 0..3   (p_k.x, p_k.y, e_k.x, e_k.y): rotated corner k, order (-,-),(+,-),(+,+),(-,+), and the
+//                     edge vector e_k = p_{k+1} - p_k exactly as cross() forms it (kernel.cu:34-41)
+//  rec[4]             (cx, cy, cull radius, dx*dy)          -- alone feeds the cull phase
+//  rec[5]             (cos(-heading), sin(-heading), dx/2 + 1e-2, dy/2 + 1e-2)   (check_in_box2d, MARGIN kernel.cu:53)
+//  rec[6]             (z + dz/2, z - dz/2, dx*dy*dz, 0)     (iou3d_nms_utils.py:60-63)
+constexpr int REC_F4 = 7;
+constexpr int REC_FLOATS = 4 * REC_F4;
+constexpr int REC_CULL = 4, REC_TRIG = 5, REC_Z = 6;
 
 // ---- arithmetic contract helpers --------------------------------------------------------------
 // FL = 1: reference CUDA build (nvcc 12.9, sm_100a):  a*b - c*d  ==  fma(a, b, -(c*d))
@@ -61,6 +67,12 @@ template <int FL>
 __device__ __forceinline__ float madd_second(float a, float b, float c, float d) {  // a*b + c*d, second fused
     if (FL) return __fmaf_rn(c, d, __fmul_rn(a, b));
     return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+// a*b - m where m is an already rounded product (shared with another determinant)
+template <int FL>
+__device__ __forceinline__ float msub_p(float a, float b, float m) {
+    if (FL) return __fmaf_rn(a, b, -m);
+    return __fsub_rn(__fmul_rn(a, b), m);
 }
 
 // ---- per-box record ----------------------------------------------------------------------------
@@ -93,45 +105,35 @@ __device__ __forceinline__ void make_record(const float* __restrict__ box, float
     // need |ca - cb| <= ra + rb with r = sqrt(tx^2 + ty^2) (tx,ty = half extents + 1 cm).  Slack on top:
     // 0.01 % + 1 mm + 1e-6 * |centre|, orders of magnitude above the few-ulp error of the rotated corners.
     const float rad = sqrtf(tx * tx + ty * ty) * 1.0001f + 1e-3f + 1e-6f * (fabsf(cx) + fabsf(cy));
-    rec[0] = make_float4(X[0], Y[0], X[1], Y[1]);
-    rec[1] = make_float4(X[2], Y[2], X[3], Y[3]);
-    rec[2] = make_float4(cx, cy, rad, area);
-    rec[3] = make_float4(cn, sn, tx, ty);
-    rec[4] = make_float4(__fadd_rn(z, __fmul_rn(dz, 0.5f)), __fsub_rn(z, __fmul_rn(dz, 0.5f)), __fmul_rn(area, dz), 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int k1 = (k + 1) & 3;
+        rec[k] = make_float4(X[k], Y[k], __fsub_rn(X[k1], X[k]), __fsub_rn(Y[k1], Y[k]));
+    }
+    rec[REC_CULL] = make_float4(cx, cy, rad, area);
+    rec[REC_TRIG] = make_float4(cn, sn, tx, ty);
+    rec[REC_Z] = make_float4(__fadd_rn(z, __fmul_rn(dz, 0.5f)), __fsub_rn(z, __fmul_rn(dz, 0.5f)), __fmul_rn(area, dz), 0.f);
 }
 
-// exact-zero cull on the rec[2] quads (cx, cy, rad, area): false => the reference returns exactly +0.0
+// exact-zero cull on the rec[REC_CULL] quads (cx, cy, rad, area): false => the reference returns exactly +0.0
 __device__ __forceinline__ bool cull_survives(const float4 ac, const float4 bc) {
     const float dx = ac.x - bc.x, dy = ac.y - bc.y, rr = ac.z + bc.z;
     return !(dx * dx + dy * dy > rr * rr);  // NaN => keep: the polygon path decides
 }
 
-// ---- sorting networks on packed 32-bit keys (verified with the 0-1 principle, tools/check_networks.py) ----
+// ---- 8-input sorting network on packed 32-bit keys (19 compare-exchanges) ------------------------
 __device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {
     const uint32_t lo = min(a, b), hi = max(a, b);
     a = lo;
     b = hi;
 }
-__device__ __forceinline__ void sort8(uint32_t (&k)[8]) {  // 19 compare-exchanges
+__device__ __forceinline__ void sort8(uint32_t (&k)[8]) {
     cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
     cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
     cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
     cex(k[2], k[4]); cex(k[3], k[5]);
     cex(k[1], k[4]); cex(k[3], k[6]);
     cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
-}
-__device__ __forceinline__ void sort16(uint32_t (&k)[16]) {  // Batcher odd-even merge sort, 63 compare-exchanges
-    cex(k[0], k[1]); cex(k[2], k[3]); cex(k[0], k[2]); cex(k[1], k[3]); cex(k[1], k[2]); cex(k[4], k[5]);
-    cex(k[6], k[7]); cex(k[4], k[6]); cex(k[5], k[7]); cex(k[5], k[6]); cex(k[0], k[4]); cex(k[2], k[6]);
-    cex(k[2], k[4]); cex(k[1], k[5]); cex(k[3], k[7]); cex(k[3], k[5]); cex(k[1], k[2]); cex(k[3], k[4]);
-    cex(k[5], k[6]); cex(k[8], k[9]); cex(k[10], k[11]); cex(k[8], k[10]); cex(k[9], k[11]); cex(k[9], k[10]);
-    cex(k[12], k[13]); cex(k[14], k[15]); cex(k[12], k[14]); cex(k[13], k[15]); cex(k[13], k[14]); cex(k[8], k[12]);
-    cex(k[10], k[14]); cex(k[10], k[12]); cex(k[9], k[13]); cex(k[11], k[15]); cex(k[11], k[13]);
-    cex(k[9], k[10]); cex(k[11], k[12]); cex(k[13], k[14]); cex(k[0], k[8]); cex(k[4], k[12]); cex(k[4], k[8]);
-    cex(k[2], k[10]); cex(k[6], k[14]); cex(k[6], k[10]); cex(k[2], k[4]); cex(k[6], k[8]); cex(k[10], k[12]);
-    cex(k[1], k[9]); cex(k[5], k[13]); cex(k[5], k[9]); cex(k[3], k[11]); cex(k[7], k[15]); cex(k[7], k[11]);
-    cex(k[3], k[5]); cex(k[7], k[9]); cex(k[11], k[13]); cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
-    cex(k[7], k[8]); cex(k[9], k[10]); cex(k[11], k[12]); cex(k[13], k[14]);
 }
 
 // Monotone stand-in for atan2f(dy, dx) on (-pi, pi]: copysign(1 - dx/(|dx|+|dy|), dy) in [-2, 2],
@@ -147,172 +149,299 @@ __device__ __forceinline__ uint32_t angle_key(float px, float py, float cx, floa
     return (q << 4) | (uint32_t)idx;
 }
 
-// fan area from the first vertex in angular order (kernel.cu:219-224): NK = 8 or 16 sorted keys
-template <int FL, int NK>
-__device__ __forceinline__ float fan_area(const uint32_t (&key)[NK], const int cnt, const float2* __restrict__ slab,
-                                          const int sstride) {
-    const float2 p0 = slab[(key[0] & 15) * sstride];
-    const float2 p1 = slab[(key[1] & 15) * sstride];
-    float ux = p1.x - p0.x, uy = p1.y - p0.y;
-    float area = 0.f;  // term 0 is cross(0, u) == +-0 exactly
-#pragma unroll
-    for (int k = 1; k < NK - 1; k++) {
-        if (k + 1 < cnt) {
-            const float2 pn = slab[(key[k + 1] & 15) * sstride];
-            const float vx = pn.x - p0.x, vy = pn.y - p0.y;
-            area = __fadd_rn(area, msub<FL>(ux, vy, uy, vx));
-            ux = vx;
-            uy = vy;
-        }
-    }
-    return area;
+constexpr uint32_t LG_TIE_UNITS = 64;
+
+// m | bit  iff  a0 <= b0 && a1 <= b1 && a2 <= b2 && a3 <= b3 && p1 > 0 && p2 > 0  (check_rect_cross and the two
+// straddle products, kernel.cu:43-49, 75).  Written as one chain of predicate-combining compares: plain C++
+// makes ptxas either branch around each edge pair ('&&') or materialise every compare in a register ('&').
+__device__ __forceinline__ uint32_t or_if_crossing(uint32_t m, const uint32_t bit, float a0, float b0, float a1, float b1, float a2,
+                                                   float b2, float a3, float b3, float p1, float p2) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %2, %3;\n\t"
+        "setp.le.and.f32 p, %4, %5, p;\n\t"
+        "setp.le.and.f32 p, %6, %7, p;\n\t"
+        "setp.le.and.f32 p, %8, %9, p;\n\t"
+        "setp.gt.and.f32 p, %10, 0f00000000, p;\n\t"
+        "setp.gt.and.f32 p, %11, 0f00000000, p;\n\t"
+        "@p or.b32 %0, %0, %1;\n\t}"
+        : "+r"(m)
+        : "r"(bit), "f"(a0), "f"(b0), "f"(a1), "f"(b1), "f"(a2), "f"(b2), "f"(a3), "f"(b3), "f"(p1), "f"(p2));
+    return m;
+#else
+    return (a0 <= b0 && a1 <= b1 && a2 <= b2 && a3 <= b3 && p1 > 0.f && p2 > 0.f) ? (m | bit) : m;
+#endif
+}
+// m | bit  iff  |rx| < tx && |ry| < ty   (check_in_box2d, kernel.cu:60)
+__device__ __forceinline__ uint32_t or_if_inside(uint32_t m, const uint32_t bit, float rx, float tx, float ry, float ty) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\t"
+        "abs.f32 t, %2;\n\t"
+        "setp.lt.f32 p, t, %3;\n\t"
+        "abs.f32 t, %4;\n\t"
+        "setp.lt.and.f32 p, t, %5, p;\n\t"
+        "@p or.b32 %0, %0, %1;\n\t}"
+        : "+r"(m)
+        : "r"(bit), "f"(rx), "f"(tx), "f"(ry), "f"(ty));
+    return m;
+#else
+    return (fabsf(rx) < tx && fabsf(ry) < ty) ? (m | bit) : m;
+#endif
 }
 
-// ---- the pair -----------------------------------------------------------------------------------
-// A, B: records in SHARED memory (16-byte aligned; corners are re-read with dynamic indices).
-// slab: this thread's vertex column, entry k at slab[k * sstride].
-// Returns the overlap area exactly as the reference defines it (kernel.cu:104-225).
-//
-// Structure (all lanes of a warp stay converged except in the two short, compact loops):
-//   A. uniform: the 16 edge x edge straddle tests -> a 16-bit mask of accepted crossings; the 8 corner
-//      margin tests -> an 8-bit mask;
-//   B. loop over the set crossing bits (ascending = the reference's i-outer / j-inner order): recompute
-//      the determinants of that one edge pair and emit the crossing point;
-//   C. append the flagged corners (reference order: B corner k, then A corner k);
-//   D. pseudo-angle keys, 8- or 16-input sorting network, fan area.
+// ---- the pair, phase A: which of the 16 edge pairs cross, which of the 8 corners are inside ------
+// A, B: records in shared (or any generic) memory.  All lanes execute the same instruction stream.
+//   xmask bit 4i+j : edge i of A (p_i -> p_i+1) properly crosses edge j of B (kernel.cu:43-49, 67-75)
+//   cmask bit 2k   : corner k of B lies in A's margin-expanded rectangle;  bit 2k+1: corner k of A in B's
+// With D[i][j] = q_j - p_i, e_i, f_j the edge vectors (all negations below are exact):
+//   s1 = cross(q0,p1,p0) = fma(Dx[i][j],  e_i.y, -(e_i.x * Dy[i][j]))
+//   s2 = cross(p1,q1,p0) =  e_i.x * Dy[i][j+1]  -  Dx[i][j+1] * e_i.y         (both products rounded: they are
+//                           the ones s1 of the next B edge and s5 use; ptxas keeps them unfused)
+//   s3 = cross(p0,q1,q0) = fma(-Dx[i][j], f_j.y,  f_j.x * Dy[i][j])
+//   s4 = cross(q1,p1,q0) = fma(f_j.x, -Dy[i+1][j], Dx[i+1][j] * f_j.y)
 template <int FL>
-__device__ float overlap_area(const float4* __restrict__ A, const float4* __restrict__ B, float2* __restrict__ slab,
-                              const int sstride) {
-    float ax[4], ay[4], bx[4], by[4];
-    {
-        const float4 a0 = A[0], a1 = A[1], b0 = B[0], b1 = B[1];
-        ax[0] = a0.x; ay[0] = a0.y; ax[1] = a0.z; ay[1] = a0.w; ax[2] = a1.x; ay[2] = a1.y; ax[3] = a1.z; ay[3] = a1.w;
-        bx[0] = b0.x; by[0] = b0.y; bx[1] = b0.z; by[1] = b0.w; bx[2] = b1.x; by[2] = b1.y; bx[3] = b1.z; by[3] = b1.w;
+__device__ __forceinline__ void pair_masks(const float4* __restrict__ A, const float4* __restrict__ B, uint32_t& xmask,
+                                           uint32_t& cmask) {
+    float px[4], py[4], ex[4], ey[4], qx[4], qy[4], fx[4], fy[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 a = A[k], b = B[k];
+        px[k] = a.x; py[k] = a.y; ex[k] = a.z; ey[k] = a.w;
+        qx[k] = b.x; qy[k] = b.y; fx[k] = b.z; fy[k] = b.w;
     }
-    // ---- A. straddle tests (kernel.cu:43-49, 67-75)
-    uint32_t xmask = 0;
+    // corner margin tests first (their operands die early): kernel.cu:51-61
+    uint32_t cm = 0;
     {
-        float eminx[4], emaxx[4], eminy[4], emaxy[4], fx[4], fy[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int j1 = (j + 1) & 3;
-            eminx[j] = fminf(bx[j], bx[j1]); emaxx[j] = fmaxf(bx[j], bx[j1]);
-            eminy[j] = fminf(by[j], by[j1]); emaxy[j] = fmaxf(by[j], by[j1]);
-            fx[j] = bx[j1] - bx[j]; fy[j] = by[j1] - by[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int i1 = (i + 1) & 3;
-            const float p0x = ax[i], p0y = ay[i], p1x = ax[i1], p1y = ay[i1];
-            const float pminx = fminf(p0x, p1x), pmaxx = fmaxf(p0x, p1x), pminy = fminf(p0y, p1y), pmaxy = fmaxf(p0y, p1y);
-            const float ex = p1x - p0x, ey = p1y - p0y;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int j1 = (j + 1) & 3;
-                const float q0x = bx[j], q0y = by[j], q1x = bx[j1], q1y = by[j1];
-                const bool rc = pminx <= emaxx[j] && eminx[j] <= pmaxx && pminy <= emaxy[j] && eminy[j] <= pmaxy;
-                const float s1 = msub<FL>(q0x - p0x, ey, ex, q0y - p0y);                         // cross(q0, p1, p0)
-                const float s2 = __fsub_rn(__fmul_rn(ex, q1y - p0y), __fmul_rn(q1x - p0x, ey));  // cross(p1, q1, p0)
-                const float s3 = msub<FL>(p0x - q0x, fy[j], fx[j], p0y - q0y);                   // cross(p0, q1, q0)
-                const float s4 = msub<FL>(fx[j], p1y - q0y, p1x - q0x, fy[j]);                   // cross(q1, p1, q0)
-                if (rc && __fmul_rn(s1, s2) > 0.f && __fmul_rn(s3, s4) > 0.f) xmask |= 1u << (i * 4 + j);
-            }
-        }
-    }
-    // ---- corner margin tests (kernel.cu:51-61): bit 2k = B corner k in A, bit 2k+1 = A corner k in B
-    uint32_t cmask = 0;
-    {
-        const float4 am = A[2], at = A[3], bm = B[2], bt = B[3];
+        const float4 am = A[REC_CULL], at = A[REC_TRIG], bm = B[REC_CULL], bt = B[REC_TRIG];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             {
-                const float dx = bx[k] - am.x, dy = by[k] - am.y;
+                const float dx = qx[k] - am.x, dy = qy[k] - am.y;
                 const float rx = msub<FL>(dx, at.x, dy, at.y);
                 const float ry = madd_second<FL>(dx, at.y, dy, at.x);
-                if (fabsf(rx) < at.z && fabsf(ry) < at.w) cmask |= 1u << (2 * k);
+                cm = or_if_inside(cm, 1u << (2 * k), rx, at.z, ry, at.w);
             }
             {
-                const float dx = ax[k] - bm.x, dy = ay[k] - bm.y;
+                const float dx = px[k] - bm.x, dy = py[k] - bm.y;
                 const float rx = msub<FL>(dx, bt.x, dy, bt.y);
                 const float ry = madd_second<FL>(dx, bt.y, dy, bt.x);
-                if (fabsf(rx) < bt.z && fabsf(ry) < bt.w) cmask |= 1u << (2 * k + 1);
+                cm = or_if_inside(cm, 1u << (2 * k + 1), rx, bt.z, ry, bt.w);
             }
         }
     }
-    const int cnt = __popc(xmask) + __popc(cmask);  // <= 16 + 8; geometrically <= 16
-    if (cnt <= 2) return 0.f;                        // the fan sum is empty or a single zero term
-
-    // ---- B. crossing points (kernel.cu:77-91), ascending bit order == reference append order
-    const float2* __restrict__ Ac = reinterpret_cast<const float2*>(A);
-    const float2* __restrict__ Bc = reinterpret_cast<const float2*>(B);
-    int n = 0;
-    float sx = 0.f, sy = 0.f;
-    while (xmask) {
-        const int e = __ffs(xmask) - 1;
-        xmask &= xmask - 1;
-        const int i = e >> 2, j = e & 3;
-        const float2 p0 = Ac[i], p1 = Ac[(i + 1) & 3], q0 = Bc[j], q1 = Bc[(j + 1) & 3];
-        const float ex = p1.x - p0.x, ey = p1.y - p0.y;
-        const float s1 = msub<FL>(q0.x - p0.x, ey, ex, q0.y - p0.y);
-        const float t72 = __fmul_rn(ex, q1.y - p0.y), t73 = __fmul_rn(q1.x - p0.x, ey);
-        const float s5 = __fsub_rn(t73, t72);  // cross(q1, p1, p0): its two products are shared with s2, unfused
-        const float den = __fsub_rn(s5, s1);
-        float X, Y;
-        if (fabsf(den) > 1e-8f) {
-            X = __fdiv_rn(msub<FL>(s5, q0.x, s1, q1.x), den);
-            Y = __fdiv_rn(msub<FL>(s5, q0.y, s1, q1.y), den);
-        } else {
-            const float a0 = p0.y - p1.y, b0 = ex, c0 = msub<FL>(p0.x, p1.y, p1.x, p0.y);
-            const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = msub<FL>(q0.x, q1.y, q1.x, q0.y);
-            const float D = msub<FL>(a0, b1, a1, b0);
-            X = __fdiv_rn(msub<FL>(b0, c1, b1, c0), D);
-            Y = __fdiv_rn(msub<FL>(a1, c0, a0, c1), D);
+    cmask = cm;
+    // per-edge bounding intervals for check_rect_cross
+    float qlox[4], qhix[4], qloy[4], qhiy[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int j1 = (j + 1) & 3;
+        qlox[j] = fminf(qx[j], qx[j1]); qhix[j] = fmaxf(qx[j], qx[j1]);
+        qloy[j] = fminf(qy[j], qy[j1]); qhiy[j] = fmaxf(qy[j], qy[j1]);
+    }
+    float Dx[4][4], Dy[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            Dx[i][j] = qx[j] - px[i];
+            Dy[i][j] = qy[j] - py[i];
         }
-        if (n < 16) slab[n * sstride] = make_float2(X, Y);
-        sx += X;
-        sy += Y;
-        n++;
+    uint32_t xm = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int i1 = (i + 1) & 3;
+        const float plox = fminf(px[i], px[i1]), phix = fmaxf(px[i], px[i1]);
+        const float ploy = fminf(py[i], py[i1]), phiy = fmaxf(py[i], py[i1]);
+        float m1[4], m2[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            m1[j] = __fmul_rn(ex[i], Dy[i][j]);
+            m2[j] = __fmul_rn(Dx[i][j], ey[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int j1 = (j + 1) & 3;
+            const float s1 = msub_p<FL>(Dx[i][j], ey[i], m1[j]);
+            const float s2 = __fsub_rn(m1[j1], m2[j1]);
+            const float s3 = FL ? __fmaf_rn(-Dx[i][j], fy[j], __fmul_rn(fx[j], Dy[i][j]))
+                                : __fsub_rn(__fmul_rn(-Dx[i][j], fy[j]), __fmul_rn(fx[j], -Dy[i][j]));
+            const float s4 = FL ? __fmaf_rn(fx[j], -Dy[i1][j], __fmul_rn(Dx[i1][j], fy[j]))
+                                : __fsub_rn(__fmul_rn(fx[j], -Dy[i1][j]), __fmul_rn(-Dx[i1][j], fy[j]));
+            xm = or_if_crossing(xm, 1u << (i * 4 + j), plox, qhix[j], qlox[j], phix, ploy, qhiy[j], qloy[j], phiy,
+                                __fmul_rn(s1, s2), __fmul_rn(s3, s4));
+        }
     }
-    // ---- C. corners
-    while (cmask) {
-        const int e = __ffs(cmask) - 1;
-        cmask &= cmask - 1;
-        const float2 c = (e & 1) ? Ac[e >> 1] : Bc[e >> 1];
-        if (n < 16) slab[n * sstride] = c;
-        sx += c.x;
-        sy += c.y;
-        n++;
-    }
-    const int m = min(cnt, 16);
-    const float inv = __fdividef(1.0f, (float)cnt);
-    const float mx = sx * inv, my = sy * inv;  // centroid: only orders the vertices
+    xmask = xm;
+}
 
-    // ---- D. order + fan
-    float area;
-    if (m <= 8) {
+// crossing point of A edge i and B edge j (kernel.cu:77-91); the determinants are re-formed for this one pair
+template <int FL>
+__device__ __forceinline__ float2 crossing_point(const float4* __restrict__ A, const float4* __restrict__ B, const int i,
+                                                 const int j) {
+    const float4 pe = A[i];
+    const float4 q0 = B[j], q1 = B[(j + 1) & 3];
+    const float d0x = q0.x - pe.x, d0y = q0.y - pe.y, d1x = q1.x - pe.x, d1y = q1.y - pe.y;
+    const float s1 = msub<FL>(d0x, pe.w, pe.z, d0y);
+    const float t72 = __fmul_rn(pe.z, d1y), t73 = __fmul_rn(d1x, pe.w);
+    const float s5 = __fsub_rn(t73, t72);  // cross(q1, p1, p0): its two products are shared with s2, unfused
+    const float den = __fsub_rn(s5, s1);
+    float X, Y;
+    if (fabsf(den) > 1e-8f) {
+        X = __fdiv_rn(msub<FL>(s5, q0.x, s1, q1.x), den);
+        Y = __fdiv_rn(msub<FL>(s5, q0.y, s1, q1.y), den);
+    } else {
+        const float4 p1 = A[(i + 1) & 3];
+        const float a0 = pe.y - p1.y, b0 = pe.z, c0 = msub<FL>(pe.x, p1.y, p1.x, pe.y);
+        const float a1 = q0.y - q1.y, b1 = q0.z, c1 = msub<FL>(q0.x, q1.y, q1.x, q0.y);
+        const float D = msub<FL>(a0, b1, a1, b0);
+        X = __fdiv_rn(msub<FL>(b0, c1, b1, c0), D);
+        Y = __fdiv_rn(msub<FL>(a1, c0, a0, c1), D);
+    }
+    return make_float2(X, Y);
+}
+
+// ---- the pair, fast path (<= 8 polygon vertices) -------------------------------------------------
+// slab: this thread's vertex column, entry k at slab[k * sstride], 8 entries.
+// wmask: the lanes of this warp that call the function together (a __ballot_sync taken where the warp was
+// converged); it is used to re-converge the warp after each data-dependent loop.
+// Returns the overlap area exactly as the reference defines it (kernel.cu:104-225), or -1 when the polygon
+// has more than 8 vertices and the pair must be handed to overlap_area_slow.
+template <int FL>
+__device__ __forceinline__ float overlap_area(const float4* __restrict__ A, const float4* __restrict__ B,
+                                              float2* __restrict__ slab, const int sstride, const unsigned wmask) {
+    uint32_t xmask, cmask;
+    pair_masks<FL>(A, B, xmask, cmask);
+    const int cnt = __popc(xmask) + __popc(cmask);
+    float res = 0.f;          // cnt <= 2: the fan sum is empty or a single zero term
+    if (cnt > 8) res = -1.f;  // deferred
+    const bool heavy = cnt > 2 && cnt <= 8;
+    const unsigned hm = __ballot_sync(wmask, heavy);
+    bool tie = false;
+    if (heavy) {
+        int n = 0;
+        float sx = 0.f, sy = 0.f;
+        // crossing points, ascending bit order == the reference's append order (i outer, j inner)
+        while (xmask) {
+            const int e = __ffs(xmask) - 1;
+            xmask &= xmask - 1;
+            const float2 v = crossing_point<FL>(A, B, e >> 2, e & 3);
+            slab[n * sstride] = v;
+            sx += v.x;
+            sy += v.y;
+            n++;
+        }
+        __syncwarp(hm);
+        // flagged corners (reference order: B corner k, then A corner k)
+        while (cmask) {
+            const int e = __ffs(cmask) - 1;
+            cmask &= cmask - 1;
+            const float4 c = (e & 1) ? A[e >> 1] : B[e >> 1];
+            slab[n * sstride] = make_float2(c.x, c.y);
+            sx += c.x;
+            sy += c.y;
+            n++;
+        }
+        __syncwarp(hm);
+        const float inv = __fdividef(1.0f, (float)cnt);
+        const float mx = sx * inv, my = sy * inv;  // centroid: only orders the vertices
         uint32_t key[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             key[k] = 0xFFFFFFF0u | k;
-            if (k < m) {
+            if (k < cnt) {
                 const float2 p = slab[k * sstride];
                 key[k] = angle_key(p.x, p.y, mx, my, k);
             }
         }
         sort8(key);
-        area = fan_area<FL, 8>(key, m, slab, sstride);
-    } else {  // near-coincident boxes (~0.5 % of overlapping pairs)
-        uint32_t key[16];
+        // near-tie of two polar angles (coincident or radially aligned vertices): the reference's order then
+        // depends on atan2f's rounding -> hand the pair to the literal path.  64 key units = 1.9e-6 of the
+        // pseudo-angle, ~10x the rounding noise of either angle function.
+        uint32_t gap = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            key[k] = 0xFFFFFFF0u | k;
-            if (k < m) {
-                const float2 p = slab[k * sstride];
-                key[k] = angle_key(p.x, p.y, mx, my, k);
+        for (int k = 0; k < 7; k++)
+            if (k + 1 < cnt) gap = min(gap, (key[k + 1] >> 4) - (key[k] >> 4));  // padding keys sort last
+        tie = gap <= LG_TIE_UNITS;
+        // fan area from the first vertex in angular order (kernel.cu:219-224); term 0 is cross(0, u) == +-0
+        const float2 p0 = slab[(key[0] & 15) * sstride];
+        const float2 p1 = slab[(key[1] & 15) * sstride];
+        float ux = p1.x - p0.x, uy = p1.y - p0.y;
+        float area = 0.f;
+#pragma unroll
+        for (int k = 2; k < 8; k++) {
+            if (k < cnt) {
+                const float2 pn = slab[(key[k] & 15) * sstride];
+                const float vx = pn.x - p0.x, vy = pn.y - p0.y;
+                area = __fadd_rn(area, msub<FL>(ux, vy, uy, vx));
+                ux = vx;
+                uy = vy;
             }
         }
-        sort16(key);
-        area = fan_area<FL, 16>(key, m, slab, sstride);
+        res = tie ? -1.f : __fmul_rn(fabsf(area), 0.5f);
+    }
+    __syncwarp(wmask);
+    return res;
+}
+
+// ---- the pair, literal path (up to 16 vertices, or angular near-ties; rare) ------------------------
+// slab16(k) / ang16(k) return references to this thread's k-th vertex / angle slot, k < 16.  This is the
+// reference's own procedure (kernel.cu:196-224): centroid by division, atan2f about it, stable ascending
+// order (its bubble sort swaps on strict >), fan area -- written as compact rolled loops (the order is found
+// by ranking), so it is small in code and free of local memory.
+template <int FL, typename Slab16, typename Ang16>
+__device__ __noinline__ float overlap_area_slow(const float4* __restrict__ A, const float4* __restrict__ B, Slab16 slab16,
+                                                Ang16 ang16) {
+    uint32_t xmask, cmask;
+    pair_masks<FL>(A, B, xmask, cmask);
+    const int cnt = __popc(xmask) + __popc(cmask);  // <= 16 + 8; geometrically <= 16
+    if (cnt <= 2) return 0.f;
+    int n = 0;
+    float sx = 0.f, sy = 0.f;
+    while (xmask) {
+        const int e = __ffs(xmask) - 1;
+        xmask &= xmask - 1;
+        const float2 v = crossing_point<FL>(A, B, e >> 2, e & 3);
+        if (n < 16) slab16(n) = v;
+        sx = __fadd_rn(sx, v.x);
+        sy = __fadd_rn(sy, v.y);
+        n++;
+    }
+    while (cmask) {
+        const int e = __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        const float4 c = (e & 1) ? A[e >> 1] : B[e >> 1];
+        if (n < 16) slab16(n) = make_float2(c.x, c.y);
+        sx = __fadd_rn(sx, c.x);
+        sy = __fadd_rn(sy, c.y);
+        n++;
+    }
+    const int m = min(cnt, 16);
+    const float mx = __fdiv_rn(sx, (float)cnt), my = __fdiv_rn(sy, (float)cnt);
+    for (int k = 0; k < m; k++) {
+        const float2 p = slab16(k);
+        ang16(k) = LG_ATAN2F(__fsub_rn(p.y, my), __fsub_rn(p.x, mx));
+    }
+    // order: 4 bits per rank = index of the vertex with that rank (stable: equal angles keep insertion order)
+    unsigned long long order = 0ull;
+    for (int k = 0; k < m; k++) {
+        const float ak = ang16(k);
+        int rank = 0;
+        for (int l = 0; l < m; l++) {
+            const float al = ang16(l);
+            rank += (al < ak || (al == ak && l < k)) ? 1 : 0;
+        }
+        order |= (unsigned long long)k << (4 * rank);
+    }
+    const float2 p0 = slab16((int)(order & 15ull));
+    const float2 p1 = slab16((int)((order >> 4) & 15ull));
+    float ux = p1.x - p0.x, uy = p1.y - p0.y;
+    float area = 0.f;
+    for (int k = 2; k < m; k++) {
+        const float2 pn = slab16((int)((order >> (4 * k)) & 15ull));
+        const float vx = pn.x - p0.x, vy = pn.y - p0.y;
+        area = __fadd_rn(area, msub<FL>(ux, vy, uy, vx));
+        ux = vx;
+        uy = vy;
     }
     return __fmul_rn(fabsf(area), 0.5f);
 }

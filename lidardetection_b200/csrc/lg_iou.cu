@@ -5,18 +5,20 @@
 // elementwise torch kernels of boxes_iou3d_gpu (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:48-81).
 //
 // Design (B200: 148 SMs, 228 KB smem/SM, HBM3e):
-//   1. prep kernel: one thread per box builds an 80-byte record (lg_geom.cuh) -- all trigonometry,
-//      corner rotation and margin arithmetic happens N+M times instead of N*M times.
-//   2. strip kernel (lg_strip.cuh): a CTA owns 64 rows x up to 512 columns (flat variant for M <= 64:
-//      256 rows x M columns, linear pair index so that stores stay coalesced for 20-column matrices).
+//   1. prep kernel: one thread per box builds a 112-byte record (lg_geom.cuh) -- all trigonometry,
+//      corner rotation, edge vectors and margin arithmetic happens N+M times instead of N*M times.
+//   2. strip kernel (lg_strip.cuh): a CTA owns 64 rows x up to 256 columns, swept in 32 x 64 tiles (flat
+//      variant for M <= 64: 256 rows x M columns, linear pair index so that stores stay coalesced for
+//      20-column matrices).
 //        cull   -- lanes run along columns; |ca - cb|^2 > (ra + rb)^2 proves the reference would
 //                  return exactly +0.0, which is stored at once (coalesced st.global.cs, one full
 //                  128-byte line per warp instruction); survivors are compacted into a smem queue;
-//        drain  -- the queue, filled by up to 8 tiles, is drained by ALL threads, so the divergent
+//        drain  -- the queue, filled by several tiles, is drained by ALL threads, so the divergent
 //                  polygon code runs with full warps whatever the survivor density (0.3 % for
 //                  anchors x GT, 100 % for the dense microbench); results are stored directly.
-//      DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+ the 80*(N+M)-byte record round trip).
-//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.
+//      DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+ the 112*(N+M)-byte record round trip).
+//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.  67 KB smem and <= 80 registers
+//      per thread keep 3 CTAs (24 warps) resident per SM.
 //   3. 64-bit output offsets (the reference's int32 index overflows at 2^31 pairs).
 #include "lg_common.cuh"
 #include "lg_strip.cuh"
@@ -38,92 +40,97 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ a, 
 enum { MODE_OVERLAP = 0, MODE_IOU_BEV = 1, MODE_IOU3D = 2 };
 
 __device__ __forceinline__ float finish_pair(const int mode, const float ov, const float4* A, const float4* B) {
-    if (mode == MODE_IOU_BEV) return iou_from_overlap(ov, A[2].w, B[2].w);
-    if (mode == MODE_IOU3D) return iou3d_from_overlap(ov, A[4], B[4]);
+    if (mode == MODE_IOU_BEV) return iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);
+    if (mode == MODE_IOU3D) return iou3d_from_overlap(ov, A[REC_Z], B[REC_Z]);
     return ov;
 }
 
-// ---- wide matrices: a CTA owns 64 rows x up to 512 columns --------------------------------------
+// ---- wide matrices: a CTA owns 64 rows x up to 256 columns ----------------------------------------
+constexpr int SK_ROWS = 64, SK_COLS = 256, SK_TROWS = 32, SK_TCOLS = 64;
+
+struct StripSmem {
+    static constexpr size_t a_bytes = (size_t)SK_ROWS * REC_F4 * sizeof(float4);
+    static constexpr size_t b_bytes = (size_t)SK_COLS * REC_F4 * sizeof(float4);
+    static constexpr size_t total = a_bytes + b_bytes + DrainSmem::total;
+};
+
 template <int FL>
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(ST_THREADS, 3)
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int64_t m,
                      float* __restrict__ out, const int64_t ld, const int mode, const int64_t strips_m) {
     constexpr int NT = ST_THREADS;
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
-    float4* sB = sA + ST_ROWS * REC_F4;
-    float2* slab = reinterpret_cast<float2*>(sB + ST_COLS * REC_F4);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 16 * NT);
-    __shared__ int qcount;
+    float4* sB = sA + SK_ROWS * REC_F4;
+    float2* slab = reinterpret_cast<float2*>(sB + SK_COLS * REC_F4);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
+    uint16_t* rareq = queue + ST_QCAP;
+    __shared__ int qcount, rcount;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t strip = blockIdx.x;
     const int64_t sn = strip / strips_m, sm = strip - sn * strips_m;
-    const int64_t row0 = sn * ST_ROWS, col0 = sm * ST_COLS;
-    const int na = (int)min((int64_t)ST_ROWS, n - row0), nb = (int)min((int64_t)ST_COLS, m - col0);
-    const int ntiles = (nb + ST_TILE - 1) / ST_TILE;
+    const int64_t row0 = sn * SK_ROWS, col0 = sm * SK_COLS;
+    const int na = (int)min((int64_t)SK_ROWS, n - row0), nb = (int)min((int64_t)SK_COLS, m - col0);
+    const int ntiles = 2 * ((nb + SK_TCOLS - 1) / SK_TCOLS);  // (column tile, row half)
 
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
     for (int e = tid; e < nb * REC_F4; e += NT) sB[e] = __ldg(rec_b + col0 * REC_F4 + e);
-    if (tid == 0) qcount = 0;
-
-    auto drain = [&](const int qn) {
-        for (int q = tid; q < qn; q += NT) {
-            const int e = queue[q];
-            const int r = e >> 9, c = e & 511;
-            const float4* A = sA + r * REC_F4;
-            const float4* B = sB + c * REC_F4;
-            const float ov = overlap_area<FL>(A, B, slab + tid, NT);
-            __stcs(out + (row0 + r) * ld + col0 + c, finish_pair(mode, ov, A, B));
-        }
+    if (tid == 0) {
+        qcount = 0;
+        rcount = 0;
+    }
+    float* const outb = out + row0 * ld + col0;
+    auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
+        __stcs(outb + (int64_t)r * ld + c, finish_pair(mode, ov, A, B));
     };
 
-    const int rbase = warp >> 1, cbase = (warp & 1) * 32;
-    for (int t = 0; t < ntiles; t++) {
+    const int rsub = warp >> 1, cbase = (warp & 1) * 32;
+    for (int t = 0;; t++) {  // one extra trip for the final drain (a single drain call site keeps the code small)
         __syncthreads();
         const int qn = qcount;
         __syncthreads();
-        if (qn > ST_QCAP - ST_TILE * ST_TILE) {  // the next tile could overflow the queue: drain first
-            drain(qn);
-            __syncthreads();
+        const bool last = t == ntiles;
+        if (last || qn > ST_QCAP - SK_TROWS * SK_TCOLS) {  // the next tile could overflow the queue: drain first
+            drain_pairs<FL, 8>(sA, sB, slab, queue, qn, rareq, &rcount, emit);
+            if (last) break;
             if (tid == 0) qcount = 0;
             __syncthreads();
         }
-        const int c = t * ST_TILE + cbase + lane;
+        const int rbase = (t & 1) * SK_TROWS + rsub;
+        if ((t & 1) * SK_TROWS >= na) continue;  // CTA-uniform
+        const int c = (t >> 1) * SK_TCOLS + cbase + lane;
         const bool cvalid = c < nb;
-        const float4 bc = cvalid ? sB[c * REC_F4 + 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float* outp = out + (row0 + rbase) * ld + col0 + c;
-        unsigned mk[16];
+        const float4 bc = cvalid ? sB[c * REC_F4 + REC_CULL] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* outp = outb + (int64_t)rbase * ld + c;
+        unsigned mk[8];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < 8; k++) {
             const int r = rbase + 4 * k;
             bool surv = false;
             if (cvalid && r < na) {
-                surv = cull_survives(sA[r * REC_F4 + 2], bc);
+                surv = cull_survives(sA[r * REC_F4 + REC_CULL], bc);
                 if (!surv) __stcs(outp + (int64_t)(4 * k) * ld, 0.f);  // culled: exactly +0.0, written once, coalesced
             }
             mk[k] = __ballot_sync(0xffffffffu, surv);
         }
-        push_survivors<9>(mk, lane, rbase, 4, c, &qcount, queue);
+        push_survivors<8, 8>(mk, lane, rbase, 4, c, &qcount, queue);
     }
-    __syncthreads();
-    drain(qcount);
 }
 
 // ---- narrow matrices (M <= 64, e.g. anchors x GT): a CTA owns 256 rows x all M columns, flat pair index ----
 constexpr int FLAT_ROWS = 256;
 constexpr int FLAT_COLS = 64;
+constexpr int FLAT_UNROLL = 8;
 
 struct FlatSmem {
     static constexpr size_t a_bytes = (size_t)FLAT_ROWS * REC_F4 * sizeof(float4);
     static constexpr size_t b_bytes = (size_t)FLAT_COLS * REC_F4 * sizeof(float4);
-    static constexpr size_t slab_bytes = (size_t)16 * ST_THREADS * sizeof(float2);
-    static constexpr size_t queue_bytes = (size_t)ST_QCAP * sizeof(uint16_t);
-    static constexpr size_t total = a_bytes + b_bytes + slab_bytes + queue_bytes;
+    static constexpr size_t total = a_bytes + b_bytes + DrainSmem::total;
 };
 
 template <int FL>
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(ST_THREADS, 3)
     iou_flat_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int m,
                     float* __restrict__ out, const int64_t ld, const int mode, const unsigned inv_m /* ceil(2^20 / m) */) {
     constexpr int NT = ST_THREADS;
@@ -131,63 +138,61 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
     float4* sA = smem4;
     float4* sB = sA + FLAT_ROWS * REC_F4;
     float2* slab = reinterpret_cast<float2*>(sB + FLAT_COLS * REC_F4);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 16 * NT);
-    __shared__ int qcount;
+    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
+    uint16_t* rareq = queue + ST_QCAP;
+    __shared__ int qcount, rcount;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * FLAT_ROWS;
     const int na = (int)min((int64_t)FLAT_ROWS, n - row0);
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
     for (int e = tid; e < m * REC_F4; e += NT) sB[e] = __ldg(rec_b + e);
-    if (tid == 0) qcount = 0;
-
-    auto drain = [&](const int qn) {
-        for (int q = tid; q < qn; q += NT) {
-            const int e = queue[q];
-            const int r = e >> 6, c = e & 63;
-            const float4* A = sA + r * REC_F4;
-            const float4* B = sB + c * REC_F4;
-            const float ov = overlap_area<FL>(A, B, slab + tid, NT);
-            __stcs(out + (row0 + r) * ld + c, finish_pair(mode, ov, A, B));
-        }
+    if (tid == 0) {
+        qcount = 0;
+        rcount = 0;
+    }
+    float* const outb = out + row0 * ld;
+    auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
+        __stcs(outb + (int64_t)r * ld + c, finish_pair(mode, ov, A, B));
     };
 
     const int npairs = na * m;  // <= 16384
-    for (int chunk = 0; chunk < npairs; chunk += 16 * NT) {
+    for (int chunk = 0;; chunk += FLAT_UNROLL * NT) {
         __syncthreads();
         const int qn = qcount;
         __syncthreads();
-        if (qn > ST_QCAP - 16 * NT) {
-            drain(qn);
-            __syncthreads();
+        const bool last = chunk >= npairs;
+        if (last || qn > ST_QCAP - FLAT_UNROLL * NT) {
+            drain_pairs<FL, 6>(sA, sB, slab, queue, qn, rareq, &rcount, emit);
+            if (last) break;
             if (tid == 0) qcount = 0;
             __syncthreads();
         }
-        unsigned mk[16];
-        int codes[16];
+        unsigned mk[FLAT_UNROLL];
+        int codes[FLAT_UNROLL];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
+        for (int k = 0; k < FLAT_UNROLL; k++) {
             const int e = chunk + k * NT + tid;  // consecutive lanes -> consecutive pairs -> consecutive addresses
             bool surv = false;
             codes[k] = 0;
             if (e < npairs) {
                 const int r = (int)(((unsigned)e * inv_m) >> 20), c = e - r * m;  // exact for e < 2^14, m <= 64
                 codes[k] = (r << 6) | c;
-                surv = cull_survives(sA[r * REC_F4 + 2], sB[c * REC_F4 + 2]);
-                if (!surv) __stcs(out + (row0 + r) * ld + c, 0.f);
+                surv = cull_survives(sA[r * REC_F4 + REC_CULL], sB[c * REC_F4 + REC_CULL]);
+                if (!surv) __stcs(outb + (int64_t)r * ld + c, 0.f);
             }
             mk[k] = __ballot_sync(0xffffffffu, surv);
         }
         int total = 0;
 #pragma unroll
-        for (int k = 0; k < 16; k++) total += __popc(mk[k]);
+        for (int k = 0; k < FLAT_UNROLL; k++) total += __popc(mk[k]);
         if (total) {
             int base = 0;
             if (lane == 0) base = atomicAdd(&qcount, total);
             base = __shfl_sync(0xffffffffu, base, 0);
             const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
+            for (int k = 0; k < FLAT_UNROLL; k++) {
                 if (mk[k]) {
                     if ((mk[k] >> lane) & 1u) queue[base + __popc(mk[k] & lt)] = (uint16_t)codes[k];
                     base += __popc(mk[k]);
@@ -195,8 +200,6 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
             }
         }
     }
-    __syncthreads();
-    drain(qcount);
 }
 
 static int check_args(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, size_t ws_bytes) {
@@ -241,7 +244,7 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         kern<<<(unsigned)ctas, ST_THREADS, FlatSmem::total, st>>>(ra, n, rb, (int)m, out, ld, mode, inv_m);
         return check_launch("iou_flat_kernel");
     }
-    const int64_t strips_n = (n + ST_ROWS - 1) / ST_ROWS, strips_m = (m + ST_COLS - 1) / ST_COLS;
+    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS, strips_m = (m + SK_COLS - 1) / SK_COLS;
     const int64_t strips = strips_n * strips_m;
     if (strips > 0x7fffffffLL) {
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);

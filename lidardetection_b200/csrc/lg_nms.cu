@@ -16,12 +16,13 @@
 //          batched loads.  keep[] / num_keep[] are written on the device, mapped through `order`.
 // All P problems of a batch go through three launches in total, with no host synchronisation.
 #include "lg_common.cuh"
-#include "lg_geom.cuh"
+#include "lg_strip.cuh"
 
 namespace lg {
 
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_TILE = 64;
+constexpr size_t NMS_STATS_BYTES = 256;  // two u64 counters (pairs tested, pairs through the polygon path), padded
 
 __device__ __forceinline__ int problem_count(const int32_t* __restrict__ counts, int p, int nmax) {
     int n = counts ? counts[p] : nmax;
@@ -58,24 +59,24 @@ __device__ __forceinline__ void tri_decode(int t, int nb, int& rb, int& cb) {
 
 struct NmsSmem {
     static constexpr size_t rec_bytes = (size_t)2 * NMS_TILE * REC_F4 * sizeof(float4);
-    static constexpr size_t slab_bytes = (size_t)16 * NMS_THREADS * sizeof(float2);
-    static constexpr size_t queue_bytes = (size_t)NMS_TILE * NMS_TILE * sizeof(uint16_t);
     static constexpr size_t mask_bytes = (size_t)NMS_TILE * sizeof(unsigned long long);
-    static constexpr size_t total = rec_bytes + slab_bytes + queue_bytes + mask_bytes;
+    static constexpr size_t total = rec_bytes + DrainSmem::total + mask_bytes;
 };
 
 template <int FL>
-__global__ void __launch_bounds__(NMS_THREADS, 2)
+__global__ void __launch_bounds__(NMS_THREADS, 3)
     nms_mask_kernel(const float4* __restrict__ rec, const int32_t* __restrict__ counts, const int nmax, const int cbk,
                     const float thresh, unsigned long long* __restrict__ mask) {
     constexpr int NT = NMS_THREADS, T = NMS_TILE;
+    static_assert(NT == ST_THREADS && T * T <= ST_QCAP, "queue sizing");
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
     float4* sB = sA + T * REC_F4;
     float2* slab = reinterpret_cast<float2*>(sB + T * REC_F4);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 16 * NT);
-    unsigned int* smask = reinterpret_cast<unsigned int*>(queue + T * T);  // 64 x (lo, hi)
-    __shared__ int qcount;
+    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
+    uint16_t* rareq = queue + ST_QCAP;
+    unsigned int* smask = reinterpret_cast<unsigned int*>(rareq + ST_QCAP);  // 64 x (lo, hi)
+    __shared__ int qcount, rcount;
 
     const int p = blockIdx.y;
     const int n = problem_count(counts, p, nmax);
@@ -84,52 +85,42 @@ __global__ void __launch_bounds__(NMS_THREADS, 2)
     tri_decode(blockIdx.x, cbk, rb, cb);
     if (rb >= nb || cb >= nb) return;  // tile outside this problem's boxes
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int na = min(T, n - rb * T), ncol = min(T, n - cb * T);
     const float4* gA = rec + ((int64_t)p * nmax + (int64_t)rb * T) * REC_F4;
     const float4* gB = rec + ((int64_t)p * nmax + (int64_t)cb * T) * REC_F4;
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(gA + e);
     for (int e = tid; e < ncol * REC_F4; e += NT) sB[e] = __ldg(gB + e);
     if (tid < 2 * T) smask[tid] = 0u;
-    if (tid == 0) qcount = 0;
+    if (tid == 0) {
+        qcount = 0;
+        rcount = 0;
+    }
     __syncthreads();
 
     {
-        const int col = tid % T, lane = tid & 31;
+        const int col = (warp & 1) * 32 + lane, rsub = warp >> 1;
         const bool diag = (rb == cb);
-        float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col < ncol) bc = sB[col * REC_F4 + 2];
-#pragma unroll 4
-        for (int r = tid / T; r < T; r += NT / T) {
+        const bool cvalid = col < ncol;
+        const float4 bc = cvalid ? sB[col * REC_F4 + REC_CULL] : make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned mk[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int r = rsub + 4 * k;
             bool surv = false;
-            if (r < na && col < ncol && (!diag || col > r)) {
-                const float4 ac = sA[r * REC_F4 + 2];
-                const float dx = ac.x - bc.x, dy = ac.y - bc.y, rr = ac.z + bc.z;
-                surv = !(dx * dx + dy * dy > rr * rr);
-            }
-            const unsigned msk = __ballot_sync(0xffffffffu, surv);
-            if (msk) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&qcount, __popc(msk));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (surv) queue[base + __popc(msk & ((1u << lane) - 1u))] = (uint16_t)((r << 8) | col);
-            }
+            if (cvalid && r < na && (!diag || col > r)) surv = cull_survives(sA[r * REC_F4 + REC_CULL], bc);
+            mk[k] = __ballot_sync(0xffffffffu, surv);
         }
+        push_survivors<8, 16>(mk, lane, rsub, 4, col, &qcount, queue);
     }
     __syncthreads();
 
-    {
-        const int qn = qcount;
-        for (int q = tid; q < qn; q += NT) {
-            const int e = queue[q];
-            const int r = e >> 8, c = e & 255;
-            const float4* A = sA + r * REC_F4;  // row = the higher-scoring box: iou_bev(row, col), kernel.cu:304
-            const float4* B = sB + c * REC_F4;
-            const float ov = overlap_area<FL>(A, B, slab + tid, NT);
-            const float iou = iou_from_overlap(ov, A[2].w, B[2].w);
-            if (iou > thresh) atomicOr(&smask[2 * r + (c >> 5)], 1u << (c & 31));
-        }
-    }
+    // row = the higher-scoring box: iou_bev(row, col), kernel.cu:304
+    auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
+        const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);
+        if (iou > thresh) atomicOr(&smask[2 * r + (c >> 5)], 1u << (c & 31));
+    };
+    drain_pairs<FL, 8>(sA, sB, slab, queue, qcount, rareq, &rcount, emit);
     __syncthreads();
 
     if (tid < na) {
@@ -256,6 +247,222 @@ __global__ void __launch_bounds__(32)
     for (int i = nk + lane; i < nmax; i += 32) keep[base + i] = -1;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Lazy rotated NMS: one CTA per problem, no N x N/64 mask.
+//
+// The reference's sweep (iou3d_nms.cpp:121-132) reads row i of the mask only when box i is KEPT, so only
+// kept rows have to exist.  Per pass the CTA takes the next LZ_G boxes that are still alive (speculating
+// that they will all be kept), and evaluates their rows against every later alive box at once:
+//   cull   -> (candidate, box) codes of the pairs the circle test cannot prove disjoint, in a smem queue;
+//   drain  -> the polygon path on full warps; iou(candidate, box) > thresh sets a bit in the candidate's
+//             suppression row (smem);
+//   resolve-> candidates are walked in score order: one that an earlier KEPT candidate of the same pass
+//             suppresses is dropped together with its row (the speculation failed, its row is discarded);
+//             the others are kept and their rows are OR-ed out of the alive bitmap.
+// Every IoU that decides anything is iou_bev(kept box, later box) exactly as in the mask formulation, so the
+// keep list is identical; the work drops from N^2/2 pairs to about (#kept + failed speculations) x N.
+constexpr int LZ_G = 8;        // speculative candidates per pass
+constexpr int LZ_QCAP = 4096;  // u32 codes: candidate << 16 | box
+constexpr int LZ_CACHE = 4096; // cull quads cached in smem; boxes beyond read theirs from the records (L2)
+constexpr int LZ_SWEEP = ST_THREADS;  // columns per sweep of the 8 warps
+
+struct LazyLayout {
+    int words;         // alive words
+    size_t off_cull, off_slab, off_queue, off_rare, off_alive, off_sup, total;
+    __host__ __device__ explicit LazyLayout(int nmax) {
+        words = (nmax + 31) / 32;
+        size_t o = (size_t)LZ_G * REC_F4 * sizeof(float4);  // candidate records first
+        off_cull = o;
+        o += (size_t)(nmax < LZ_CACHE ? nmax : LZ_CACHE) * sizeof(float4);
+        off_slab = o;
+        o += DrainSmem::slab_bytes;
+        off_queue = o;
+        o += (size_t)LZ_QCAP * sizeof(uint32_t);
+        off_rare = o;
+        o += (size_t)LZ_QCAP * sizeof(uint32_t);
+        off_alive = o;
+        o += (size_t)words * sizeof(uint32_t);
+        off_sup = o;
+        o += (size_t)LZ_G * words * sizeof(uint32_t);
+        total = o;
+    }
+};
+
+template <int FL>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+    nms_lazy_kernel(const float4* __restrict__ rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
+                    const int nmax, const float thresh, int64_t* __restrict__ keep, int32_t* __restrict__ num_keep,
+                    unsigned long long* __restrict__ stats) {
+    constexpr int NT = ST_THREADS, G = LZ_G;
+    extern __shared__ float4 smem4[];
+    const LazyLayout L(nmax);
+    char* sm = reinterpret_cast<char*>(smem4);
+    float4* sA = smem4;
+    float4* scull = reinterpret_cast<float4*>(sm + L.off_cull);
+    float2* slab = reinterpret_cast<float2*>(sm + L.off_slab);
+    uint32_t* queue = reinterpret_cast<uint32_t*>(sm + L.off_queue);
+    uint32_t* rareq = reinterpret_cast<uint32_t*>(sm + L.off_rare);
+    uint32_t* alive = reinterpret_cast<uint32_t*>(sm + L.off_alive);
+    uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
+    __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s;
+    __shared__ unsigned long long st_tested, st_heavy;
+
+    const int p = blockIdx.x;
+    const int n = problem_count(counts, p, nmax);
+    const int W = (n + 31) / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base = (int64_t)p * nmax;
+    const float4* grec = rec + base * REC_F4;
+
+    for (int w = tid; w < W; w += NT) alive[w] = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu;
+    for (int w = tid; w < G * W; w += NT) sup[w] = 0u;
+    for (int j = tid; j < min(n, LZ_CACHE); j += NT) scull[j] = __ldg(grec + (int64_t)j * REC_F4 + REC_CULL);
+    if (tid == 0) {
+        qcount = 0;
+        rcount = 0;
+        nk_s = 0;
+        st_tested = 0ull;
+        st_heavy = 0ull;
+    }
+    int cursor = 0;  // every box below it is decided
+    unsigned my_tested = 0u;
+
+    auto emit = [&](int g, int j, float ov, const float4* A, const float4* B) {
+        const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);  // row = the higher-scoring box (kernel.cu:304)
+        if (iou > thresh) atomicOr(&sup[g * W + (j >> 5)], 1u << (j & 31));
+    };
+
+    while (true) {
+        __syncthreads();
+        // ---- the next G alive boxes at or after the cursor (warp 0)
+        if (warp == 0) {
+            int found = 0;
+            for (int w0 = cursor >> 5; w0 < W && found < G; w0 += 32) {
+                const int w = w0 + lane;
+                unsigned word = w < W ? alive[w] : 0u;
+                if (w == (cursor >> 5)) word &= 0xFFFFFFFFu << (cursor & 31);
+                int incl = __popc(word);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                int slot = found + incl - __popc(word);
+                while (word && slot < G) {
+                    const int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    group[slot++] = w * 32 + b;
+                }
+                found += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) ng_s = min(found, G);
+        }
+        __syncthreads();
+        const int ng = ng_s;
+        if (ng == 0) break;
+        for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
+        __syncthreads();
+        const int g0 = group[0];
+        float4 ac[G];
+        int gi[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            ac[g] = sA[(g < ng ? g : 0) * REC_F4 + REC_CULL];
+            gi[g] = g < ng ? group[g] : 0x7fffffff;  // an unused slot is "after" every box: never tested
+        }
+        // ---- rows of the candidates against every later alive box, a chunk of columns at a time
+        int jw = ((g0 + 1) >> 5) << 5;
+        while (jw < n) {
+            __syncthreads();
+            const int qn = qcount;
+            __syncthreads();
+            const int room = (LZ_QCAP - qn) / G;  // columns that cannot overflow the queue
+            if (room < LZ_SWEEP) {
+                drain_pairs<FL, 16>(sA, grec, slab, queue, qn, rareq, &rcount, emit);
+                if (tid == 0) {
+                    qcount = 0;
+                    st_heavy += (unsigned long long)qn;
+                }
+                continue;
+            }
+            const int sweeps = min(room / LZ_SWEEP, (n - jw + LZ_SWEEP - 1) / LZ_SWEEP);
+            for (int s = 0; s < sweeps; s++) {
+                const int jb = jw + s * LZ_SWEEP + warp * 32;  // this warp's 32-aligned word of columns
+                if (jb >= n) break;
+                const unsigned word = alive[jb >> 5];
+                if (word == 0u) continue;  // warp-uniform
+                const int j = jb + lane;
+                const bool a = (word >> lane) & 1u;
+                const float4 cj = a ? (j < LZ_CACHE ? scull[j] : __ldg(grec + (int64_t)j * REC_F4 + REC_CULL)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned mk[G];
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const bool t = a && j > gi[g];
+                    my_tested += t ? 1u : 0u;
+                    mk[g] = __ballot_sync(0xffffffffu, t && cull_survives(ac[g], cj));
+                }
+                // code = candidate << 16 | box: push_survivors' (row << SHIFT | col) with row = g, col = j
+                push_survivors<16, G>(mk, lane, 0, 1, j, &qcount, queue);
+            }
+            jw += sweeps * LZ_SWEEP;
+        }
+        __syncthreads();
+        {
+            const int qn = qcount;
+            drain_pairs<FL, 16>(sA, grec, slab, queue, qn, rareq, &rcount, emit);
+            if (tid == 0) {
+                qcount = 0;
+                st_heavy += (unsigned long long)qn;
+            }
+        }
+        __syncthreads();
+        // ---- resolve the speculation in score order (one thread; at most G*(G-1)/2 bit tests)
+        if (tid == 0) {
+            int km = 0, nk = nk_s;
+            for (int g = 0; g < ng; g++) {
+                const int j = group[g];
+                bool dead = false;
+                for (int h = 0; h < g; h++)
+                    if (((km >> h) & 1) && ((sup[h * W + (j >> 5)] >> (j & 31)) & 1u)) dead = true;
+                if (!dead) {
+                    km |= 1 << g;
+                    keep[base + nk++] = order ? order[base + j] : (int64_t)j;
+                }
+            }
+            keptmask_s = km;
+            nk_s = nk;
+        }
+        __syncthreads();
+        const int km = keptmask_s;
+        for (int w = (g0 >> 5) + tid; w < W; w += NT) {
+            unsigned kill = 0u;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                if (g < ng) {
+                    if ((km >> g) & 1) kill |= sup[g * W + w];
+                    sup[g * W + w] = 0u;
+                }
+            }
+            alive[w] &= ~kill;
+        }
+        __syncthreads();
+        if (tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));  // candidates are decided either way
+        cursor = group[ng - 1] + 1;
+    }
+    // all threads left the loop together
+    const int nk = nk_s;
+    if (tid == 0) num_keep[p] = nk;
+    for (int i = nk + tid; i < nmax; i += NT) keep[base + i] = -1;
+    if (stats) {
+        atomicAdd(&st_tested, (unsigned long long)my_tested);
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(stats, st_tested);
+            atomicAdd(stats + 1, st_heavy);
+        }
+    }
+}
+
 enum { PHASE_RECORDS = 1, PHASE_MASK = 2, PHASE_SWEEP = 4, PHASE_ALL = 7 };
 
 static int nms_entry(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax, float thresh, void* ws,
@@ -287,7 +494,7 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
         }
         return LG_OK;
     }
-    const size_t need = lg_nms_workspace_bytes(P, nmax);
+    const size_t need = lg_nms_workspace_bytes_ex(P, nmax, normal ? 1 : 0, flags);
     if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15)) {
         set_error("workspace %p of %zu B; need %zu B, 16-byte aligned", ws, ws_bytes, need);
         return LG_ERR_WORKSPACE;
@@ -296,8 +503,10 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
     const int tri = cbk * (cbk + 1) / 2;
     float4* rec = reinterpret_cast<float4*>(ws);
     const size_t rec_bytes = align_up((size_t)P * nmax * REC_F4 * sizeof(float4), 256);
-    unsigned long long* mask = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes);
+    unsigned long long* stats = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes);
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes + NMS_STATS_BYTES);
     const bool strict = (flags & LG_FLAG_STRICT_FP32) != 0;
+    const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0;
     int rc;
     if (!normal) {
         if (phases & PHASE_RECORDS) {
@@ -305,6 +514,24 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
             if (strict) nms_prep_kernel<0><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
             else nms_prep_kernel<1><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
             if ((rc = check_launch("nms_prep_kernel"))) return rc;
+        }
+        if (!full) {
+            // lazy path: only the rows of kept boxes are ever evaluated
+            if (!(phases & PHASE_SWEEP)) return LG_OK;
+            cudaError_t e = cudaMemsetAsync(stats, 0, NMS_STATS_BYTES, st);
+            if (e != cudaSuccess) {
+                set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+                return (int)e;
+            }
+            const LazyLayout L(nmax);
+            if (strict) {
+                if ((rc = set_smem(nms_lazy_kernel<0>, L.total))) return rc;
+                nms_lazy_kernel<0><<<P, ST_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
+            } else {
+                if ((rc = set_smem(nms_lazy_kernel<1>, L.total))) return rc;
+                nms_lazy_kernel<1><<<P, ST_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
+            }
+            return check_launch("nms_lazy_kernel");
         }
         if (!(phases & PHASE_MASK)) goto sweep;
         dim3 mg(tri, P);
@@ -330,10 +557,19 @@ sweep:
 
 }  // namespace lg
 
-extern "C" size_t lg_nms_workspace_bytes(int P, int nmax) {
+extern "C" size_t lg_nms_workspace_bytes_ex(int P, int nmax, int normal, unsigned flags) {
     if (P <= 0 || nmax <= 0) return 0;
     const size_t cbk = ((size_t)nmax + 63) / 64;
-    return lg::align_up((size_t)P * nmax * lg::REC_F4 * sizeof(float4), 256) + (size_t)P * nmax * cbk * sizeof(unsigned long long) + 16;
+    size_t b = lg::align_up((size_t)P * nmax * lg::REC_F4 * sizeof(float4), 256) + lg::NMS_STATS_BYTES + 16;
+    if (normal || (flags & LG_FLAG_NMS_FULL_MASK)) b += (size_t)P * nmax * cbk * sizeof(unsigned long long);
+    return b;
+}
+
+extern "C" size_t lg_nms_workspace_bytes(int P, int nmax) { return lg_nms_workspace_bytes_ex(P, nmax, 1, LG_FLAG_NMS_FULL_MASK); }
+
+extern "C" size_t lg_nms_stats_offset(int P, int nmax) {
+    if (P <= 0 || nmax <= 0) return 0;
+    return lg::align_up((size_t)P * nmax * lg::REC_F4 * sizeof(float4), 256);
 }
 
 extern "C" int lg_nms_rotated_batched(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax,

@@ -100,7 +100,7 @@ def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE):
         return keep, num
     L = _lib.lib()
     with torch.cuda.device(dev):
-        ws_bytes = L.lg_nms_workspace_bytes(P, N)
+        ws_bytes = L.lg_nms_workspace_bytes_ex(P, N, 1 if 'normal' in fn_name else 0, flags)
         ws = _workspace(ws_bytes, dev)
         rc = getattr(L, fn_name)(_lib.ptr(boxes), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), _lib.ptr(ws),
                                  ws.numel(), _lib.ptr(keep), _lib.ptr(num), flags, _lib.stream_ptr(dev))

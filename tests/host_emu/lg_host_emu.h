@@ -16,6 +16,10 @@ extern "C" float lgo_cosf(float, int);
 #define LG_SINF(x) lgo_sinf((x), 1)
 #define LG_COSF(x) lgo_cosf((x), 1)
 
+#ifndef __noinline__
+#define __noinline__ __attribute__((noinline))
+#endif
+
 using std::max;
 using std::min;
 
@@ -40,6 +44,9 @@ static inline float __double2float_rd(double d) {
     if ((double)f > d) f = nextafterf(f, -INFINITY);
     return f;
 }
+static inline unsigned __ballot_sync(unsigned m, bool p) { return (m & 1u) && p ? 1u : 0u; }
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline unsigned __activemask() { return 1u; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
