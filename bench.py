@@ -153,7 +153,7 @@ class NmsWorkload(Workload):
         self.scores = torch.from_numpy(self.scores_np).cuda()
         self.h_boxes = torch.from_numpy(self.boxes_np).pin_memory()
         self.h_scores = torch.from_numpy(self.scores_np).pin_memory()
-        self.launches_per_step = 3  # nms_prep_kernel, nms_mask_kernel, nms_sweep_kernel (torch.sort is not ours)
+        self.launches_per_step = 2  # nms_prep_kernel, nms_lazy_kernel (torch.sort is not ours)
         self.h2d = self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
         self.d2h = self.scores.numel() * 8 + self.units * 4
 
@@ -174,8 +174,14 @@ class NmsWorkload(Workload):
         return list(out)
 
     def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
-        """dominant kernel = nms_mask_kernel (rotated IoU on the upper triangle): FP32-pipe bound.
-        algorithmic flops = pairs * (307 (1-p) + 818 p), p = fraction of pairs with non-zero overlap."""
+        """dominant kernel = nms_lazy_kernel: rotated IoU of the kept boxes' rows (FP32-pipe bound).
+
+        Work accounting (307 flops for a pair whose overlap is exactly 0, 818 otherwise):
+          executed   the pairs the lazy kernel puts to the test (its own device counters): the rows of kept
+                     boxes plus failed speculation -- this is the work `achieved` / `frac` are quoted on;
+          reference  N(N-1)/2 pairs per problem, the mask the reference materialises; the same metric for the
+                     mask + sweep formulation (LG_FLAG_NMS_FULL_MASK) is reported beside it.
+        """
         torch = self.torch
         from lidardetection_b200 import _lib
         from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
@@ -188,44 +194,59 @@ class NmsWorkload(Workload):
             nz += int((torch.triu(ov, 1) > 0).sum())
             tot += N * (N - 1) // 2
         p = nz / max(tot, 1)
-        pairs = P * N * (N - 1) // 2
-        flops = pairs * (307.0 * (1 - p) + 818.0 * p)
+        pairs_ref = P * N * (N - 1) // 2
         L = _lib.lib()
         order = self.scores.sort(1, descending=True)[1].contiguous()
         keep = torch.empty((P, N), dtype=torch.int64, device="cuda")
         num = torch.zeros((P,), dtype=torch.int32, device="cuda")
         ws = torch.empty(L.lg_nms_workspace_bytes(P, N), dtype=torch.uint8, device="cuda")
         st = _lib.stream_ptr(self.boxes.device)
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
-        def phases(ph):
+        def phases(ph, flags):
             rc = L.lg_nms_batched_phases(_lib.ptr(self.boxes), _lib.ptr(order), None, P, N, self.thresh, _lib.ptr(ws), ws.numel(),
-                                         _lib.ptr(keep), _lib.ptr(num), 0, st, 0, ph)
+                                         _lib.ptr(keep), _lib.ptr(num), flags, st, 0, ph)
             _lib.check(rc, "lg_nms_batched_phases")
 
-        phases(7)
-        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
-        times = {1: [], 2: [], 4: []}
-        for _ in range(max(3, steps)):
-            for ph in (1, 2, 4):
-                if ph == 2:
-                    flush.zero_()
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                phases(ph)
-                e.record()
-                e.synchronize()
-                times[ph].append(s.elapsed_time(e))
-        t_mask = float(np.mean(times[2])) * 1e-3
-        achieved = flops / t_mask / 1e12
+        def timed(plan, flags):
+            phases(7, flags)
+            times = {ph: [] for ph in plan}
+            for _ in range(max(3, steps)):
+                for ph in plan:
+                    if ph != 1:
+                        flush.zero_()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record()
+                    phases(ph, flags)
+                    e.record()
+                    e.synchronize()
+                    times[ph].append(s.elapsed_time(e))
+            return {ph: float(np.mean(v)) for ph, v in times.items()}
+
+        t_lazy = timed((1, 4), _lib.LG_FLAG_NONE)
+        off = L.lg_nms_stats_offset(P, N)
+        tested, heavy, nonzero = (int(x) for x in ws[off:off + 24].view(torch.int64).cpu().tolist())
+        t_full = timed((1, 2, 4), _lib.LG_FLAG_NMS_FULL_MASK)
+        t_k = t_lazy[4] * 1e-3
+        flops = 307.0 * (tested - nonzero) + 818.0 * nonzero
+        achieved = flops / t_k / 1e12
         peak = fp32_peak or 74.4
-        return {"bound": "fp32", "kernel": "nms_mask_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        f_ref = 307.0 * (1 - p) + 818.0 * p
+        return {"bound": "fp32", "kernel": "nms_lazy_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "tools/peak_fp32.cu unrolled-FFMA microbenchmark measured live (MEASURED_PEAKS.json has no FP32 figure)"
                 if fp32_peak else "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz",
-                "algorithmic": {"pairs_per_launch": pairs, "nonzero_fraction": p, "flops_per_pair": 307.0 * (1 - p) + 818.0 * p,
-                                "gpairs_per_s": pairs / t_mask / 1e9},
-                "kernel_ms": {"nms_prep_kernel": float(np.mean(times[1])), "nms_mask_kernel": float(np.mean(times[2])),
-                              "nms_sweep_kernel": float(np.mean(times[4]))}}
+                "algorithmic": {"pairs_executed_per_launch": tested, "pairs_through_polygon_path": heavy, "pairs_nonzero": nonzero,
+                                "flops_per_launch": flops, "accounting": "307 flops per zero-overlap pair, 818 otherwise (SURVEY 8d), on the pairs "
+                                "the kernel evaluates: rows of kept boxes + failed speculation, counted on the device",
+                                "reference_pairs_per_launch": pairs_ref, "reference_nonzero_fraction": p,
+                                "reference_equivalent_tflops": pairs_ref * f_ref / t_k / 1e12},
+                "kernel_ms": {"nms_prep_kernel": t_lazy[1], "nms_lazy_kernel": t_lazy[4]},
+                "full_mask_formulation": {"kernel": "nms_mask_kernel", "kernel_ms": {"nms_prep_kernel": t_full[1], "nms_mask_kernel": t_full[2],
+                                                                                   "nms_sweep_kernel": t_full[4]},
+                                          "achieved": pairs_ref * f_ref / (t_full[2] * 1e-3) / 1e12,
+                                          "frac": pairs_ref * f_ref / (t_full[2] * 1e-3) / 1e12 / peak,
+                                          "gpairs_per_s": pairs_ref / (t_full[2] * 1e-3) / 1e9}}
 
     def cpu_sample(self, pool):
         keep, dt = pool.nms_frame(self.boxes_np[0], self.scores_np[0], self.thresh)
@@ -258,7 +279,7 @@ class IouWorkload(Workload):
         self.pairs = a.shape[0] * b.shape[0]
         self.units = self.pairs / 1e9
         self.out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device="cuda")
-        self.launches_per_step = 2  # prep_kernel, iou_tile_kernel
+        self.launches_per_step = 2  # prep_kernel, iou_strip_kernel (iou_flat_kernel for M <= 64)
         self.h2d = (a.size + b.size) * 4
         self.e2e_d2h_full = self.pairs * 4 <= (1 << 30)
         self.d2h = self.pairs * 4 if self.e2e_d2h_full else a.shape[0] * 8
@@ -307,12 +328,12 @@ class IouWorkload(Workload):
             nz = float((self.out[:2048] > 0).float().mean())
             flops = self.pairs * (307.0 * (1 - nz) + 818.0 * nz)
             ach, peak = flops / t / 1e12, (fp32_peak or 74.4)
-            return {"bound": "fp32", "kernel": "iou_tile_kernel (+prep_kernel, <1%)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            return {"bound": "fp32", "kernel": "iou_strip_kernel (+prep_kernel, <1%)", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                     "traffic": None, "peak_source": "tools/peak_fp32.cu FFMA microbenchmark, measured live",
                     "algorithmic": {"pairs_per_launch": self.pairs, "nonzero_fraction": nz, "flops_per_pair": 307.0 * (1 - nz) + 818.0 * nz}}
         byts = 4.0 * n * m + 28.0 * (n + m)
         ach = byts / t / 1e9
-        return {"bound": "hbm", "kernel": "iou_tile_kernel (+prep_kernel)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+        return {"bound": "hbm", "kernel": "iou_strip_kernel / iou_flat_kernel (+prep_kernel)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": None, "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "4*N*M + 28*(N+M)"}}
 
     def cpu_sample(self, pool):

@@ -108,8 +108,9 @@ LG_API int lg_boxes_iou3d(const float *boxes_a, int64_t n, const float *boxes_b,
 LG_API size_t lg_nms_workspace_bytes(int num_problems, int nmax); /* enough for every variant and flag */
 /* exact size for one variant: normal = 0 rotated / 1 axis-aligned; flags as passed to the NMS call */
 LG_API size_t lg_nms_workspace_bytes_ex(int num_problems, int nmax, int normal, unsigned flags);
-/* byte offset inside ws of two uint64 work counters the lazy rotated NMS leaves behind: [0] pairs put to the
- * exact-zero cull test, [1] pairs evaluated by the polygon path (bench.py's roofline accounting reads them) */
+/* byte offset inside ws of three uint64 work counters the lazy rotated NMS leaves behind: [0] pairs put to the
+ * exact-zero cull test, [1] pairs evaluated by the polygon path, [2] pairs with a non-zero overlap
+ * (bench.py's roofline accounting reads them) */
 LG_API size_t lg_nms_stats_offset(int num_problems, int nmax);
 LG_API int lg_nms_rotated_batched(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
                            float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,

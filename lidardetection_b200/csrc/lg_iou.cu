@@ -6,18 +6,20 @@
 //
 // Design (B200: 148 SMs, 228 KB smem/SM, HBM3e):
 //   1. prep kernel: one thread per box builds a 112-byte record (lg_geom.cuh) -- all trigonometry,
-//      corner rotation, edge vectors and margin arithmetic happens N+M times instead of N*M times.
-//   2. strip kernel (lg_strip.cuh): a CTA owns 64 rows x up to 256 columns, swept in 32 x 64 tiles (flat
-//      variant for M <= 64: 256 rows x M columns, linear pair index so that stores stay coalesced for
-//      20-column matrices).
+//      corner rotation, edge vectors and margin arithmetic happens N+M times instead of N*M times -- and,
+//      for the column boxes, a compact 16-byte cull quad (centre, radius) that the cull phase reads coalesced.
+//   2. strip kernel (lg_strip.cuh): a CTA owns 64 rows (records in smem) x a run of columns, swept in
+//      32 x 64 tiles (flat variant for M <= 64: 256 rows x M columns, linear pair index so that stores stay
+//      coalesced for 20-column matrices).
 //        cull   -- lanes run along columns; |ca - cb|^2 > (ra + rb)^2 proves the reference would
 //                  return exactly +0.0, which is stored at once (coalesced st.global.cs, one full
 //                  128-byte line per warp instruction); survivors are compacted into a smem queue;
-//        drain  -- the queue, filled by several tiles, is drained by ALL threads, so the divergent
-//                  polygon code runs with full warps whatever the survivor density (0.3 % for
-//                  anchors x GT, 100 % for the dense microbench); results are stored directly.
-//      DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+ the 112*(N+M)-byte record round trip).
-//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.  67 KB smem and <= 80 registers
+//        drain  -- the queue keeps filling across the column tiles and is drained by ALL threads when
+//                  it is nearly full, so the divergent polygon code runs with full warps whatever the
+//                  survivor density (0.3 % for anchors x GT, 100 % for the dense microbench); column
+//                  records are read through L1/L2 (they are 112 B x M, L2 resident); results are stored directly.
+//      DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+ the 128*(N+M)-byte record round trip).
+//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.  63 KB smem and <= 80 registers
 //      per thread keep 3 CTAs (24 warps) resident per SM.
 //   3. 64-bit output offsets (the reference's int32 index overflows at 2^31 pairs).
 #include "lg_common.cuh"
@@ -27,13 +29,15 @@ namespace lg {
 
 template <int FL>
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ a, int64_t n, const float* __restrict__ b,
-                                                   int64_t m, float4* __restrict__ rec_a, float4* __restrict__ rec_b) {
+                                                   int64_t m, float4* __restrict__ rec_a, float4* __restrict__ rec_b,
+                                                   float4* __restrict__ cull_b) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         make_record<FL>(a + i * 7, rec_a + i * REC_F4);
     } else if (i < n + m) {
         const int64_t j = i - n;
         make_record<FL>(b + j * 7, rec_b + j * REC_F4);
+        cull_b[j] = rec_b[j * REC_F4 + REC_CULL];
     }
 }
 
@@ -45,76 +49,105 @@ __device__ __forceinline__ float finish_pair(const int mode, const float ov, con
     return ov;
 }
 
-// ---- wide matrices: a CTA owns 64 rows x up to 256 columns ----------------------------------------
-constexpr int SK_ROWS = 64, SK_COLS = 256, SK_TROWS = 32, SK_TCOLS = 64;
+// ---- wide matrices: a CTA owns 64 rows x cols_per_cta columns --------------------------------------
+constexpr int SK_ROWS = 64, SK_TROWS = 32, SK_TCOLS = 64;
+constexpr int SK_SHIFT = 20;  // queue code = row << 20 | (column - first column of the CTA)
+constexpr int SK_MAX_COLS = 1 << SK_SHIFT;
 
 struct StripSmem {
     static constexpr size_t a_bytes = (size_t)SK_ROWS * REC_F4 * sizeof(float4);
-    static constexpr size_t b_bytes = (size_t)SK_COLS * REC_F4 * sizeof(float4);
-    static constexpr size_t total = a_bytes + b_bytes + DrainSmem::total;
+    static constexpr size_t total = a_bytes + ST_SLAB_BYTES + (size_t)(ST_QCAP + ST_RARECAP) * sizeof(uint32_t);
 };
 
 template <int FL>
 __global__ void __launch_bounds__(ST_THREADS, 3)
-    iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int64_t m,
-                     float* __restrict__ out, const int64_t ld, const int mode, const int64_t strips_m) {
+    iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
+                     const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
+                     const int mode, const int cols_per_cta, const int64_t strips_m) {
     constexpr int NT = ST_THREADS;
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
-    float4* sB = sA + SK_ROWS * REC_F4;
-    float2* slab = reinterpret_cast<float2*>(sB + SK_COLS * REC_F4);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
-    uint16_t* rareq = queue + ST_QCAP;
+    float2* slab = reinterpret_cast<float2*>(sA + SK_ROWS * REC_F4);
+    uint32_t* queue = reinterpret_cast<uint32_t*>(slab + 8 * NT);
+    uint32_t* rareq = queue + ST_QCAP;
     __shared__ int qcount, rcount;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t strip = blockIdx.x;
     const int64_t sn = strip / strips_m, sm = strip - sn * strips_m;
-    const int64_t row0 = sn * SK_ROWS, col0 = sm * SK_COLS;
-    const int na = (int)min((int64_t)SK_ROWS, n - row0), nb = (int)min((int64_t)SK_COLS, m - col0);
+    const int64_t row0 = sn * SK_ROWS, col0 = sm * cols_per_cta;
+    const int na = (int)min((int64_t)SK_ROWS, n - row0), nb = (int)min((int64_t)cols_per_cta, m - col0);
     const int ntiles = 2 * ((nb + SK_TCOLS - 1) / SK_TCOLS);  // (column tile, row half)
 
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
-    for (int e = tid; e < nb * REC_F4; e += NT) sB[e] = __ldg(rec_b + col0 * REC_F4 + e);
     if (tid == 0) {
         qcount = 0;
         rcount = 0;
     }
+    const float4* const gB = rec_b + col0 * REC_F4;
+    const float4* const gcull = cull_b + col0;
     float* const outb = out + row0 * ld + col0;
     auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
         __stcs(outb + (int64_t)r * ld + c, finish_pair(mode, ov, A, B));
     };
 
     const int rsub = warp >> 1, cbase = (warp & 1) * 32;
+    float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cbase + lane < nb) bc = __ldg(gcull + cbase + lane);
     for (int t = 0;; t++) {  // one extra trip for the final drain (a single drain call site keeps the code small)
         __syncthreads();
-        const int qn = qcount;
+        const int qn = qcount, rn = rcount;
         __syncthreads();
         const bool last = t == ntiles;
         if (last || qn > ST_QCAP - SK_TROWS * SK_TCOLS) {  // the next tile could overflow the queue: drain first
-            drain_pairs<FL, 8>(sA, sB, slab, queue, qn, rareq, &rcount, emit);
-            if (last) break;
+            if (rn + qn > ST_RARECAP) {  // (rarely) make room in the rare queue first
+                drain_rare<FL, SK_SHIFT>(sA, gB, slab, rareq, &rcount, emit);
+                __syncthreads();
+            }
+            drain_main<FL, SK_SHIFT>(sA, gB, slab, queue, qn, rareq, &rcount, emit);
+            if (last) {
+                __syncthreads();
+                drain_rare<FL, SK_SHIFT>(sA, gB, slab, rareq, &rcount, emit);
+                break;
+            }
             if (tid == 0) qcount = 0;
             __syncthreads();
         }
-        const int rbase = (t & 1) * SK_TROWS + rsub;
-        if ((t & 1) * SK_TROWS >= na) continue;  // CTA-uniform
-        const int c = (t >> 1) * SK_TCOLS + cbase + lane;
-        const bool cvalid = c < nb;
-        const float4 bc = cvalid ? sB[c * REC_F4 + REC_CULL] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float* outp = outb + (int64_t)rbase * ld + c;
-        unsigned mk[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int r = rbase + 4 * k;
-            bool surv = false;
-            if (cvalid && r < na) {
-                surv = cull_survives(sA[r * REC_F4 + REC_CULL], bc);
-                if (!surv) __stcs(outp + (int64_t)(4 * k) * ld, 0.f);  // culled: exactly +0.0, written once, coalesced
-            }
-            mk[k] = __ballot_sync(0xffffffffu, surv);
+        const int c = (t >> 1) * SK_TCOLS + cbase + lane;  // column relative to col0
+        const float4 bcur = bc;
+        if (t & 1) {  // both row halves of this column tile use bcur; fetch the next tile's quad now
+            const int cn = c + SK_TCOLS;
+            bc = cn < nb ? __ldg(gcull + cn) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        push_survivors<8, 8>(mk, lane, rbase, 4, c, &qcount, queue);
+        const int rhalf = (t & 1) * SK_TROWS;
+        if (rhalf >= na) continue;  // CTA-uniform
+        const int rbase = rhalf + rsub;
+        float* outp = outb + (int64_t)rbase * ld + c;
+        const int64_t ostep = 4 * ld;
+        unsigned mk[8];
+        if (rhalf + SK_TROWS <= na && (t >> 1) * SK_TCOLS + SK_TCOLS <= nb) {  // full tile (CTA-uniform): no bounds tests
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const bool surv = cull_survives(sA[(rbase + 4 * k) * REC_F4 + REC_CULL], bcur);
+                if (!surv) __stcs(outp, 0.f);  // culled: exactly +0.0, written once, coalesced
+                outp += ostep;
+                mk[k] = __ballot_sync(0xffffffffu, surv);
+            }
+        } else {
+            const bool cvalid = c < nb;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int r = rbase + 4 * k;
+                bool surv = false;
+                if (cvalid && r < na) {
+                    surv = cull_survives(sA[r * REC_F4 + REC_CULL], bcur);
+                    if (!surv) __stcs(outp, 0.f);
+                }
+                outp += ostep;
+                mk[k] = __ballot_sync(0xffffffffu, surv);
+            }
+        }
+        push_survivors<SK_SHIFT, 8>(mk, lane, rbase, 4, c, &qcount, queue);
     }
 }
 
@@ -126,7 +159,7 @@ constexpr int FLAT_UNROLL = 8;
 struct FlatSmem {
     static constexpr size_t a_bytes = (size_t)FLAT_ROWS * REC_F4 * sizeof(float4);
     static constexpr size_t b_bytes = (size_t)FLAT_COLS * REC_F4 * sizeof(float4);
-    static constexpr size_t total = a_bytes + b_bytes + DrainSmem::total;
+    static constexpr size_t total = a_bytes + b_bytes + ST_SLAB_BYTES + (size_t)(ST_QCAP + ST_RARECAP) * sizeof(uint16_t);
 };
 
 template <int FL>
@@ -159,12 +192,20 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     const int npairs = na * m;  // <= 16384
     for (int chunk = 0;; chunk += FLAT_UNROLL * NT) {
         __syncthreads();
-        const int qn = qcount;
+        const int qn = qcount, rn = rcount;
         __syncthreads();
         const bool last = chunk >= npairs;
         if (last || qn > ST_QCAP - FLAT_UNROLL * NT) {
-            drain_pairs<FL, 6>(sA, sB, slab, queue, qn, rareq, &rcount, emit);
-            if (last) break;
+            if (rn + qn > ST_RARECAP) {
+                drain_rare<FL, 6>(sA, sB, slab, rareq, &rcount, emit);
+                __syncthreads();
+            }
+            drain_main<FL, 6>(sA, sB, slab, queue, qn, rareq, &rcount, emit);
+            if (last) {
+                __syncthreads();
+                drain_rare<FL, 6>(sA, sB, slab, rareq, &rcount, emit);
+                break;
+            }
             if (tid == 0) qcount = 0;
             __syncthreads();
         }
@@ -183,10 +224,13 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
             }
             mk[k] = __ballot_sync(0xffffffffu, surv);
         }
-        int total = 0;
+        unsigned any = 0u;
 #pragma unroll
-        for (int k = 0; k < FLAT_UNROLL; k++) total += __popc(mk[k]);
-        if (total) {
+        for (int k = 0; k < FLAT_UNROLL; k++) any |= mk[k];
+        if (any) {
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < FLAT_UNROLL; k++) total += __popc(mk[k]);
             int base = 0;
             if (lane == 0) base = atomicAdd(&qcount, total);
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -228,8 +272,9 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
                    cudaStream_t st) {
     float4* ra = reinterpret_cast<float4*>(ws);
     float4* rb = ra + n * REC_F4;
+    float4* cb = rb + m * REC_F4;
     const int64_t total = n + m;
-    prep_kernel<FL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb);
+    prep_kernel<FL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb, cb);
     int rc = check_launch("prep_kernel");
     if (rc) return rc;
     if (m <= FLAT_COLS) {
@@ -244,7 +289,15 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         kern<<<(unsigned)ctas, ST_THREADS, FlatSmem::total, st>>>(ra, n, rb, (int)m, out, ld, mode, inv_m);
         return check_launch("iou_flat_kernel");
     }
-    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS, strips_m = (m + SK_COLS - 1) / SK_COLS;
+    // columns per CTA: as long a run as still leaves >= ~16 CTAs per SM-slot for load balance (148 SMs x 3 CTAs)
+    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS;
+    int64_t want_m = (16 * 444 + strips_n - 1) / strips_n;  // column splits wanted
+    if (want_m < 1) want_m = 1;
+    int64_t cols = (m + want_m - 1) / want_m;
+    cols = (cols + SK_TCOLS - 1) / SK_TCOLS * SK_TCOLS;
+    if (cols < 4 * SK_TCOLS) cols = 4 * SK_TCOLS;
+    if (cols > SK_MAX_COLS) cols = SK_MAX_COLS;
+    const int64_t strips_m = (m + cols - 1) / cols;
     const int64_t strips = strips_n * strips_m;
     if (strips > 0x7fffffffLL) {
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
@@ -252,7 +305,7 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
     }
     auto kern = iou_strip_kernel<FL>;
     if ((rc = set_smem(kern, StripSmem::total))) return rc;
-    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, m, out, ld, mode, strips_m);
+    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m);
     return check_launch("iou_strip_kernel");
 }
 
@@ -269,7 +322,7 @@ static int iou_entry(const float* a, int64_t n, const float* b, int64_t m, float
 
 extern "C" size_t lg_iou_workspace_bytes(int64_t n, int64_t m) {
     if (n < 0 || m < 0) return 0;
-    return (size_t)(n + m) * lg::REC_F4 * sizeof(float4) + 16;
+    return (size_t)(n + m) * lg::REC_F4 * sizeof(float4) + (size_t)m * sizeof(float4) + 16;
 }
 
 extern "C" int lg_boxes_overlap_bev(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws,

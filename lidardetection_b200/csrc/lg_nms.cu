@@ -22,7 +22,7 @@ namespace lg {
 
 constexpr int NMS_THREADS = 256;
 constexpr int NMS_TILE = 64;
-constexpr size_t NMS_STATS_BYTES = 256;  // two u64 counters (pairs tested, pairs through the polygon path), padded
+constexpr size_t NMS_STATS_BYTES = 256;  // three u64 counters (pairs cull-tested, pairs through the polygon path, pairs with non-zero overlap), padded
 
 __device__ __forceinline__ int problem_count(const int32_t* __restrict__ counts, int p, int nmax) {
     int n = counts ? counts[p] : nmax;
@@ -60,7 +60,7 @@ __device__ __forceinline__ void tri_decode(int t, int nb, int& rb, int& cb) {
 struct NmsSmem {
     static constexpr size_t rec_bytes = (size_t)2 * NMS_TILE * REC_F4 * sizeof(float4);
     static constexpr size_t mask_bytes = (size_t)NMS_TILE * sizeof(unsigned long long);
-    static constexpr size_t total = rec_bytes + DrainSmem::total + mask_bytes;
+    static constexpr size_t total = rec_bytes + ST_SLAB_BYTES + (size_t)(ST_QCAP + ST_RARECAP) * sizeof(uint16_t) + mask_bytes;
 };
 
 template <int FL>
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 3)
     float2* slab = reinterpret_cast<float2*>(sB + T * REC_F4);
     uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
     uint16_t* rareq = queue + ST_QCAP;
-    unsigned int* smask = reinterpret_cast<unsigned int*>(rareq + ST_QCAP);  // 64 x (lo, hi)
+    unsigned int* smask = reinterpret_cast<unsigned int*>(rareq + ST_RARECAP);  // 64 x (lo, hi)
     __shared__ int qcount, rcount;
 
     const int p = blockIdx.y;
@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 3)
         const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);
         if (iou > thresh) atomicOr(&smask[2 * r + (c >> 5)], 1u << (c & 31));
     };
-    drain_pairs<FL, 8>(sA, sB, slab, queue, qcount, rareq, &rcount, emit);
+    drain_main<FL, 8>(sA, sB, slab, queue, qcount, rareq, &rcount, emit);
+    __syncthreads();
+    drain_rare<FL, 8>(sA, sB, slab, rareq, &rcount, emit);
     __syncthreads();
 
     if (tid < na) {
@@ -261,10 +263,12 @@ __global__ void __launch_bounds__(32)
 //             the others are kept and their rows are OR-ed out of the alive bitmap.
 // Every IoU that decides anything is iou_bev(kept box, later box) exactly as in the mask formulation, so the
 // keep list is identical; the work drops from N^2/2 pairs to about (#kept + failed speculations) x N.
-constexpr int LZ_G = 8;        // speculative candidates per pass
-constexpr int LZ_QCAP = 4096;  // u32 codes: candidate << 16 | box
-constexpr int LZ_CACHE = 4096; // cull quads cached in smem; boxes beyond read theirs from the records (L2)
-constexpr int LZ_SWEEP = ST_THREADS;  // columns per sweep of the 8 warps
+constexpr int LZ_THREADS = 512;  // one problem is latency-bound: 16 warps hide the polygon path's dependency chains
+constexpr int LZ_G = 8;          // speculative candidates per pass
+constexpr int LZ_QCAP = 8192;    // u32 codes: candidate << 16 | box
+constexpr int LZ_RARECAP = LZ_QCAP + 1024;
+constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
+constexpr int LZ_SWEEP = LZ_THREADS;  // columns per sweep of the 16 warps
 
 struct LazyLayout {
     int words;         // alive words
@@ -275,11 +279,11 @@ struct LazyLayout {
         off_cull = o;
         o += (size_t)(nmax < LZ_CACHE ? nmax : LZ_CACHE) * sizeof(float4);
         off_slab = o;
-        o += DrainSmem::slab_bytes;
+        o += (size_t)8 * LZ_THREADS * sizeof(float2);
         off_queue = o;
         o += (size_t)LZ_QCAP * sizeof(uint32_t);
         off_rare = o;
-        o += (size_t)LZ_QCAP * sizeof(uint32_t);
+        o += (size_t)LZ_RARECAP * sizeof(uint32_t);
         off_alive = o;
         o += (size_t)words * sizeof(uint32_t);
         off_sup = o;
@@ -289,11 +293,11 @@ struct LazyLayout {
 };
 
 template <int FL>
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(LZ_THREADS, 1)
     nms_lazy_kernel(const float4* __restrict__ rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
                     const int nmax, const float thresh, int64_t* __restrict__ keep, int32_t* __restrict__ num_keep,
                     unsigned long long* __restrict__ stats) {
-    constexpr int NT = ST_THREADS, G = LZ_G;
+    constexpr int NT = LZ_THREADS, G = LZ_G;
     extern __shared__ float4 smem4[];
     const LazyLayout L(nmax);
     char* sm = reinterpret_cast<char*>(smem4);
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
     uint32_t* alive = reinterpret_cast<uint32_t*>(sm + L.off_alive);
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s;
-    __shared__ unsigned long long st_tested, st_heavy;
+    __shared__ unsigned long long st_tested, st_heavy, st_nonzero;
 
     const int p = blockIdx.x;
     const int n = problem_count(counts, p, nmax);
@@ -323,12 +327,14 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
         nk_s = 0;
         st_tested = 0ull;
         st_heavy = 0ull;
+        st_nonzero = 0ull;
     }
     int cursor = 0;  // every box below it is decided
-    unsigned my_tested = 0u;
+    unsigned my_tested = 0u, my_nonzero = 0u;
 
     auto emit = [&](int g, int j, float ov, const float4* A, const float4* B) {
         const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);  // row = the higher-scoring box (kernel.cu:304)
+        my_nonzero += ov > 0.f ? 1u : 0u;
         if (iou > thresh) atomicOr(&sup[g * W + (j >> 5)], 1u << (j & 31));
     };
 
@@ -372,17 +378,23 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
         }
         // ---- rows of the candidates against every later alive box, a chunk of columns at a time
         int jw = ((g0 + 1) >> 5) << 5;
-        while (jw < n) {
+        while (true) {
             __syncthreads();
-            const int qn = qcount;
+            const int qn = qcount, rn = rcount;
             __syncthreads();
             const int room = (LZ_QCAP - qn) / G;  // columns that cannot overflow the queue
-            if (room < LZ_SWEEP) {
-                drain_pairs<FL, 16>(sA, grec, slab, queue, qn, rareq, &rcount, emit);
+            const bool done = jw >= n;
+            if (done || room < LZ_SWEEP) {  // single drain call site: mid-row when the queue is full, and at the end of the rows
+                if (rn + qn > LZ_RARECAP) {
+                    drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
+                    __syncthreads();
+                }
+                drain_main<FL, 16, NT>(sA, grec, slab, queue, qn, rareq, &rcount, emit);
                 if (tid == 0) {
                     qcount = 0;
                     st_heavy += (unsigned long long)qn;
                 }
+                if (done) break;
                 continue;
             }
             const int sweeps = min(room / LZ_SWEEP, (n - jw + LZ_SWEEP - 1) / LZ_SWEEP);
@@ -407,14 +419,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
             jw += sweeps * LZ_SWEEP;
         }
         __syncthreads();
-        {
-            const int qn = qcount;
-            drain_pairs<FL, 16>(sA, grec, slab, queue, qn, rareq, &rcount, emit);
-            if (tid == 0) {
-                qcount = 0;
-                st_heavy += (unsigned long long)qn;
-            }
-        }
+        drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
         __syncthreads();
         // ---- resolve the speculation in score order (one thread; at most G*(G-1)/2 bit tests)
         if (tid == 0) {
@@ -455,10 +460,12 @@ __global__ void __launch_bounds__(ST_THREADS, 2)
     for (int i = nk + tid; i < nmax; i += NT) keep[base + i] = -1;
     if (stats) {
         atomicAdd(&st_tested, (unsigned long long)my_tested);
+        atomicAdd(&st_nonzero, (unsigned long long)my_nonzero);
         __syncthreads();
         if (tid == 0) {
             atomicAdd(stats, st_tested);
             atomicAdd(stats + 1, st_heavy);
+            atomicAdd(stats + 2, st_nonzero);
         }
     }
 }
@@ -526,10 +533,10 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
             const LazyLayout L(nmax);
             if (strict) {
                 if ((rc = set_smem(nms_lazy_kernel<0>, L.total))) return rc;
-                nms_lazy_kernel<0><<<P, ST_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
+                nms_lazy_kernel<0><<<P, LZ_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
             } else {
                 if ((rc = set_smem(nms_lazy_kernel<1>, L.total))) return rc;
-                nms_lazy_kernel<1><<<P, ST_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
+                nms_lazy_kernel<1><<<P, LZ_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
             }
             return check_launch("nms_lazy_kernel");
         }

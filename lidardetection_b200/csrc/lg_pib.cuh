@@ -1,0 +1,112 @@
+// lg_pib.cuh -- per-point / per-box pieces of points-in-boxes, shared by lg_points.cu and the host
+// emulation of the CPU-only test tier (tests/host_emu/).
+//
+// Predicate (check_pt_in_box3d, /root/reference/pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu:16-36),
+// reproduced bit-exactly:
+//     |z - cz| <= dz/2                      (closed; the reference compares in double, which for
+//                                            float operands equals the float compare against dz*0.5f)
+//     |lx| < dx/2 + MARGIN, |ly| < dy/2 + MARGIN   (open; compared in DOUBLE in the reference).
+//       For a float v and a double D,  (double)v < D  <=>  v < RU(D)  with RU = round-up to float,
+//       so the per-box thresholds are converted once (cvt.rp.f32.f64) and the per-point compare is FP32.
+//     lx = fma(sx, cosa, -(sy*sina)),  ly = fma(sy, cosa, sx*sina)    with cosa = cosf(-rz), sina = sinf(-rz)
+//       -- the contraction ptxas applies to lidar_to_local_coords on sm_100a (FL = 1); FL = 0 is the
+//       un-contracted CPU build.
+//
+// Spatial cull (new): a uniform BEV grid over the frame's boxes; every cell holds a bit mask of the boxes
+// whose conservative footprint touches it.  A point looks up its cell and tests only those boxes, lowest
+// index first -- the reference's "first box wins" order.  The footprint bound is derived below and is
+// checked against the brute-force oracle by tests/test_host_emu.py.
+#pragma once
+#include "lg_geom.cuh"
+
+namespace lg {
+
+// record: r0 = (cx, cy, cz, dz/2)   r1 = (cosa, sina, tx, ty)
+__device__ __forceinline__ void make_pib_record(const float* __restrict__ box, const float margin, float4& r0, float4& r1) {
+    const float cx = box[0], cy = box[1], cz = box[2], dx = box[3], dy = box[4], dz = box[5], rz = box[6];
+    const float cosa = LG_COSF(-rz), sina = LG_SINF(-rz);
+    const float tx = __double2float_ru((double)dx / 2.0 + (double)margin);
+    const float ty = __double2float_ru((double)dy / 2.0 + (double)margin);
+    // (double)|z-cz| > (double)dz/2.0  <=>  |z-cz| > RD(dz/2); dz/2 is exact in float except for
+    // subnormal underflow, where round-down keeps the equivalence.
+    const float hz = __double2float_rd((double)dz / 2.0);
+    r0 = make_float4(cx, cy, cz, hz);
+    r1 = make_float4(cosa, sina, tx, ty);
+}
+
+template <int FL>
+__device__ __forceinline__ bool pt_in_box(const float x, const float y, const float z, const float4 r0, const float4 r1) {
+    if (fabsf(z - r0.z) > r0.w) return false;
+    const float sx = x - r0.x, sy = y - r0.y;
+    const float lx = msub<FL>(sx, r1.x, sy, r1.y);
+    const float ly = madd_second<FL>(sx, r1.y, sy, r1.x);
+    return (fabsf(lx) < r1.z) & (fabsf(ly) < r1.w);
+}
+
+// Conservative BEV footprint of a box: every point the predicate accepts satisfies
+//     |x - cx| <= ex  and  |y - cy| <= ey.
+// Proof sketch.  With c = cosa, s = sina (|c^2 + s^2 - 1| < 4e-7) and the exact lx* = sx c - sy s,
+// ly* = sy c + sx s:  sx = (lx* c + ly* s)/(c^2+s^2).  The computed lx, ly differ from lx*, ly* by at most
+// 2e-7 (|sx| + |sy|), and acceptance needs |lx| < tx, |ly| < ty, hence |sx| <= E + 1.2e-6 (E + F) with
+// E = tx|c| + ty|s|, F = ty|c| + tx|s|; sx itself is x - cx rounded (6e-8 relative).  The slack below
+// (1e-4 relative, 4e-7 |centre| for the rounding of cx +- ex) is two orders of magnitude above that.
+// Returns false when the box can never contain a point (tx or ty <= 0, or a NaN anywhere);
+// `bounded` is cleared when the footprint is not finite (the caller then falls back to testing every box).
+__device__ __forceinline__ bool pib_footprint(const float4 r0, const float4 r1, float& ex, float& ey, bool& bounded) {
+    const float c = fabsf(r1.x), s = fabsf(r1.y), tx = r1.z, ty = r1.w;
+    if (!(tx > 0.f) || !(ty > 0.f) || !(c == c) || !(s == s) || !(r0.x == r0.x) || !(r0.y == r0.y)) {
+        ex = ey = 0.f;
+        return false;  // fabsf(l) < t is false for t <= 0 and for any NaN operand
+    }
+    const float E = tx * c + ty * s, F = ty * c + tx * s;
+    const float slack = 1e-4f * (E + F);
+    ex = E + slack + 4e-7f * fabsf(r0.x);
+    ey = F + slack + 4e-7f * fabsf(r0.y);
+    if (!(ex < 1e18f) || !(ey < 1e18f) || !(fabsf(r0.x) < 1e18f) || !(fabsf(r0.y) < 1e18f)) bounded = false;
+    return true;
+}
+
+struct PibGrid {
+    float x0, y0, invx, invy;  // cell(x) = trunc((x - x0) * invx), valid iff 0 <= (x - x0) * invx < nx
+    int nx, ny;
+};
+
+// Grid over [X0, X1] x [Y0, Y1] with at most ncap cells; mean_ext = mean footprint half-extent of the boxes
+// (cells much smaller than the boxes only make the marking pass longer).
+__device__ __forceinline__ PibGrid pib_make_grid(float X0, float X1, float Y0, float Y1, float mean_ext, int ncap) {
+    PibGrid g;
+    g.x0 = X0;
+    g.y0 = Y0;
+    const float wx = fmaxf(X1 - X0, 1e-6f * (fabsf(X0) + fabsf(X1)) + 1e-20f);
+    const float wy = fmaxf(Y1 - Y0, 1e-6f * (fabsf(Y0) + fabsf(Y1)) + 1e-20f);
+    float cell = fmaxf(sqrtf(wx * wy / (float)ncap), 0.66f * mean_ext);
+    cell = fmaxf(cell, 1e-20f);
+    int nx = (int)fminf(ceilf(wx / cell), (float)ncap);
+    int ny = (int)fminf(ceilf(wy / cell), (float)ncap);
+    nx = max(nx, 1);
+    ny = max(ny, 1);
+    while ((long long)nx * ny > ncap) {  // rounding up twice can overshoot the capacity
+        if (nx >= ny) nx = max(1, nx - 1);
+        else ny = max(1, ny - 1);
+    }
+    g.nx = nx;
+    g.ny = ny;
+    // slightly under nx / wx so that X1 itself still maps below nx
+    g.invx = (float)nx / wx * 0.99999f;
+    g.invy = (float)ny / wy * 0.99999f;
+    return g;
+}
+
+// the ONE mapping from a coordinate to a (fractional) cell coordinate; both the marking pass and the point
+// lookup go through it, and it is monotone in v, so a point inside [lo, hi] lands in a cell inside
+// [cell(lo), cell(hi)]
+__device__ __forceinline__ float pib_cellf(float v, float origin, float inv) { return __fmul_rn(__fsub_rn(v, origin), inv); }
+
+__device__ __forceinline__ int pib_cell_clamped(float v, float origin, float inv, int n) {
+    const float f = pib_cellf(v, origin, inv);
+    if (!(f > 0.f)) return 0;  // also NaN
+    if (f >= (float)n) return n - 1;
+    return (int)f;
+}
+
+}  // namespace lg

@@ -2,88 +2,247 @@
 //
 // Replaces points_in_boxes_kernel + launcher (/root/reference/pcdet/ops/roiaware_pool3d/src/
 // roiaware_pool3d_kernel.cu:16-36, 313-359) and offers the all-pairs mask form of points_in_boxes_cpu
-// (roiaware_pool3d.cpp:121-168) on the GPU.
+// (roiaware_pool3d.cpp:121-168) on the GPU.  The predicate and its bit-exactness argument are in lg_pib.cuh.
 //
-// Predicate (check_pt_in_box3d), reproduced bit-exactly:
-//     |z - cz| <= dz/2                      (closed; the reference compares in double, which for
-//                                            float operands equals the float compare against dz*0.5f)
-//     |lx| < dx/2 + MARGIN, |ly| < dy/2 + MARGIN   (open; compared in DOUBLE in the reference).
-//       For a float v and a double D,  (double)v < D  <=>  v < RU(D)  with RU = round-up to float,
-//       so the per-box thresholds are converted once (cvt.rp.f32.f64) and the per-point compare is FP32.
-//     lx = fma(sx, cosa, -(sy*sina)),  ly = fma(sy, cosa, sx*sina)    with cosa = cosf(-rz), sina = sinf(-rz)
-//       -- the contraction ptxas applies to lidar_to_local_coords on sm_100a (FL = 1); FL = 0 is the
-//       un-contracted CPU build.
-// Per-box trigonometry and thresholds are hoisted into a 32-byte record kept in shared memory.
+// Index form (B frames x M points x T boxes -> first containing box or -1): the reference does M*T predicate
+// evaluations with per-pair trigonometry; here a CTA
+//   1. builds the T 32-byte box records (trigonometry hoisted) and their conservative BEV footprints,
+//   2. lays a uniform grid over the frame's boxes in shared memory -- one bit mask of candidate boxes per cell
+//      (48 KB: 3072 cells at T <= 128) -- with one warp per box marking the cells its footprint touches,
+//   3. streams its points through shared memory with 1-D bulk async copies (TMA, cp.async.bulk + mbarrier,
+//      three 12 KB stages in flight per CTA) and, per point, tests only the boxes of the point's cell in
+//      ascending index order.
+// HBM traffic is the algorithmic 16 B per point (+ 28 T per CTA); the kernel is HBM-bound when the batch is
+// large enough to fill the machine.  Frames whose boxes have a non-finite footprint fall back to
+// testing every box.
 #include "lg_common.cuh"
-#include "lg_geom.cuh"
+#include "lg_pib.cuh"
 
 namespace lg {
 
 constexpr int PIB_THREADS = 256;
-constexpr int PIB_PPT = 4;  // points per thread
+constexpr int PIB_TILE = 1024;                 // points per stage (4 per thread)
+constexpr int PIB_STAGES = 3;
+constexpr int PIB_TILE_BYTES = PIB_TILE * 12;  // 12 KB
+constexpr int PIB_GRID_WORDS = 12288;          // 48 KB of cell masks
 
-// record: (cx, cy, cz, dz/2) (cosa, sina, tx, ty)
-__device__ __forceinline__ void make_pib_record(const float* __restrict__ box, const float margin, float4& r0, float4& r1) {
-    const float cx = box[0], cy = box[1], cz = box[2], dx = box[3], dy = box[4], dz = box[5], rz = box[6];
-    const float cosa = cosf(-rz), sina = sinf(-rz);
-    const float tx = __double2float_ru((double)dx / 2.0 + (double)margin);
-    const float ty = __double2float_ru((double)dy / 2.0 + (double)margin);
-    // (double)|z-cz| > (double)dz/2.0  <=>  |z-cz| > RD(dz/2); dz/2 is exact in float except for
-    // subnormal underflow, where round-down keeps the equivalence.
-    const float hz = __double2float_rd((double)dz / 2.0);
-    r0 = make_float4(cx, cy, cz, hz);
-    r1 = make_float4(cosa, sina, tx, ty);
+// ---- mbarrier / bulk-copy wrappers (PTX ISA: cp.async.bulk, mbarrier) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct PibSmem {
+    // dynamic smem layout: [stages][grid][records]
+    static constexpr size_t stage_bytes = (size_t)PIB_STAGES * PIB_TILE_BYTES;
+    static constexpr size_t grid_bytes = (size_t)PIB_GRID_WORDS * sizeof(uint32_t);
+    static size_t total(int T) { return stage_bytes + grid_bytes + (size_t)T * 2 * sizeof(float4); }
+};
+
+template <int FL>
+__device__ __forceinline__ int first_box_in_cell(const uint32_t* __restrict__ cw, const int W, const float4* __restrict__ srec,
+                                                 const float x, const float y, const float z) {
+    for (int w = 0; w < W; w++) {
+        uint32_t bits = cw[w];
+        while (bits) {
+            const int k = (w << 5) + __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) return k;  // ascending index: lowest box wins
+        }
+    }
+    return -1;
 }
 
 template <int FL>
-__device__ __forceinline__ bool pt_in_box(const float x, const float y, const float z, const float4 r0, const float4 r1) {
-    if (fabsf(z - r0.z) > r0.w) return false;
-    const float sx = x - r0.x, sy = y - r0.y;
-    const float lx = msub<FL>(sx, r1.x, sy, r1.y);
-    const float ly = madd_second<FL>(sx, r1.y, sy, r1.x);
-    return (fabsf(lx) < r1.z) & (fabsf(ly) < r1.w);
-}
+__global__ void __launch_bounds__(PIB_THREADS, 2)
+    pib_grid_kernel(const float* __restrict__ boxes, const float* __restrict__ pts, int32_t* __restrict__ out, const int T,
+                    const int64_t M, const int64_t pts_per_cta) {
+    constexpr int NT = PIB_THREADS;
+    extern __shared__ float4 smem4[];
+    float* stage = reinterpret_cast<float*>(smem4);
+    uint32_t* grid = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem4) + PibSmem::stage_bytes);
+    float4* srec = reinterpret_cast<float4*>(grid + PIB_GRID_WORDS);
+    __shared__ uint64_t bars[PIB_STAGES];
+    __shared__ float red[8][6];
+    __shared__ PibGrid sgrid;
+    __shared__ int s_use_grid, s_nvalid;
 
-template <int FL>
-__global__ void __launch_bounds__(PIB_THREADS)
-    pib_idx_kernel(const float* __restrict__ boxes, const float* __restrict__ pts, int32_t* __restrict__ out, const int T,
-                   const int64_t M) {
-    extern __shared__ float4 srec[];  // 2 * T
-    const int b = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t p_begin = (int64_t)blockIdx.x * pts_per_cta;
+    const int64_t p_end = min(M, p_begin + pts_per_cta);
+    const int64_t npts = p_end - p_begin;
+    const float* gp = pts + ((int64_t)b * M + p_begin) * 3;
+    int32_t* go = out + (int64_t)b * M + p_begin;
+    const int ntiles = (int)((npts + PIB_TILE - 1) / PIB_TILE);
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(gp) & 15) == 0;  // bulk copies need 16-byte aligned sources
+
+    auto tile_bytes = [&](int t) -> unsigned { return (unsigned)(min((int64_t)PIB_TILE, npts - (int64_t)t * PIB_TILE) * 12); };
+    auto issue = [&](int t) {  // thread 0 only; a tile whose byte count is not a multiple of 16 is loaded by the fallback
+        const unsigned bytes = tile_bytes(t);
+        if (tma_ok && (bytes & 15) == 0) {
+            uint64_t* bar = &bars[t % PIB_STAGES];
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(stage + (size_t)(t % PIB_STAGES) * (PIB_TILE * 3), gp + (int64_t)t * PIB_TILE * 3, bytes, bar);
+        }
+    };
+    if (tid == 0) {
+        for (int s = 0; s < PIB_STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int t = 0; t < min(ntiles, PIB_STAGES); t++) issue(t);  // the points start flowing while the grid is built
+    }
+
+    // ---- 1. records, footprints, frame bounds
     const float* fb = boxes + (int64_t)b * T * 7;
-    for (int k = tid; k < T; k += PIB_THREADS) {
+    float lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY, sum_ext = 0.f, nvalid = 0.f;
+    bool bounded = true;
+    for (int k = tid; k < T; k += NT) {
         float4 r0, r1;
         make_pib_record(fb + k * 7, 1e-5f, r0, r1);
         srec[2 * k] = r0;
         srec[2 * k + 1] = r1;
-    }
-    __syncthreads();
-    const int64_t p0 = (int64_t)blockIdx.x * (PIB_THREADS * PIB_PPT) + tid;
-    const float* fp = pts + (int64_t)b * M * 3;
-    float x[PIB_PPT], y[PIB_PPT], z[PIB_PPT];
-    int res[PIB_PPT];
-#pragma unroll
-    for (int u = 0; u < PIB_PPT; u++) {
-        const int64_t p = p0 + (int64_t)u * PIB_THREADS;
-        res[u] = -1;
-        x[u] = y[u] = z[u] = 0.f;
-        if (p < M) {
-            x[u] = __ldg(fp + p * 3);
-            y[u] = __ldg(fp + p * 3 + 1);
-            z[u] = __ldg(fp + p * 3 + 2);
+        float ex, ey;
+        if (pib_footprint(r0, r1, ex, ey, bounded)) {
+            lo_x = fminf(lo_x, r0.x - ex);
+            hi_x = fmaxf(hi_x, r0.x + ex);
+            lo_y = fminf(lo_y, r0.y - ey);
+            hi_y = fmaxf(hi_y, r0.y + ey);
+            sum_ext += 0.5f * (ex + ey);
+            nvalid += 1.f;
         }
     }
-    for (int k = 0; k < T; k++) {
-        const float4 r0 = srec[2 * k], r1 = srec[2 * k + 1];
+    const unsigned all_bounded = __ballot_sync(0xffffffffu, bounded) == 0xffffffffu;
 #pragma unroll
-        for (int u = 0; u < PIB_PPT; u++)
-            if (res[u] < 0 && pt_in_box<FL>(x[u], y[u], z[u], r0, r1)) res[u] = k;  // lowest index wins
+    for (int d = 16; d > 0; d >>= 1) {
+        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, d));
+        hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, d));
+        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, d));
+        hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, d));
+        sum_ext += __shfl_xor_sync(0xffffffffu, sum_ext, d);
+        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
     }
+    if (lane == 0) {
+        red[warp][0] = lo_x;
+        red[warp][1] = hi_x;
+        red[warp][2] = lo_y;
+        red[warp][3] = hi_y;
+        red[warp][4] = sum_ext;
+        red[warp][5] = all_bounded ? nvalid : -1e30f;  // poison: any unbounded box disables the grid
+    }
+    for (int w = tid; w < PIB_GRID_WORDS; w += NT) grid[w] = 0u;
+    __syncthreads();
+    const int W = (T + 31) >> 5;
+    if (tid == 0) {
+        float a = INFINITY, bb = -INFINITY, c = INFINITY, d = -INFINITY, se = 0.f, nv = 0.f;
+        for (int w = 0; w < NT / 32; w++) {
+            a = fminf(a, red[w][0]);
+            bb = fmaxf(bb, red[w][1]);
+            c = fminf(c, red[w][2]);
+            d = fmaxf(d, red[w][3]);
+            se += red[w][4];
+            nv += red[w][5];
+        }
+        const bool ok = nv >= 0.f && W <= PIB_GRID_WORDS;  // (a frame with more than 393,216 boxes cannot get here)
+        s_use_grid = ok ? 1 : 0;
+        s_nvalid = nv > 0.f ? 1 : 0;
+        if (ok && nv > 0.f) sgrid = pib_make_grid(a, bb, c, d, se / nv, PIB_GRID_WORDS / W);
+    }
+    __syncthreads();
+    const bool use_grid = s_use_grid != 0, any_valid = s_nvalid != 0;
+    const PibGrid g = sgrid;
+
+    // ---- 2. mark the cells each footprint touches: one warp per box
+    if (use_grid && any_valid) {
+        for (int k = warp; k < T; k += NT / 32) {
+            const float4 r0 = srec[2 * k], r1 = srec[2 * k + 1];
+            float ex, ey;
+            bool dummy = true;
+            if (!pib_footprint(r0, r1, ex, ey, dummy)) continue;  // warp-uniform
+            const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
+            const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
+            const int ncx = ix1 - ix0 + 1, total = ncx * (iy1 - iy0 + 1);
+            const uint32_t bit = 1u << (k & 31);
+            for (int c = lane; c < total; c += 32) {
+                const int cy = c / ncx, cx = c - cy * ncx;
+                atomicOr(&grid[((iy0 + cy) * g.nx + ix0 + cx) * W + (k >> 5)], bit);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 3. the points, a tile per trip, four consecutive points per thread
+    for (int t = 0; t < ntiles; t++) {
+        const int s = t % PIB_STAGES;
+        float* sp = stage + (size_t)s * (PIB_TILE * 3);
+        const unsigned bytes = tile_bytes(t);
+        const int np = (int)(bytes / 12);
+        if (tma_ok && (bytes & 15) == 0) {
+            mbar_wait(&bars[s], (unsigned)((t / PIB_STAGES) & 1));
+        } else {
+            const float* src = gp + (int64_t)t * PIB_TILE * 3;
+            for (int i = tid; i < np * 3; i += NT) sp[i] = __ldg(src + i);
+            __syncthreads();
+        }
+        const int i0 = tid * 4;
+        if (i0 < np) {
+            float v[12];
+            if (i0 + 4 <= np) {
+                const float4* q = reinterpret_cast<const float4*>(sp + i0 * 3);  // 48-byte stride: conflict-free LDS.128
+                const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y;
+                v[6] = q1.z; v[7] = q1.w; v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
+            } else {
 #pragma unroll
-    for (int u = 0; u < PIB_PPT; u++) {
-        const int64_t p = p0 + (int64_t)u * PIB_THREADS;
-        if (p < M) out[(int64_t)b * M + p] = res[u];
+                for (int u = 0; u < 12; u++) v[u] = (i0 * 3 + u < np * 3) ? sp[i0 * 3 + u] : 0.f;
+            }
+            int res[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float x = v[3 * u], y = v[3 * u + 1], z = v[3 * u + 2];
+                int r = -1;
+                if (use_grid) {
+                    const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
+                    if (any_valid && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny)
+                        r = first_box_in_cell<FL>(grid + ((int)fy * g.nx + (int)fx) * W, W, srec, x, y, z);
+                } else {
+                    for (int k = 0; k < T; k++)
+                        if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
+                            r = k;
+                            break;
+                        }
+                }
+                res[u] = r;
+            }
+            int32_t* o = go + (int64_t)t * PIB_TILE + i0;
+            if (i0 + 4 <= np && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                __stcs(reinterpret_cast<int4*>(o), make_int4(res[0], res[1], res[2], res[3]));
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (i0 + u < np) o[u] = res[u];
+            }
+        }
+        __syncthreads();  // everyone is done with this stage: refill it
+        if (tid == 0 && t + PIB_STAGES < ntiles) issue(t + PIB_STAGES);
     }
 }
 
@@ -138,17 +297,31 @@ extern "C" int lg_points_in_boxes(const float* boxes, const float* pts, int32_t*
         return LG_ERR_TOO_LARGE;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t smem = (size_t)T * 2 * sizeof(float4);
-    dim3 grid((unsigned)((M + PIB_THREADS * PIB_PPT - 1) / (PIB_THREADS * PIB_PPT)), B);
+    // points per CTA: a whole frame when the batch alone fills the machine (the grid is built once per CTA),
+    // otherwise split the frame, but never below 4 tiles, so that the build stays a small part of the work
+    const int64_t tiles = (M + PIB_TILE - 1) / PIB_TILE;
+    int64_t split = 1;
+    if (B < 2 * 148 * 2) split = (2 * 148 * 2 + B - 1) / B;
+    int64_t tiles_per_cta = (tiles + split - 1) / split;
+    if (tiles_per_cta < 4) tiles_per_cta = tiles < 4 ? tiles : 4;
+    if (tiles_per_cta > 64) tiles_per_cta = 64;
+    const int64_t pts_per_cta = tiles_per_cta * PIB_TILE;
+    const int64_t gx = (M + pts_per_cta - 1) / pts_per_cta;
+    if (gx > 0x7fffffffLL) {
+        set_error("num_points=%lld exceeds the grid limit", (long long)M);
+        return LG_ERR_TOO_LARGE;
+    }
+    const size_t smem = PibSmem::total(T);
+    dim3 grid((unsigned)gx, B);
     int rc;
     if (flags & LG_FLAG_STRICT_FP32) {
-        if ((rc = set_smem(pib_idx_kernel<0>, smem))) return rc;
-        pib_idx_kernel<0><<<grid, PIB_THREADS, smem, st>>>(boxes, pts, out, T, M);
+        if ((rc = set_smem(pib_grid_kernel<0>, smem))) return rc;
+        pib_grid_kernel<0><<<grid, PIB_THREADS, smem, st>>>(boxes, pts, out, T, M, pts_per_cta);
     } else {
-        if ((rc = set_smem(pib_idx_kernel<1>, smem))) return rc;
-        pib_idx_kernel<1><<<grid, PIB_THREADS, smem, st>>>(boxes, pts, out, T, M);
+        if ((rc = set_smem(pib_grid_kernel<1>, smem))) return rc;
+        pib_grid_kernel<1><<<grid, PIB_THREADS, smem, st>>>(boxes, pts, out, T, M, pts_per_cta);
     }
-    return check_launch("pib_idx_kernel");
+    return check_launch("pib_grid_kernel");
 }
 
 extern "C" int lg_points_in_boxes_mask(const float* boxes, int64_t n, const float* pts, int64_t m, int32_t* out, float margin,

@@ -143,7 +143,7 @@ def nms_normal_gpu(boxes, scores, thresh, **kwargs):
     return _nms_single('lg_nms_normal_batched', boxes, scores, thresh, None)
 
 
-def _nms_batched(fn_name, boxes, scores, thresh, counts):
+def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE):
     assert boxes.dim() == 3 and boxes.shape[2] == 7 and scores.shape == boxes.shape[:2]
     b = boxes.contiguous().float()
     if counts is not None:
@@ -152,15 +152,18 @@ def _nms_batched(fn_name, boxes, scores, thresh, counts):
         scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
         counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
     order = scores.sort(1, descending=True)[1].contiguous()
-    return _nms_call(fn_name, b, order, counts, thresh)
+    return _nms_call(fn_name, b, order, counts, thresh, flags)
 
 
-def nms_gpu_batched(boxes, scores, thresh, counts=None):
-    """P independent rotated-NMS problems in three launches and no host sync.
+def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False):
+    """P independent rotated-NMS problems in two launches (records, lazy NMS) and no host sync.
     :param boxes: (P, N, 7), :param scores: (P, N), :param counts: optional (P,) valid boxes per problem
+    :param full_mask: materialise the reference's N x N/64 suppression mask and sweep it (three launches)
+        instead of evaluating kept rows only; the keep lists are identical
     :return: keep (P, N) int64 indices into each problem's boxes, padded with -1; num_keep (P,) int32
     """
-    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts)
+    flags = _lib.LG_FLAG_NMS_FULL_MASK if full_mask else _lib.LG_FLAG_NONE
+    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts, flags)
 
 
 def nms_normal_gpu_batched(boxes, scores, thresh, counts=None):

@@ -77,3 +77,72 @@ extern "C" int emu_debug_pair(const float* a, const float* b, float* verts /*[16
     for (int k = 0; k < n && k < 16; k++) keys[k] = angle_key(verts[2 * k], verts[2 * k + 1], centroid[0], centroid[1], k);
     return n;
 }
+
+// ---- points in boxes: the grid algorithm of lg_points.cu, serial (same lg_pib.cuh functions) ----------------
+#include "../../lidardetection_b200/csrc/lg_pib.cuh"
+
+#include <vector>
+
+// boxes (T,7), pts (M,3) -> out (M); grid_words = capacity of the cell-mask array (kernel: 12288).
+// returns the number of (point, box) predicate evaluations performed (for the pruning statistics)
+extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float* pts, long long M, int32_t* out, int grid_words,
+                                         int* used_grid) {
+    std::vector<float4> rec(2 * (size_t)T);
+    float lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY, sum_ext = 0.f, nv = 0.f;
+    bool bounded = true;
+    for (int k = 0; k < T; k++) {
+        make_pib_record(boxes + k * 7, 1e-5f, rec[2 * k], rec[2 * k + 1]);
+        float ex, ey;
+        if (pib_footprint(rec[2 * k], rec[2 * k + 1], ex, ey, bounded)) {
+            lo_x = fminf(lo_x, rec[2 * k].x - ex); hi_x = fmaxf(hi_x, rec[2 * k].x + ex);
+            lo_y = fminf(lo_y, rec[2 * k].y - ey); hi_y = fmaxf(hi_y, rec[2 * k].y + ey);
+            sum_ext += 0.5f * (ex + ey);
+            nv += 1.f;
+        }
+    }
+    const int W = (T + 31) >> 5;
+    const bool use_grid = bounded && W <= grid_words;
+    *used_grid = use_grid ? 1 : 0;
+    long long tests = 0;
+    std::vector<uint32_t> grid((size_t)grid_words, 0u);
+    PibGrid g{};
+    if (use_grid && nv > 0.f) {
+        g = pib_make_grid(lo_x, hi_x, lo_y, hi_y, sum_ext / nv, grid_words / W);
+        for (int k = 0; k < T; k++) {
+            float ex, ey;
+            bool dummy = true;
+            const float4 r0 = rec[2 * k], r1 = rec[2 * k + 1];
+            if (!pib_footprint(r0, r1, ex, ey, dummy)) continue;
+            const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
+            const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
+            for (int iy = iy0; iy <= iy1; iy++)
+                for (int ix = ix0; ix <= ix1; ix++) grid[(size_t)(iy * g.nx + ix) * W + (k >> 5)] |= 1u << (k & 31);
+        }
+    }
+    for (long long p = 0; p < M; p++) {
+        const float x = pts[3 * p], y = pts[3 * p + 1], z = pts[3 * p + 2];
+        int r = -1;
+        if (use_grid) {
+            const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
+            if (nv > 0.f && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny) {
+                const uint32_t* cw = grid.data() + (size_t)((int)fy * g.nx + (int)fx) * W;
+                for (int w = 0; w < W && r < 0; w++) {
+                    uint32_t bits = cw[w];
+                    while (bits) {
+                        const int k = (w << 5) + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        tests++;
+                        if (pt_in_box<1>(x, y, z, rec[2 * k], rec[2 * k + 1])) { r = k; break; }
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < T; k++) {
+                tests++;
+                if (pt_in_box<1>(x, y, z, rec[2 * k], rec[2 * k + 1])) { r = k; break; }
+            }
+        }
+        out[p] = r;
+    }
+    return tests;
+}

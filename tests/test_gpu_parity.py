@@ -152,6 +152,30 @@ def test_nms_vs_oracle(n, thresh, normal):
         pytest.fail(explain_nms_mismatch(boxes[0][order], inv[got], inv[want], thresh, normal))
 
 
+@pytest.mark.parametrize("n,thresh,seed", [(4096, 0.01, 1), (4096, 0.5, 2), (1000, 0.2, 3), (777, 0.7, 4), (2500, 0.1, 5), (33, 0.3, 6)])
+def test_nms_lazy_equals_full_mask_equals_oracle(n, thresh, seed):
+    """the default (kept rows only) and the mask + sweep formulation give the identical keep lists"""
+    boxes, scores = synth.nms_frames(3, n, seed=500 + seed)
+    # one frame of near-duplicates: exercises the literal (atan2) path for > 8 vertices and angular ties
+    r = np.random.default_rng(seed)
+    boxes[2] = boxes[2][r.integers(0, max(n // 8, 1), n)] + r.normal(0, 2e-3, (n, 7)).astype(np.float32)
+    tb, ts = cu(boxes), cu(scores)
+    k_lazy, n_lazy = U.nms_gpu_batched(tb, ts, thresh)
+    k_full, n_full = U.nms_gpu_batched(tb, ts, thresh, full_mask=True)
+    assert torch.equal(n_lazy, n_full) and torch.equal(k_lazy, k_full)
+    for f in range(3):
+        order = ts[f].sort(0, descending=True)[1].cpu().numpy()
+        want = O.nms(boxes[f], scores[f], thresh, flavor=O.FLAVOR_CUDA, order=order)
+        got = k_lazy[f, : int(n_lazy[f])].cpu().numpy()
+        inv = np.empty(n, np.int64)
+        inv[order] = np.arange(n)
+        if f < 2:
+            assert np.array_equal(got, want), explain_nms_mismatch(boxes[f][order], inv[got], inv[want], thresh, False)
+        elif not np.array_equal(got, want):
+            # near-duplicates sit on vertex-order ties (libdevice vs glibc atan2f): report, do not require
+            print("near-duplicate frame differs from the CPU oracle:", explain_nms_mismatch(boxes[f][order], inv[got], inv[want], thresh, False))
+
+
 def test_nms_vs_golden_reference_cuda(ggpu):
     boxes, scores = ggpu["nms_boxes"], ggpu["nms_scores"]
     for f in range(boxes.shape[0]):

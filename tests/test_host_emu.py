@@ -1,0 +1,152 @@
+"""CPU tier: the DEVICE per-pair code (lidardetection_b200/csrc/lg_geom.cuh, lg_pib.cuh) compiled for the host
+(tests/host_emu/, every CUDA intrinsic mapped to the IEEE operation it denotes, libdevice sinf/cosf taken from
+the oracle's restatement) must agree with the oracle BIT FOR BIT.  This is what lets the arithmetic contract of
+the kernels be iterated on without a GPU; the GPU tier then only has to show that nvcc compiles the same
+header to the same arithmetic (tests/test_gpu_parity.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from lidardetection_b200 import synth
+from oracle import lg_oracle as O
+from tests.host_emu import build as ebuild
+
+fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = C.CDLL(ebuild.build())
+    L.emu_pairs.argtypes = [fp, C.c_int64, fp, C.c_int64, fp, C.c_int, C.c_int]
+    L.emu_slow_count.restype = C.c_longlong
+    L.emu_points_in_boxes.restype = C.c_longlong
+    L.emu_points_in_boxes.argtypes = [fp, C.c_int, fp, C.c_longlong, ip, C.c_int, C.POINTER(C.c_int)]
+    return L
+
+
+def pairs(L, a, b, mode, flavor=1):
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    out = np.empty((len(a), len(b)), np.float32)
+    L.emu_pairs(a.ctypes.data_as(fp), len(a), b.ctypes.data_as(fp), len(b), out.ctypes.data_as(fp), mode, flavor)
+    return out
+
+
+def bits(x):
+    return np.ascontiguousarray(x, np.float32).view(np.uint32)
+
+
+SETS = {
+    "car35": lambda: synth.clustered_pairs(300, 300, 1, (35, 17.5), synth.KITTI_PRIORS[:1]),
+    "ped70": lambda: synth.clustered_pairs(300, 300, 2, (70, 35), synth.KITTI_PRIORS[1:2]),
+    "mix150": lambda: synth.clustered_pairs(300, 300, 3, (150, 75)),
+    "dense": lambda: synth.dense_overlap(300, 300),
+    "cfg3iou": synth.cfg3_iou,
+    "cfg1sub": lambda: (synth.cfg1()[0][::97], synth.cfg1()[1]),
+    "nms": lambda: (synth.cfg2(1, 512)[0][0],) * 2,
+}
+
+
+@pytest.mark.parametrize("name", sorted(SETS))
+def test_device_pair_code_matches_oracle_bit_for_bit(emu, name):
+    a, b = SETS[name]()
+    for mode, ora in ((0, O.boxes_overlap_bev), (1, O.boxes_iou_bev), (2, O.boxes_iou3d)):
+        got = pairs(emu, a, b, mode + 4)  # +4: with the exact-zero cull in front, as the kernels run it
+        want = ora(a, b, O.FLAVOR_CUDA)
+        assert np.array_equal(bits(got), bits(want)), f"{name} mode {mode}: {(bits(got) != bits(want)).sum()} of {got.size} differ"
+
+
+def test_cull_never_drops_a_nonzero_pair(emu):
+    r = np.random.default_rng(11)
+    a = synth.gt_boxes(400, 5, x_range=(-30, 30), y_range=(-30, 30))
+    a[:, 3] = r.uniform(0.3, 10.3, 400)
+    a[:, 4] = r.uniform(0.3, 4.3, 400)
+    with_cull, without = pairs(emu, a, a, 0 + 4), pairs(emu, a, a, 0)
+    assert np.array_equal(bits(with_cull), bits(without))
+    assert 0.01 < (without > 0).mean() < 0.2
+
+
+@pytest.mark.parametrize("jitter", [1e-4, 1e-3, 5e-3, 2e-2])
+def test_near_coincident_boxes_take_the_literal_path_and_still_match(emu, jitter):
+    """> 8 polygon vertices and angular near-ties are deferred to overlap_area_slow (atan2f + stable order)"""
+    r = np.random.default_rng(5)
+    base = synth.gt_boxes(200, 11)
+
+    def jit():
+        d = base.copy()
+        d[:, 0:2] += r.normal(0, jitter, (200, 2))
+        d[:, 3:5] *= 1 + r.normal(0, jitter * 0.3, (200, 2))
+        d[:, 6] += r.normal(0, jitter, 200)
+        return d.astype(np.float32)
+
+    a, b = jit(), jit()
+    before = emu.emu_slow_count()
+    got = pairs(emu, a, b, 1 + 4)
+    assert emu.emu_slow_count() - before >= 10
+    assert np.array_equal(bits(got), bits(O.boxes_iou_bev(a, b, O.FLAVOR_CUDA)))
+
+
+def test_known_answers_through_the_device_code(emu):
+    a = np.array([[0, 0, 0, 4, 2, 1.5, 0]], np.float32)
+    cases = {(1, 0.5, 0, 4, 2, 1.5, 0.7): 0.414507687, (0, 0, 0, 4, 2, 1.5, np.pi / 2): 0.333333343, (4.005, 0, 0, 4, 2, 1.5, 0): 6.2540517e-4,
+             (4.02, 0, 0, 4, 2, 1.5, 0): 0.0, (4, 0, 0, 4, 2, 1.5, 0): 0.0, (50, 50, 0, 4, 2, 1.5, 0): 0.0, (0, 0, 0, 4, 2, 1.5, 0): 1.0}
+    for b, want in cases.items():
+        got = float(pairs(emu, a, np.array([b], np.float32), 1 + 4, flavor=0)[0, 0])
+        assert abs(got - want) < 2e-7, (b, got, want)
+
+
+# ------------------------------------------------------------------------------------------ points
+def pib(L, boxes, pts, grid_words=12288):
+    boxes, pts = np.ascontiguousarray(boxes, np.float32), np.ascontiguousarray(pts, np.float32)
+    out, used = np.empty(len(pts), np.int32), C.c_int(0)
+    tests = L.emu_points_in_boxes(boxes.ctypes.data_as(fp), len(boxes), pts.ctypes.data_as(fp), len(pts), out.ctypes.data_as(ip),
+                                  grid_words, C.byref(used))
+    return out, tests, used.value
+
+
+def boundary_points(r, b, m):
+    """points inside / on the faces (+- a few ulp) / just outside randomly chosen boxes"""
+    k = r.integers(0, len(b), m)
+    loc = r.uniform(-0.52, 0.52, (m, 3))
+    edge, ax, sgn = r.random(m) < 0.5, r.integers(0, 2, m), r.choice([-1, 1], m)
+    loc[edge, 0] = np.where(ax[edge] == 0, sgn[edge] * (0.5 + r.normal(0, 2e-6, edge.sum())), loc[edge, 0])
+    loc[edge, 1] = np.where(ax[edge] == 1, sgn[edge] * (0.5 + r.normal(0, 2e-6, edge.sum())), loc[edge, 1])
+    loc *= b[k, 3:6]
+    c, s = np.cos(b[k, 6]), np.sin(b[k, 6])
+    return np.stack([b[k, 0] + loc[:, 0] * c - loc[:, 1] * s, b[k, 1] + loc[:, 0] * s + loc[:, 1] * c, b[k, 2] + loc[:, 2]], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("T,M,scale", [(1, 3000, 1), (7, 8000, 0.2), (100, 16384, 1), (300, 10000, 3), (1000, 8000, 1), (4096, 4000, 1)])
+def test_grid_cull_of_points_in_boxes_is_exact(emu, T, M, scale):
+    r = np.random.default_rng(T)
+    b = synth.gt_boxes(T, int(r.integers(1 << 30)))
+    b[:, 3:6] *= scale
+    p = boundary_points(r, b, M)
+    if T >= 100:  # padded all-zero box, negative size, NaN heading, NaN centre: none may break the cull
+        b[3] = 0
+        b[5, 3] = -1.0
+        b[7, 6] = np.nan
+        b[9, 0] = np.nan
+    got, tests, used = pib(emu, b, p)
+    want = O.points_in_boxes_idx(p[None], b[None], O.FLAVOR_CUDA)[0]
+    assert used == 1 and np.array_equal(got, want)
+    assert tests < 0.3 * M * T or T < 8  # the grid prunes
+
+
+def test_grid_cull_cfg3_and_fallbacks(emu):
+    pts, rois = synth.cfg3(n_frames=2)
+    for f in range(2):
+        got, tests, used = pib(emu, rois[f], pts[f])
+        assert used == 1 and np.array_equal(got, O.points_in_boxes_idx(pts[f:f + 1], rois[f:f + 1], O.FLAVOR_CUDA)[0])
+        assert tests < 1.0 * len(got)  # < 1 predicate evaluation per point (the reference: up to 100)
+    r = np.random.default_rng(1)
+    b = synth.gt_boxes(50, 3)
+    b[4, 3] = np.inf  # an unbounded footprint disables the grid: every box is tested
+    p = np.concatenate([r.uniform(-10, 80, (3000, 2)), r.uniform(-2, 0, (3000, 1))], 1).astype(np.float32)
+    got, _, used = pib(emu, b, p)
+    assert used == 0 and np.array_equal(got, O.points_in_boxes_idx(p[None], b[None], O.FLAVOR_CUDA)[0])
+    z = np.zeros((5, 7), np.float32)  # only padded boxes: the origin matches box 0 (dataset.py:172-177 padding is not skipped)
+    p0 = np.zeros((10, 3), np.float32)
+    p0[1:] = r.normal(0, 1e-3, (9, 3))
+    got, _, _ = pib(emu, z, p0)
+    assert np.array_equal(got, O.points_in_boxes_idx(p0[None], z[None], O.FLAVOR_CUDA)[0]) and got[0] == 0

@@ -14,7 +14,12 @@ from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU 
 op = sys.argv[1] if len(sys.argv) > 1 else "nms"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cu = lambda x: torch.from_numpy(x).cuda()
-if op == "nms":
+if op == "nms_full":
+    b, s = synth.cfg2(16, 4096)
+    tb, ts = cu(b), cu(s)
+    for _ in range(iters):
+        U.nms_gpu_batched(tb, ts, 0.01, full_mask=True)
+elif op == "nms":
     b, s = synth.cfg2(16, 4096)
     tb, ts = cu(b), cu(s)
     for _ in range(iters):
