@@ -390,7 +390,7 @@ class PibWorkload(Workload):
         t = float(np.mean(ts)) * 1e-3
         byts = self.units * (12.0 * 16384 + 28.0 * 100 + 4.0 * 16384)
         ach = byts / t / 1e9
-        return {"bound": "hbm", "kernel": "pib_idx_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        return {"bound": "hbm", "kernel": "pib_grid_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                 "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "B*(12*M + 28*T + 4*M)", "bytes_per_frame": 264944}}
 
     def cpu_sample(self, pool):

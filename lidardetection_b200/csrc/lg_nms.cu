@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
     uint32_t* alive = reinterpret_cast<uint32_t*>(sm + L.off_alive);
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s;
-    __shared__ unsigned long long st_tested, st_heavy, st_nonzero;
+    __shared__ unsigned long long st_heavy;
 
     const int p = blockIdx.x;
     const int n = problem_count(counts, p, nmax);
@@ -325,9 +325,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
         qcount = 0;
         rcount = 0;
         nk_s = 0;
-        st_tested = 0ull;
         st_heavy = 0ull;
-        st_nonzero = 0ull;
     }
     int cursor = 0;  // every box below it is decided
     unsigned my_tested = 0u, my_nonzero = 0u;
@@ -421,21 +419,23 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
         __syncthreads();
         drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
         __syncthreads();
-        // ---- resolve the speculation in score order (one thread; at most G*(G-1)/2 bit tests)
-        if (tid == 0) {
-            int km = 0, nk = nk_s;
+        // ---- resolve the speculation in score order (warp 0: lane h holds candidate h's row; at most G ballots)
+        if (warp == 0) {
+            const int jl = lane < ng ? group[lane] : 0;
+            const int64_t ol = (lane < ng && order) ? order[base + jl] : (int64_t)jl;  // loads issued before the serial part
+            unsigned km = 0u;
             for (int g = 0; g < ng; g++) {
                 const int j = group[g];
-                bool dead = false;
-                for (int h = 0; h < g; h++)
-                    if (((km >> h) & 1) && ((sup[h * W + (j >> 5)] >> (j & 31)) & 1u)) dead = true;
-                if (!dead) {
-                    km |= 1 << g;
-                    keep[base + nk++] = order ? order[base + j] : (int64_t)j;
-                }
+                const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
+                const unsigned by = __ballot_sync(0xffffffffu, hit);  // earlier candidates whose row suppresses g
+                if ((by & km) == 0u) km |= 1u << g;
             }
-            keptmask_s = km;
-            nk_s = nk;
+            const int nk = nk_s;
+            if ((km >> lane) & 1u) keep[base + nk + __popc(km & ((1u << lane) - 1u))] = ol;
+            if (lane == 0) {
+                keptmask_s = (int)km;
+                nk_s = nk + __popc(km);
+            }
         }
         __syncthreads();
         const int km = keptmask_s;
@@ -459,14 +459,16 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
     if (tid == 0) num_keep[p] = nk;
     for (int i = nk + tid; i < nmax; i += NT) keep[base + i] = -1;
     if (stats) {
-        atomicAdd(&st_tested, (unsigned long long)my_tested);
-        atomicAdd(&st_nonzero, (unsigned long long)my_nonzero);
-        __syncthreads();
-        if (tid == 0) {
-            atomicAdd(stats, st_tested);
-            atomicAdd(stats + 1, st_heavy);
-            atomicAdd(stats + 2, st_nonzero);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            my_tested += __shfl_xor_sync(0xffffffffu, my_tested, d);
+            my_nonzero += __shfl_xor_sync(0xffffffffu, my_nonzero, d);
         }
+        if (lane == 0) {
+            atomicAdd(stats, (unsigned long long)my_tested);
+            atomicAdd(stats + 2, (unsigned long long)my_nonzero);
+        }
+        if (tid == 0) atomicAdd(stats + 1, st_heavy);
     }
 }
 

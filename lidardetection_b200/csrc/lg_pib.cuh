@@ -109,4 +109,21 @@ __device__ __forceinline__ int pib_cell_clamped(float v, float origin, float inv
     return (int)f;
 }
 
+// Can the footprint of box (r0, r1) reach cell (ix, iy)?  Conservative separating-axis test along the box's
+// own axes (the grid axes are covered by the cell range of pib_footprint): a point q of the cell can only be
+// accepted if |lx(q)| < tx, and lx(q) differs from lx(cell centre) by at most hx|c| + hy|s| (hx, hy = half
+// cell size).  The cell is inflated by 1e-4 relative + 2e-6 (|x0| + extent) for the rounding of the cell
+// mapping, the thresholds by the same slack as pib_footprint.
+__device__ __forceinline__ bool pib_cell_touches(const float4 r0, const float4 r1, const PibGrid& g, const int ix, const int iy) {
+    const float wx = 1.0f / g.invx, wy = 1.0f / g.invy;  // cell size (slightly over, see pib_make_grid)
+    const float hx = 0.5f * wx * 1.0001f + 2e-6f * (fabsf(g.x0) + wx * (float)g.nx);
+    const float hy = 0.5f * wy * 1.0001f + 2e-6f * (fabsf(g.y0) + wy * (float)g.ny);
+    const float sx = g.x0 + ((float)ix + 0.5f) * wx - r0.x, sy = g.y0 + ((float)iy + 0.5f) * wy - r0.y;
+    const float c = r1.x, s = r1.y, ac = fabsf(c), as = fabsf(s);
+    const float lx = sx * c - sy * s, ly = sy * c + sx * s;
+    const float E = r1.z * ac + r1.w * as, F = r1.w * ac + r1.z * as;
+    const float slack = 1e-4f * (E + F) + 4e-7f * (fabsf(r0.x) + fabsf(r0.y));
+    return fabsf(lx) <= r1.z + slack + hx * ac + hy * as && fabsf(ly) <= r1.w + slack + hx * as + hy * ac;
+}
+
 }  // namespace lg

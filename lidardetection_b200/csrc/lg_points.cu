@@ -51,11 +51,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+constexpr int PIB_WARPS = PIB_THREADS / 32;
+constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
+constexpr int PIB_LIST = PIB_WPTS * 4;          // (point, mask word) work items per warp and tile, worst case
+
 struct PibSmem {
-    // dynamic smem layout: [stages][grid][records]
+    // dynamic smem layout: [stages][grid][work lists][results][records]
     static constexpr size_t stage_bytes = (size_t)PIB_STAGES * PIB_TILE_BYTES;
     static constexpr size_t grid_bytes = (size_t)PIB_GRID_WORDS * sizeof(uint32_t);
-    static size_t total(int T) { return stage_bytes + grid_bytes + (size_t)T * 2 * sizeof(float4); }
+    static constexpr size_t list_bytes = (size_t)PIB_WARPS * PIB_LIST * sizeof(uint32_t);
+    static constexpr size_t res_bytes = (size_t)PIB_TILE * sizeof(int);
+    static size_t total(int T) { return stage_bytes + grid_bytes + list_bytes + res_bytes + (size_t)T * 2 * sizeof(float4); }
 };
 
 template <int FL>
@@ -80,7 +86,9 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
     extern __shared__ float4 smem4[];
     float* stage = reinterpret_cast<float*>(smem4);
     uint32_t* grid = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem4) + PibSmem::stage_bytes);
-    float4* srec = reinterpret_cast<float4*>(grid + PIB_GRID_WORDS);
+    uint32_t* lists = grid + PIB_GRID_WORDS;
+    int* sres = reinterpret_cast<int*>(lists + PIB_WARPS * PIB_LIST);
+    float4* srec = reinterpret_cast<float4*>(sres + PIB_TILE);
     __shared__ uint64_t bars[PIB_STAGES];
     __shared__ float red[8][6];
     __shared__ PibGrid sgrid;
@@ -149,6 +157,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
         red[warp][5] = all_bounded ? nvalid : -1e30f;  // poison: any unbounded box disables the grid
     }
     for (int w = tid; w < PIB_GRID_WORDS; w += NT) grid[w] = 0u;
+    for (int w = tid; w < PIB_TILE; w += NT) sres[w] = 0x7fffffff;
     __syncthreads();
     const int W = (T + 31) >> 5;
     if (tid == 0) {
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             const uint32_t bit = 1u << (k & 31);
             for (int c = lane; c < total; c += 32) {
                 const int cy = c / ncx, cx = c - cy * ncx;
-                atomicOr(&grid[((iy0 + cy) * g.nx + ix0 + cx) * W + (k >> 5)], bit);
+                if (pib_cell_touches(r0, r1, g, ix0 + cx, iy0 + cy)) atomicOr(&grid[((iy0 + cy) * g.nx + ix0 + cx) * W + (k >> 5)], bit);
             }
         }
     }
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             __syncthreads();
         }
         const int i0 = tid * 4;
-        if (i0 < np) {
+        {  // every lane runs this block (it holds warp collectives); points at or beyond np are masked out
             float v[12];
             if (i0 + 4 <= np) {
                 const float4* q = reinterpret_cast<const float4*>(sp + i0 * 3);  // 48-byte stride: conflict-free LDS.128
@@ -214,26 +223,96 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
 #pragma unroll
                 for (int u = 0; u < 12; u++) v[u] = (i0 * 3 + u < np * 3) ? sp[i0 * 3 + u] : 0.f;
             }
-            int res[4];
+            int res[4] = {-1, -1, -1, -1};
+            if (use_grid && W <= 4) {
+                // T <= 128.  Work items are (point, non-empty mask word) pairs: every lane lists the items of its
+                // four points in the warp's smem list, then ALL lanes take items round-robin -- the predicate
+                // runs on full warps although only ~40 % of the points have a candidate at all -- and the lowest
+                // box that contains a point wins through atomicMin on the point's result slot.
+                uint32_t* list = lists + warp * PIB_LIST;
+                int* wres = sres + warp * PIB_WPTS;
+                uint32_t item[4];  // cell << 9 | point << 2 (word index added below); nz: 4 bits per point
+                uint32_t nz = 0u;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const float x = v[3 * u], y = v[3 * u + 1], z = v[3 * u + 2];
-                int r = -1;
-                if (use_grid) {
-                    const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
-                    if (any_valid && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny)
-                        r = first_box_in_cell<FL>(grid + ((int)fy * g.nx + (int)fx) * W, W, srec, x, y, z);
-                } else {
-                    for (int k = 0; k < T; k++)
+                for (int u = 0; u < 4; u++) {
+                    const float fx = pib_cellf(v[3 * u], g.x0, g.invx), fy = pib_cellf(v[3 * u + 1], g.y0, g.invy);
+                    const bool in = any_valid && i0 + u < np && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny;
+                    const int cell = in ? (int)fy * g.nx + (int)fx : 0;
+                    item[u] = ((uint32_t)cell << 9) | ((uint32_t)(lane * 4 + u) << 2);
+                    const uint32_t* cw = grid + cell * W;
+                    uint32_t f = 0u;
+                    if (W == 4) {
+                        const uint4 m = *reinterpret_cast<const uint4*>(cw);
+                        f = (m.x ? 1u : 0u) | (m.y ? 2u : 0u) | (m.z ? 4u : 0u) | (m.w ? 8u : 0u);
+                    } else {
+                        for (int w = 0; w < W; w++) f |= cw[w] ? (1u << w) : 0u;
+                    }
+                    nz |= (in ? f : 0u) << (4 * u);
+                }
+                // exclusive scan of the item counts over the warp
+                const int mine = __popc(nz);
+                int incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = incl - mine;
+                while (nz) {
+                    const int b = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t it = item[0];
+#pragma unroll
+                    for (int q = 1; q < 4; q++) it = (b >> 2) == q ? item[q] : it;
+                    list[pos++] = it | (uint32_t)(b & 3);
+                }
+                __syncwarp();
+                const float* wp = sp + warp * (PIB_WPTS * 3);
+                for (int i = lane; i < total; i += 32) {
+                    const uint32_t it = list[i];
+                    const int w = it & 3, pid = (it >> 2) & 127;
+                    uint32_t bits = grid[(it >> 9) * W + w];
+                    const float x = wp[pid * 3], y = wp[pid * 3 + 1], z = wp[pid * 3 + 2];
+                    while (bits) {
+                        const int k = (w << 5) + __ffs(bits) - 1;
+                        bits &= bits - 1;
                         if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
-                            r = k;
+                            atomicMin(&wres[pid], k);  // ascending within the word; min across the words
                             break;
                         }
+                    }
                 }
-                res[u] = r;
+                __syncwarp();
+                const int4 r4 = *reinterpret_cast<const int4*>(wres + lane * 4);
+                *reinterpret_cast<int4*>(wres + lane * 4) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+                res[0] = r4.x == 0x7fffffff ? -1 : r4.x;
+                res[1] = r4.y == 0x7fffffff ? -1 : r4.y;
+                res[2] = r4.z == 0x7fffffff ? -1 : r4.z;
+                res[3] = r4.w == 0x7fffffff ? -1 : r4.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float x = v[3 * u], y = v[3 * u + 1], z = v[3 * u + 2];
+                    int r = -1;
+                    if (use_grid) {
+                        const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
+                        if (any_valid && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny)
+                            r = first_box_in_cell<FL>(grid + ((int)fy * g.nx + (int)fx) * W, W, srec, x, y, z);
+                    } else {
+                        for (int k = 0; k < T; k++)
+                            if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
+                                r = k;
+                                break;
+                            }
+                    }
+                    res[u] = r;
+                }
             }
             int32_t* o = go + (int64_t)t * PIB_TILE + i0;
-            if (i0 + 4 <= np && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            if (i0 >= np) {
+                // nothing to store
+            } else if (i0 + 4 <= np && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
                 __stcs(reinterpret_cast<int4*>(o), make_int4(res[0], res[1], res[2], res[3]));
             } else {
 #pragma unroll

@@ -116,7 +116,8 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
             const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
             const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
             for (int iy = iy0; iy <= iy1; iy++)
-                for (int ix = ix0; ix <= ix1; ix++) grid[(size_t)(iy * g.nx + ix) * W + (k >> 5)] |= 1u << (k & 31);
+                for (int ix = ix0; ix <= ix1; ix++)
+                    if (pib_cell_touches(r0, r1, g, ix, iy)) grid[(size_t)(iy * g.nx + ix) * W + (k >> 5)] |= 1u << (k & 31);
         }
     }
     for (long long p = 0; p < M; p++) {
@@ -145,4 +146,27 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
         out[p] = r;
     }
     return tests;
+}
+
+// diagnostics: classify pairs: 0 = zero/cnt<=2, 1 = fast path, 2 = deferred (cnt > 8), 3 = deferred (angular near-tie)
+extern "C" void emu_classify(const float* a, int64_t n, const float* b, int64_t m, int* hist /*[4]*/, unsigned tie_units) {
+    float4* ra = new float4[(size_t)n * REC_F4];
+    float4* rb = new float4[(size_t)m * REC_F4];
+    for (int64_t i = 0; i < n; i++) make_record<1>(a + i * 7, ra + i * REC_F4);
+    for (int64_t j = 0; j < m; j++) make_record<1>(b + j * 7, rb + j * REC_F4);
+    float2 slab[16];
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t j = i + 1; j < m; j++) {
+            const float4 *A = ra + i * REC_F4, *B = rb + j * REC_F4;
+            if (!cull_survives(A[REC_CULL], B[REC_CULL])) { hist[0]++; continue; }
+            uint32_t xm, cm;
+            pair_masks<1>(A, B, xm, cm);
+            const int cnt = __popc(xm) + __popc(cm);
+            if (cnt <= 2) { hist[0]++; continue; }
+            if (cnt > 8) { hist[2]++; continue; }
+            const float v = overlap_area<1>(A, B, slab, 1, 1u);
+            hist[v < 0.f ? 3 : 1]++;
+        }
+    delete[] ra;
+    delete[] rb;
 }
