@@ -121,6 +121,8 @@ __device__ __forceinline__ bool cull_survives(const float4 ac, const float4 bc) 
     return !(dx * dx + dy * dy > rr * rr);  // NaN => keep: the polygon path decides
 }
 
+constexpr uint32_t LG_TIE_UNITS = 64;  // adjacent pseudo-angle keys closer than this are an angular near-tie
+
 // ---- 8-input sorting network on packed 32-bit keys (19 compare-exchanges) ------------------------
 __device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {
     const uint32_t lo = min(a, b), hi = max(a, b);
@@ -136,6 +138,20 @@ __device__ __forceinline__ void sort8(uint32_t (&k)[8]) {
     cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
 }
 
+__device__ __forceinline__ void sort16(uint32_t (&k)[16]) {  // Batcher odd-even merge sort, 63 compare-exchanges
+    cex(k[0], k[1]); cex(k[2], k[3]); cex(k[0], k[2]); cex(k[1], k[3]); cex(k[1], k[2]); cex(k[4], k[5]);
+    cex(k[6], k[7]); cex(k[4], k[6]); cex(k[5], k[7]); cex(k[5], k[6]); cex(k[0], k[4]); cex(k[2], k[6]);
+    cex(k[2], k[4]); cex(k[1], k[5]); cex(k[3], k[7]); cex(k[3], k[5]); cex(k[1], k[2]); cex(k[3], k[4]);
+    cex(k[5], k[6]); cex(k[8], k[9]); cex(k[10], k[11]); cex(k[8], k[10]); cex(k[9], k[11]); cex(k[9], k[10]);
+    cex(k[12], k[13]); cex(k[14], k[15]); cex(k[12], k[14]); cex(k[13], k[15]); cex(k[13], k[14]); cex(k[8], k[12]);
+    cex(k[10], k[14]); cex(k[10], k[12]); cex(k[9], k[13]); cex(k[11], k[15]); cex(k[11], k[13]);
+    cex(k[9], k[10]); cex(k[11], k[12]); cex(k[13], k[14]); cex(k[0], k[8]); cex(k[4], k[12]); cex(k[4], k[8]);
+    cex(k[2], k[10]); cex(k[6], k[14]); cex(k[6], k[10]); cex(k[2], k[4]); cex(k[6], k[8]); cex(k[10], k[12]);
+    cex(k[1], k[9]); cex(k[5], k[13]); cex(k[5], k[9]); cex(k[3], k[11]); cex(k[7], k[15]); cex(k[7], k[11]);
+    cex(k[3], k[5]); cex(k[7], k[9]); cex(k[11], k[13]); cex(k[1], k[2]); cex(k[3], k[4]); cex(k[5], k[6]);
+    cex(k[7], k[8]); cex(k[9], k[10]); cex(k[11], k[12]); cex(k[13], k[14]);
+}
+
 // Monotone stand-in for atan2f(dy, dx) on (-pi, pi]: copysign(1 - dx/(|dx|+|dy|), dy) in [-2, 2],
 // quantised to 2^-25 and packed above the 4-bit vertex index (ties keep insertion order, like the
 // reference's stable bubble sort).  Only the ORDER of the vertices depends on it.
@@ -148,8 +164,6 @@ __device__ __forceinline__ uint32_t angle_key(float px, float py, float cx, floa
     const uint32_t q = __float2uint_rn(__fmaf_rn(k, 33554432.0f, 67108864.0f));  // (k + 2) * 2^25 <= 2^27
     return (q << 4) | (uint32_t)idx;
 }
-
-constexpr uint32_t LG_TIE_UNITS = 64;
 
 // m | bit  iff  a0 <= b0 && a1 <= b1 && a2 <= b2 && a3 <= b3 && p1 > 0 && p2 > 0  (check_rect_cross and the two
 // straddle products, kernel.cu:43-49, 75).  Written as one chain of predicate-combining compares: plain C++
@@ -381,6 +395,70 @@ __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, cons
     }
     __syncwarp(wmask);
     return res;
+}
+
+// ---- the pair, 9..16 vertices (near-coincident boxes; ~0.3 % of overlapping pairs) -----------------
+// Same construction as the fast path with 16 vertex slots and a 16-input network; returns -1 on an angular
+// near-tie (the caller then runs the literal path).  Called for the pairs the fast path deferred.
+template <int FL, typename Slab16>
+__device__ __noinline__ float overlap_area16(const float4* __restrict__ A, const float4* __restrict__ B, Slab16 slab16) {
+    uint32_t xmask, cmask;
+    pair_masks<FL>(A, B, xmask, cmask);
+    const int cnt = __popc(xmask) + __popc(cmask);  // <= 16 + 8; geometrically <= 16
+    if (cnt <= 2) return 0.f;
+    if (cnt > 16) return -1.f;
+    int n = 0;
+    float sx = 0.f, sy = 0.f;
+    while (xmask) {
+        const int e = __ffs(xmask) - 1;
+        xmask &= xmask - 1;
+        const float2 v = crossing_point<FL>(A, B, e >> 2, e & 3);
+        slab16(n) = v;
+        sx += v.x;
+        sy += v.y;
+        n++;
+    }
+    while (cmask) {
+        const int e = __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        const float4 c = (e & 1) ? A[e >> 1] : B[e >> 1];
+        slab16(n) = make_float2(c.x, c.y);
+        sx += c.x;
+        sy += c.y;
+        n++;
+    }
+    const float inv = __fdividef(1.0f, (float)cnt);
+    const float mx = sx * inv, my = sy * inv;
+    uint32_t key[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        key[k] = 0xFFFFFFF0u | k;
+        if (k < cnt) {
+            const float2 p = slab16(k);
+            key[k] = angle_key(p.x, p.y, mx, my, k);
+        }
+    }
+    sort16(key);
+    uint32_t gap = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 15; k++)
+        if (k + 1 < cnt) gap = min(gap, (key[k + 1] >> 4) - (key[k] >> 4));
+    if (gap <= LG_TIE_UNITS) return -1.f;
+    const float2 p0 = slab16((int)(key[0] & 15));
+    const float2 p1 = slab16((int)(key[1] & 15));
+    float ux = p1.x - p0.x, uy = p1.y - p0.y;
+    float area = 0.f;
+#pragma unroll
+    for (int k = 2; k < 16; k++) {
+        if (k < cnt) {
+            const float2 pn = slab16((int)(key[k] & 15));
+            const float vx = pn.x - p0.x, vy = pn.y - p0.y;
+            area = __fadd_rn(area, msub<FL>(ux, vy, uy, vx));
+            ux = vx;
+            uy = vy;
+        }
+    }
+    return __fmul_rn(fabsf(area), 0.5f);
 }
 
 // ---- the pair, literal path (up to 16 vertices, or angular near-ties; rare) ------------------------

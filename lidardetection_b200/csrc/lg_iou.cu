@@ -56,7 +56,7 @@ constexpr int SK_MAX_COLS = 1 << SK_SHIFT;
 
 struct StripSmem {
     static constexpr size_t a_bytes = (size_t)SK_ROWS * REC_F4 * sizeof(float4);
-    static constexpr size_t total = a_bytes + ST_SLAB_BYTES + (size_t)(ST_QCAP + ST_RARECAP) * sizeof(uint32_t);
+    static constexpr size_t total = a_bytes + ST_SLAB_BYTES + (size_t)(ST_THREADS / 32) * (WQ_CAP + 1 + WR_CAP) * sizeof(uint32_t);
 };
 
 template <int FL>
@@ -68,9 +68,7 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
     float2* slab = reinterpret_cast<float2*>(sA + SK_ROWS * REC_F4);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(slab + 8 * NT);
-    uint32_t* rareq = queue + ST_QCAP;
-    __shared__ int qcount, rcount;
+    uint32_t* lists = reinterpret_cast<uint32_t*>(slab + 8 * NT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t strip = blockIdx.x;
@@ -80,75 +78,67 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     const int ntiles = 2 * ((nb + SK_TCOLS - 1) / SK_TCOLS);  // (column tile, row half)
 
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
-    if (tid == 0) {
-        qcount = 0;
-        rcount = 0;
-    }
+    __syncthreads();  // the only CTA barrier: from here on the warps run independently
+
     const float4* const gB = rec_b + col0 * REC_F4;
     const float4* const gcull = cull_b + col0;
     float* const outb = out + row0 * ld + col0;
     auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
         __stcs(outb + (int64_t)r * ld + c, finish_pair(mode, ov, A, B));
     };
+    WarpQueue q;
+    q.list = lists + warp * (WQ_CAP + 1 + WR_CAP);
+    q.rare = q.list + WQ_CAP + 1;
+    q.count = 0;
+    q.rcount = 0;
+    float2* const slab_warp = slab + warp * 32;
 
     const int rsub = warp >> 1, cbase = (warp & 1) * 32;
     float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cbase + lane < nb) bc = __ldg(gcull + cbase + lane);
-    for (int t = 0;; t++) {  // one extra trip for the final drain (a single drain call site keeps the code small)
-        __syncthreads();
-        const int qn = qcount, rn = rcount;
-        __syncthreads();
-        const bool last = t == ntiles;
-        if (last || qn > ST_QCAP - SK_TROWS * SK_TCOLS) {  // the next tile could overflow the queue: drain first
-            if (rn + qn > ST_RARECAP) {  // (rarely) make room in the rare queue first
-                drain_rare<FL, SK_SHIFT>(sA, gB, slab, rareq, &rcount, emit);
-                __syncthreads();
+    for (int t = 0;; t++) {  // one extra trip flushes the list (a single call site of the polygon path keeps the code small)
+        const bool last = t >= ntiles;
+        if (!last) {
+            const int c = (t >> 1) * SK_TCOLS + cbase + lane;  // column relative to col0
+            const float4 bcur = bc;
+            if (t & 1) {  // both row halves of this column tile use bcur; fetch the next tile's quad now
+                const int cn = c + SK_TCOLS;
+                bc = cn < nb ? __ldg(gcull + cn) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            drain_main<FL, SK_SHIFT>(sA, gB, slab, queue, qn, rareq, &rcount, emit);
-            if (last) {
-                __syncthreads();
-                drain_rare<FL, SK_SHIFT>(sA, gB, slab, rareq, &rcount, emit);
-                break;
-            }
-            if (tid == 0) qcount = 0;
-            __syncthreads();
-        }
-        const int c = (t >> 1) * SK_TCOLS + cbase + lane;  // column relative to col0
-        const float4 bcur = bc;
-        if (t & 1) {  // both row halves of this column tile use bcur; fetch the next tile's quad now
-            const int cn = c + SK_TCOLS;
-            bc = cn < nb ? __ldg(gcull + cn) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const int rhalf = (t & 1) * SK_TROWS;
-        if (rhalf >= na) continue;  // CTA-uniform
-        const int rbase = rhalf + rsub;
-        float* outp = outb + (int64_t)rbase * ld + c;
-        const int64_t ostep = 4 * ld;
-        unsigned mk[8];
-        if (rhalf + SK_TROWS <= na && (t >> 1) * SK_TCOLS + SK_TCOLS <= nb) {  // full tile (CTA-uniform): no bounds tests
+            const int rhalf = (t & 1) * SK_TROWS;
+            if (rhalf >= na) continue;
+            const int rbase = rhalf + rsub;
+            float* outp = outb + (int64_t)rbase * ld + c;
+            const int64_t ostep = 4 * ld;
+            unsigned mk[8];
+            if (rhalf + SK_TROWS <= na && (t >> 1) * SK_TCOLS + SK_TCOLS <= nb) {  // full tile: no bounds tests
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const bool surv = cull_survives(sA[(rbase + 4 * k) * REC_F4 + REC_CULL], bcur);
-                if (!surv) __stcs(outp, 0.f);  // culled: exactly +0.0, written once, coalesced
-                outp += ostep;
-                mk[k] = __ballot_sync(0xffffffffu, surv);
-            }
-        } else {
-            const bool cvalid = c < nb;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int r = rbase + 4 * k;
-                bool surv = false;
-                if (cvalid && r < na) {
-                    surv = cull_survives(sA[r * REC_F4 + REC_CULL], bcur);
-                    if (!surv) __stcs(outp, 0.f);
+                for (int k = 0; k < 8; k++) {
+                    const bool surv = cull_survives(sA[(rbase + 4 * k) * REC_F4 + REC_CULL], bcur);
+                    if (!surv) __stcs(outp, 0.f);  // culled: exactly +0.0, written once, coalesced
+                    outp += ostep;
+                    mk[k] = __ballot_sync(0xffffffffu, surv);
                 }
-                outp += ostep;
-                mk[k] = __ballot_sync(0xffffffffu, surv);
+            } else {
+                const bool cvalid = c < nb;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int r = rbase + 4 * k;
+                    bool surv = false;
+                    if (cvalid && r < na) {
+                        surv = cull_survives(sA[r * REC_F4 + REC_CULL], bcur);
+                        if (!surv) __stcs(outp, 0.f);
+                    }
+                    outp += ostep;
+                    mk[k] = __ballot_sync(0xffffffffu, surv);
+                }
             }
+            warp_push<SK_SHIFT, 8>(q, mk, lane, rbase, 4, c);
         }
-        push_survivors<SK_SHIFT, 8>(mk, lane, rbase, 4, c, &qcount, queue);
+        while (q.count >= (last ? 1 : 32)) warp_round<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
+        if (last) break;
     }
+    if (q.rcount > 0) warp_drain_rare<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
 }
 
 // ---- narrow matrices (M <= 64, e.g. anchors x GT): a CTA owns 256 rows x all M columns, flat pair index ----

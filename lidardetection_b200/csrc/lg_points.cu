@@ -53,15 +53,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 
 constexpr int PIB_WARPS = PIB_THREADS / 32;
 constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
-constexpr int PIB_LIST = PIB_WPTS * 4;          // (point, mask word) work items per warp and tile, worst case
+constexpr int PIB_WLIST = 31 + PIB_WPTS + 1;    // per-warp work list (float4 items): leftover + one tile, padded to 160
 
 struct PibSmem {
-    // dynamic smem layout: [stages][grid][work lists][results][records]
+    // dynamic smem layout: [stages][grid][work lists][records]
     static constexpr size_t stage_bytes = (size_t)PIB_STAGES * PIB_TILE_BYTES;
     static constexpr size_t grid_bytes = (size_t)PIB_GRID_WORDS * sizeof(uint32_t);
-    static constexpr size_t list_bytes = (size_t)PIB_WARPS * PIB_LIST * sizeof(uint32_t);
-    static constexpr size_t res_bytes = (size_t)PIB_TILE * sizeof(int);
-    static size_t total(int T) { return stage_bytes + grid_bytes + list_bytes + res_bytes + (size_t)T * 2 * sizeof(float4); }
+    static constexpr size_t list_bytes = (size_t)PIB_WARPS * PIB_WLIST * sizeof(float4);
+    static size_t total(int T) { return stage_bytes + grid_bytes + list_bytes + (size_t)T * 2 * sizeof(float4); }
 };
 
 template <int FL>
@@ -87,8 +86,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
     float* stage = reinterpret_cast<float*>(smem4);
     uint32_t* grid = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem4) + PibSmem::stage_bytes);
     uint32_t* lists = grid + PIB_GRID_WORDS;
-    int* sres = reinterpret_cast<int*>(lists + PIB_WARPS * PIB_LIST);
-    float4* srec = reinterpret_cast<float4*>(sres + PIB_TILE);
+    float4* srec = reinterpret_cast<float4*>(lists) + PIB_WARPS * PIB_WLIST;
     __shared__ uint64_t bars[PIB_STAGES];
     __shared__ float red[8][6];
     __shared__ PibGrid sgrid;
@@ -157,7 +155,6 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
         red[warp][5] = all_bounded ? nvalid : -1e30f;  // poison: any unbounded box disables the grid
     }
     for (int w = tid; w < PIB_GRID_WORDS; w += NT) grid[w] = 0u;
-    for (int w = tid; w < PIB_TILE; w += NT) sres[w] = 0x7fffffff;
     __syncthreads();
     const int W = (T + 31) >> 5;
     if (tid == 0) {
@@ -198,7 +195,49 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
     }
     __syncthreads();
 
-    // ---- 3. the points, a tile per trip, four consecutive points per thread
+    // ---- 3. the points, a tile per trip.  Each warp owns 128 consecutive points of the tile.
+    //   step     one point per lane (conflict-free LDS): cell lookup; points whose cell lists a candidate box
+    //            are appended -- coordinates, cell and output offset -- to the warp's work list;
+    //   fill     the tile's results are pre-set to -1 with one 16-byte store per lane;
+    //   rounds   whenever the list holds 32 items, all 32 lanes test one item each against its cell's boxes in
+    //            ascending order and overwrite the -1 of a point that is inside one (first hit = lowest box).
+    // The list carries over from tile to tile, so the predicate always runs on full warps.
+    float4* wlist = reinterpret_cast<float4*>(lists) + warp * PIB_WLIST;
+    int wcount = 0;
+    auto round = [&](const int n) {  // the top n (<= 32) items of the list
+        const int idx = wcount - n + lane;
+        if (lane < n) {
+            const float4 e = wlist[idx];
+            const uint32_t code = __float_as_uint(e.w);
+            const uint32_t* cw = grid + (code >> 16) * W;
+            unsigned long long lo = cw[0], hi = 0ull;
+            if (W > 1) lo |= (unsigned long long)cw[1] << 32;
+            if (W > 2) hi = cw[2];
+            if (W > 3) hi |= (unsigned long long)cw[3] << 32;
+            int found = -1;
+            while (lo) {
+                const int k = __ffsll((long long)lo) - 1;
+                lo &= lo - 1;
+                if (pt_in_box<FL>(e.x, e.y, e.z, srec[2 * k], srec[2 * k + 1])) {
+                    found = k;
+                    lo = 0ull;
+                    hi = 0ull;
+                }
+            }
+            while (hi) {
+                const int k = 64 + __ffsll((long long)hi) - 1;
+                hi &= hi - 1;
+                if (pt_in_box<FL>(e.x, e.y, e.z, srec[2 * k], srec[2 * k + 1])) {
+                    found = k;
+                    hi = 0ull;
+                }
+            }
+            if (found >= 0) go[code & 0xffffu] = found;
+        }
+        wcount -= n;
+        __syncwarp();
+    };
+    const bool fast = use_grid && W <= 4;
     for (int t = 0; t < ntiles; t++) {
         const int s = t % PIB_STAGES;
         float* sp = stage + (size_t)s * (PIB_TILE * 3);
@@ -211,119 +250,73 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             for (int i = tid; i < np * 3; i += NT) sp[i] = __ldg(src + i);
             __syncthreads();
         }
-        const int i0 = tid * 4;
-        {  // every lane runs this block (it holds warp collectives); points at or beyond np are masked out
-            float v[12];
-            if (i0 + 4 <= np) {
-                const float4* q = reinterpret_cast<const float4*>(sp + i0 * 3);  // 48-byte stride: conflict-free LDS.128
-                const float4 q0 = q[0], q1 = q[1], q2 = q[2];
-                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y;
-                v[6] = q1.z; v[7] = q1.w; v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
-            } else {
+        const int wbase = warp * PIB_WPTS;          // this warp's first point within the tile
+        const int tbase = t * PIB_TILE + wbase;     // ... within the CTA's chunk (< 65536)
+        if (fast) {
+            // fill: -1 for the warp's 128 points (results of hits are written over it after the __syncwarp below)
+            {
+                const int i0 = wbase + lane * 4;
+                int32_t* o = go + (int64_t)t * PIB_TILE + i0;
+                if (i0 + 4 <= np && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    __stcs(reinterpret_cast<int4*>(o), make_int4(-1, -1, -1, -1));
+                } else {
 #pragma unroll
-                for (int u = 0; u < 12; u++) v[u] = (i0 * 3 + u < np * 3) ? sp[i0 * 3 + u] : 0.f;
+                    for (int u = 0; u < 4; u++)
+                        if (i0 + u < np) o[u] = -1;
+                }
             }
-            int res[4] = {-1, -1, -1, -1};
-            if (use_grid && W <= 4) {
-                // T <= 128.  Work items are (point, non-empty mask word) pairs: every lane lists the items of its
-                // four points in the warp's smem list, then ALL lanes take items round-robin -- the predicate
-                // runs on full warps although only ~40 % of the points have a candidate at all -- and the lowest
-                // box that contains a point wins through atomicMin on the point's result slot.
-                uint32_t* list = lists + warp * PIB_LIST;
-                int* wres = sres + warp * PIB_WPTS;
-                uint32_t item[4];  // cell << 9 | point << 2 (word index added below); nz: 4 bits per point
-                uint32_t nz = 0u;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const float fx = pib_cellf(v[3 * u], g.x0, g.invx), fy = pib_cellf(v[3 * u + 1], g.y0, g.invy);
-                    const bool in = any_valid && i0 + u < np && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny;
-                    const int cell = in ? (int)fy * g.nx + (int)fx : 0;
-                    item[u] = ((uint32_t)cell << 9) | ((uint32_t)(lane * 4 + u) << 2);
-                    const uint32_t* cw = grid + cell * W;
-                    uint32_t f = 0u;
-                    if (W == 4) {
-                        const uint4 m = *reinterpret_cast<const uint4*>(cw);
-                        f = (m.x ? 1u : 0u) | (m.y ? 2u : 0u) | (m.z ? 4u : 0u) | (m.w ? 8u : 0u);
-                    } else {
-                        for (int w = 0; w < W; w++) f |= cw[w] ? (1u << w) : 0u;
-                    }
-                    nz |= (in ? f : 0u) << (4 * u);
+            for (int st = 0; st < PIB_WPTS / 32; st++) {
+                const int p = st * 32 + lane;
+                const float* q = sp + (wbase + p) * 3;
+                const float x = q[0], y = q[1], z = q[2];
+                const int ix = __float2int_rd(pib_cellf(x, g.x0, g.invx)), iy = __float2int_rd(pib_cellf(y, g.y0, g.invy));
+                bool has = any_valid && wbase + p < np && (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny;
+                const int cell = has ? iy * g.nx + ix : 0;
+                const uint32_t* cw = grid + cell * W;
+                uint32_t any;
+                if (W == 4) {
+                    const uint4 m = *reinterpret_cast<const uint4*>(cw);
+                    any = m.x | m.y | m.z | m.w;
+                } else {
+                    any = cw[0];
+                    for (int w = 1; w < W; w++) any |= cw[w];
                 }
-                // exclusive scan of the item counts over the warp
-                const int mine = __popc(nz);
-                int incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += o;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int pos = incl - mine;
-                while (nz) {
-                    const int b = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    uint32_t it = item[0];
-#pragma unroll
-                    for (int q = 1; q < 4; q++) it = (b >> 2) == q ? item[q] : it;
-                    list[pos++] = it | (uint32_t)(b & 3);
-                }
-                __syncwarp();
-                const float* wp = sp + warp * (PIB_WPTS * 3);
-                for (int i = lane; i < total; i += 32) {
-                    const uint32_t it = list[i];
-                    const int w = it & 3, pid = (it >> 2) & 127;
-                    uint32_t bits = grid[(it >> 9) * W + w];
-                    const float x = wp[pid * 3], y = wp[pid * 3 + 1], z = wp[pid * 3 + 2];
-                    while (bits) {
-                        const int k = (w << 5) + __ffs(bits) - 1;
-                        bits &= bits - 1;
+                has = has && any != 0u;
+                const unsigned hm = __ballot_sync(0xffffffffu, has);
+                if (has) wlist[wcount + __popc(hm & ((1u << lane) - 1u))] = make_float4(x, y, z, __uint_as_float(((uint32_t)cell << 16) | (uint32_t)(tbase + p)));
+                wcount += __popc(hm);
+            }
+            __syncwarp();  // orders the fill above, and the list writes, before the rounds
+            while (wcount >= 32) round(32);
+        } else {
+            // general path (T > 128, or a frame with an unbounded box): every lane resolves its point itself
+            for (int st = 0; st < PIB_WPTS / 32; st++) {
+                const int p = st * 32 + lane;
+                if (wbase + p >= np) continue;
+                const float* q = sp + (wbase + p) * 3;
+                const float x = q[0], y = q[1], z = q[2];
+                int r = -1;
+                if (use_grid) {
+                    const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
+                    if (any_valid && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny)
+                        r = first_box_in_cell<FL>(grid + ((int)fy * g.nx + (int)fx) * W, W, srec, x, y, z);
+                } else {
+                    for (int k = 0; k < T; k++)
                         if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
-                            atomicMin(&wres[pid], k);  // ascending within the word; min across the words
+                            r = k;
                             break;
                         }
-                    }
                 }
-                __syncwarp();
-                const int4 r4 = *reinterpret_cast<const int4*>(wres + lane * 4);
-                *reinterpret_cast<int4*>(wres + lane * 4) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
-                res[0] = r4.x == 0x7fffffff ? -1 : r4.x;
-                res[1] = r4.y == 0x7fffffff ? -1 : r4.y;
-                res[2] = r4.z == 0x7fffffff ? -1 : r4.z;
-                res[3] = r4.w == 0x7fffffff ? -1 : r4.w;
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const float x = v[3 * u], y = v[3 * u + 1], z = v[3 * u + 2];
-                    int r = -1;
-                    if (use_grid) {
-                        const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
-                        if (any_valid && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny)
-                            r = first_box_in_cell<FL>(grid + ((int)fy * g.nx + (int)fx) * W, W, srec, x, y, z);
-                    } else {
-                        for (int k = 0; k < T; k++)
-                            if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
-                                r = k;
-                                break;
-                            }
-                    }
-                    res[u] = r;
-                }
-            }
-            int32_t* o = go + (int64_t)t * PIB_TILE + i0;
-            if (i0 >= np) {
-                // nothing to store
-            } else if (i0 + 4 <= np && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-                __stcs(reinterpret_cast<int4*>(o), make_int4(res[0], res[1], res[2], res[3]));
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (i0 + u < np) o[u] = res[u];
+                go[tbase + p] = r;
             }
         }
         __syncthreads();  // everyone is done with this stage: refill it
         if (tid == 0 && t + PIB_STAGES < ntiles) issue(t + PIB_STAGES);
     }
+    if (fast && wcount > 0) round(wcount);
 }
+
 
 constexpr int PIBM_BOXES = 32;  // boxes per CTA in the mask form
 

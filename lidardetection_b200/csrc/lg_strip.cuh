@@ -87,11 +87,97 @@ __device__ __forceinline__ void drain_rare(const float4* __restrict__ sA, const 
             const int r = e >> SHIFT, c = e & ((1u << SHIFT) - 1u);
             const float4* A = sA + (size_t)r * REC_F4;
             const float4* B = sB + (size_t)c * REC_F4;
-            emit(r, c, overlap_area_slow<FL>(A, B, slab16, ang16), A, B);
+            float ov = overlap_area16<FL>(A, B, slab16);
+            if (ov < 0.f) ov = overlap_area_slow<FL>(A, B, slab16, ang16);  // angular near-tie: the reference's own procedure
+            emit(r, c, ov, A, B);
         }
     }
     __syncthreads();
     if (tid == 0) *rcount = 0;
+}
+
+// ---- warp-autonomous variant: every warp owns a private work list, no CTA barrier anywhere in the sweep ----
+// Used by the N x M IoU strip kernel, whose warps have nothing to exchange: a warp appends the survivors of its
+// own tile slice, runs the polygon path on full 32-entry rounds taken from the top of its list, and keeps the
+// (< 32) rest for the next tile.  Deferred pairs go to a small per-warp list that 8 lanes work off.
+constexpr int WQ_CAP = 31 + 256;  // leftover of the previous tiles + one tile slice (8 rows x 32 columns)
+constexpr int WR_CAP = 64;
+
+struct WarpQueue {
+    uint32_t* list;  // WQ_CAP entries (shared memory)
+    uint32_t* rare;  // WR_CAP entries
+    int count, rcount;  // warp-uniform
+};
+
+template <int SHIFT, int NK>
+__device__ __forceinline__ void warp_push(WarpQueue& q, const unsigned (&m)[NK], const int lane, const int rbase, const int rstep,
+                                          const int col) {
+    unsigned any = 0u;
+#pragma unroll
+    for (int k = 0; k < NK; k++) any |= m[k];
+    if (any == 0u) return;
+    const unsigned lt = (1u << lane) - 1u;
+    int base = q.count;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        if (m[k]) {
+            if ((m[k] >> lane) & 1u) q.list[base + __popc(m[k] & lt)] = (uint32_t)(((rbase + rstep * k) << SHIFT) | col);
+            base += __popc(m[k]);
+        }
+    }
+    q.count = base;
+    __syncwarp();
+}
+
+// the deferred pairs of this warp: lanes 0..7, each with 16 vertex + 16 angle slots carved out of the warp's 32 slab columns
+template <int FL, int SHIFT, typename Emit>
+__device__ __forceinline__ void warp_drain_rare(WarpQueue& q, const float4* __restrict__ sA, const float4* __restrict__ sB,
+                                                float2* __restrict__ slab_warp, const int sstride, const int lane, Emit emit) {
+    __syncwarp();
+    if (lane < 8) {
+        auto slab16 = [&](int k) -> float2& { return slab_warp[(k & 7) * sstride + lane + ((k >> 3) << 3)]; };
+        auto ang16 = [&](int k) -> float& { return reinterpret_cast<float*>(slab_warp + (k >> 1) * sstride + 16 + lane)[k & 1]; };
+        for (int i = lane; i < q.rcount; i += 8) {
+            const unsigned e = q.rare[i];
+            const int r = e >> SHIFT, c = e & ((1u << SHIFT) - 1u);
+            const float4* A = sA + (size_t)r * REC_F4;
+            const float4* B = sB + (size_t)c * REC_F4;
+            float ov = overlap_area16<FL>(A, B, slab16);
+            if (ov < 0.f) ov = overlap_area_slow<FL>(A, B, slab16, ang16);
+            emit(r, c, ov, A, B);
+        }
+    }
+    q.rcount = 0;
+    __syncwarp();
+}
+
+// run the polygon path on the top min(count, 32) entries of the warp's list
+template <int FL, int SHIFT, typename Emit>
+__device__ __forceinline__ void warp_round(WarpQueue& q, const float4* __restrict__ sA, const float4* __restrict__ sB,
+                                           float2* __restrict__ slab_warp, const int sstride, const int lane, Emit emit) {
+    const int n = min(q.count, 32);
+    const int idx = q.count - n + lane;
+    const bool act = lane < n;
+    const unsigned wm = __ballot_sync(0xffffffffu, act);
+    bool defer = false;
+    unsigned e = 0u;
+    if (act) {
+        e = q.list[idx];
+        const int r = e >> SHIFT, c = e & ((1u << SHIFT) - 1u);
+        const float4* A = sA + (size_t)r * REC_F4;
+        const float4* B = sB + (size_t)c * REC_F4;
+        const float ov = overlap_area<FL>(A, B, slab_warp + lane, sstride, wm);
+        if (ov < 0.f) defer = true;
+        else emit(r, c, ov, A, B);
+    }
+    q.count -= n;
+    const unsigned dm = __ballot_sync(0xffffffffu, defer);
+    if (dm) {
+        if (defer) q.rare[q.rcount + __popc(dm & ((1u << lane) - 1u))] = e;
+        q.rcount += __popc(dm);
+        if (q.rcount > WR_CAP - 32) warp_drain_rare<FL, SHIFT>(q, sA, sB, slab_warp, sstride, lane, emit);
+    }
+    __syncwarp();
 }
 
 }  // namespace lg

@@ -4,7 +4,8 @@
 
 using namespace lg;
 
-static long long g_slow = 0;
+static long long g_slow = 0, g_literal = 0;
+extern "C" long long emu_literal_count() { return g_literal; }
 extern "C" long long emu_slow_count() { return g_slow; }
 
 template <int FL>
@@ -21,7 +22,11 @@ static void run(const float* a, int64_t n, const float* b, int64_t m, float* out
         float v = overlap_area<FL>(A, B, slab, 1, 1u);
         if (v < 0.f) {
             g_slow++;
-            v = overlap_area_slow<FL>(A, B, slab16, ang16);
+            v = overlap_area16<FL>(A, B, slab16);
+            if (v < 0.f) {
+                g_literal++;
+                v = overlap_area_slow<FL>(A, B, slab16, ang16);
+            }
         }
         return v;
     };

@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Turn the ncu reports / bench lines that came back in gpurun_out/ into the committed text summaries under profiles/.
+
+    python tools/make_profiles.py r01 <name>=<report.ncu-rep>:<kernel substring>[:<mangled substring>] ...
+
+For every report: the headline raw metrics of the first matching launch (duration, issue / pipe utilisation, occupancy,
+DRAM bytes) and the per-source-line table of tools/ncu_lines.py.  Developer tool (CPU container; needs ncu + nvdisasm).
+"""
+import csv
+import io
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__average_warp_latency_per_inst_issued.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def raw_metrics(rep, kernel):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    kn = hdr.index("Kernel Name")
+    for r in rows[2:]:
+        if kernel in r[kn]:
+            return [(k, r[hdr.index(k)], units[hdr.index(k)]) for k in KEYS if k in hdr], r[kn]
+    raise SystemExit(f"{kernel} not in {rep}")
+
+
+def main():
+    tag = sys.argv[1]
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    for spec in sys.argv[2:]:
+        name, rest = spec.split("=", 1)
+        parts = rest.split(":")
+        rep, kernel = parts[0], parts[1]
+        mangled = parts[2] if len(parts) > 2 else kernel
+        met, kname = raw_metrics(rep, kernel)
+        lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kernel, "--mangled", mangled, "--top", "30"],
+                               capture_output=True, text=True).stdout
+        out = os.path.join(ROOT, "profiles", f"{tag}_{name}.txt")
+        with open(out, "w") as f:
+            f.write(f"# {name}: ncu --set full --clock-control none --import-source on (B200, gpurun), report {os.path.basename(rep)}\n")
+            f.write(f"# kernel: {kname}\n\n")
+            for k, v, u in met:
+                f.write(f"{k:90s} {v} {u}\n")
+            f.write("\n# per source line (tools/ncu_lines.py): executed warp instructions, active lanes, stall samples\n")
+            f.write(lines)
+        print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,11 @@ if op == "nms_full":
     tb, ts = cu(b), cu(s)
     for _ in range(iters):
         U.nms_gpu_batched(tb, ts, 0.01, full_mask=True)
+elif op == "nms64":
+    b, s = synth.cfg2(64, 4096)
+    tb, ts = cu(b), cu(s)
+    for _ in range(iters):
+        U.nms_gpu_batched(tb, ts, 0.01)
 elif op == "nms":
     b, s = synth.cfg2(16, 4096)
     tb, ts = cu(b), cu(s)
