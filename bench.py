@@ -8,7 +8,7 @@
 Workloads (BASELINE.json `configs`; a "step" is one pass of the op over one resident batch of synthetic input):
     nms_cfg2  (default) SECOND KITTI post-processing: rotated nms_gpu, 4096 boxes/frame, thresh 0.01,
               64 frames per GPU (weak scaling: frames are independent problems, no data-path collective;
-              keep lists are all-gathered over NCCL inside the timed region when N > 1).  metric: frames/s.
+              every rank keeps the keep lists of its own frames, as the reference's DDP evaluation does).  metric: frames/s.
     nms_cfg5  NuScenes CBGS multi-head: 1000 boxes x 10 classes x 256 frames, thresh 0.2.  metric: problems/s.
     iou_dense FP32-roofline microbench: 16384 x 16384 all-overlapping pairs.  metric: Gpairs/s.
     iou_cfg1  PointPillars anchors x GT, 321,408 x 20 boxes_iou_bev.  metric: Gpairs/s.
@@ -476,6 +476,10 @@ def run_reference(args, rank):
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON record: libraries that print there (NCCL's version banner does) are sent to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -528,10 +532,10 @@ def main():
         torch.cuda.synchronize()
 
     def gather(out):
-        if world > 1:
-            for t in wl.result_for_gather(out):
-                buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-                dist.all_gather_into_tensor(buf, t.contiguous())
+        # The path has no exchange step: every rank keeps the results of the frames / row blocks it
+        # owns, exactly as the reference's DDP evaluation does (eval_utils.py:54-57; results are merged once, at the end of
+        # the epoch, through pickle files: common_utils.py:206-227).  So there is no per-step collective to time.
+        return out
 
     # ---- device-resident timing -----------------------------------------------------------------
     for _ in range(args.warmup):
@@ -591,7 +595,9 @@ def main():
         "dtype": wl.dtype, "data": "synthetic (seeded, SURVEY.md 8d shapes; no datasets offline)",
         "config": {"workload": wl.name, "units_per_step_per_gpu": wl.units, "l2": "256 MB L2 flush between timed iterations",
                    "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
-                   "multi_gpu": "independent problems per rank; results all-gathered over NCCL inside the timed region" if world > 1 else "single GPU"},
+                   "multi_gpu": "independent problems per rank, no data-path collective (results stay on the owning rank, as in the "
+                                "reference's DDP evaluation); NCCL only for the barrier and the max-over-ranks of the timings"
+                   if world > 1 else "single GPU"},
         "e2e": {"value": total_units * args.steps / e2e_s, "unit": wl.unit, "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h)},
         "gpu_launches": wl.launches_per_step * args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
