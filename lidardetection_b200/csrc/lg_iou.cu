@@ -50,15 +50,19 @@ __device__ __forceinline__ float finish_pair(const int mode, const float ov, con
 }
 
 // ---- wide matrices: a CTA owns 64 rows x cols_per_cta columns --------------------------------------
-constexpr int SK_ROWS = 64, SK_TROWS = 32, SK_TCOLS = 64;
+constexpr int SK_ROWS = 64, SK_TROWS = 32, SK_TCOLS = 128;
 constexpr int SK_SHIFT = 20;  // queue code = row << 20 | (column - first column of the CTA)
 constexpr int SK_MAX_COLS = 1 << SK_SHIFT;
 
 struct StripSmem {
     static constexpr size_t a_bytes = (size_t)SK_ROWS * REC_F4 * sizeof(float4);
-    static constexpr size_t total = a_bytes + ST_SLAB_BYTES + (size_t)(ST_THREADS / 32) * (WQ_CAP + 1 + WR_CAP) * sizeof(uint32_t);
+    static constexpr size_t dup_bytes = (size_t)SK_ROWS * 2 * sizeof(float4);
+    static constexpr size_t total = a_bytes + dup_bytes + ST_SLAB_BYTES + (size_t)(ST_THREADS / 32) * (WQ_CAP + 1 + WR_CAP) * sizeof(uint32_t);
 };
 
+// A tile is 32 rows x 128 columns; a warp owns 8 of its rows (rsub + 4k) x 64 columns, two adjacent columns per
+// lane.  The exact-zero cull of a full tile runs on packed FP32 pairs -- FADD2 / FMUL2 / FFMA2, the two columns of
+// a lane in one instruction -- and stores the two zeros of a culled pair with one 8-byte st.global.cs.
 template <int FL>
 __global__ void __launch_bounds__(ST_THREADS, 3)
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     constexpr int NT = ST_THREADS;
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
-    float2* slab = reinterpret_cast<float2*>(sA + SK_ROWS * REC_F4);
+    float4* sDup = sA + SK_ROWS * REC_F4;  // per row: (cx, cx, cy, cy), (rad, rad, -, -)
+    float2* slab = reinterpret_cast<float2*>(sDup + SK_ROWS * 2);
     uint32_t* lists = reinterpret_cast<uint32_t*>(slab + 8 * NT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -78,11 +83,18 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     const int ntiles = 2 * ((nb + SK_TCOLS - 1) / SK_TCOLS);  // (column tile, row half)
 
     for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
+    if (tid < na) {
+        const float4 c = __ldg(rec_a + (row0 + tid) * REC_F4 + REC_CULL);
+        sDup[2 * tid] = make_float4(c.x, c.x, c.y, c.y);
+        sDup[2 * tid + 1] = make_float4(c.z, c.z, 0.f, 0.f);
+    }
     __syncthreads();  // the only CTA barrier: from here on the warps run independently
 
     const float4* const gB = rec_b + col0 * REC_F4;
     const float4* const gcull = cull_b + col0;
     float* const outb = out + row0 * ld + col0;
+    // 8-byte stores need an even pitch and an 8-byte aligned first element of every row of this CTA
+    const bool vec2_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(outb) & 7) == 0);
     auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
         __stcs(outb + (int64_t)r * ld + c, finish_pair(mode, ov, A, B));
     };
@@ -93,47 +105,71 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     q.rcount = 0;
     float2* const slab_warp = slab + warp * 32;
 
-    const int rsub = warp >> 1, cbase = (warp & 1) * 32;
-    float4 bc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cbase + lane < nb) bc = __ldg(gcull + cbase + lane);
+    const int rsub = warp >> 1, cbase = (warp & 1) * 64 + 2 * lane;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bn0 = cbase < nb ? __ldg(gcull + cbase) : zero4, bn1 = cbase + 1 < nb ? __ldg(gcull + cbase + 1) : zero4;
     for (int t = 0;; t++) {  // one extra trip flushes the list (a single call site of the polygon path keeps the code small)
         const bool last = t >= ntiles;
         if (!last) {
-            const int c = (t >> 1) * SK_TCOLS + cbase + lane;  // column relative to col0
-            const float4 bcur = bc;
-            if (t & 1) {  // both row halves of this column tile use bcur; fetch the next tile's quad now
+            const int c = (t >> 1) * SK_TCOLS + cbase;  // first of this lane's two columns, relative to col0
+            const float4 b0 = bn0, b1 = bn1;
+            if (t & 1) {  // both row halves of this column tile use b0, b1; fetch the next tile's quads now
                 const int cn = c + SK_TCOLS;
-                bc = cn < nb ? __ldg(gcull + cn) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bn0 = cn < nb ? __ldg(gcull + cn) : zero4;
+                bn1 = cn + 1 < nb ? __ldg(gcull + cn + 1) : zero4;
             }
             const int rhalf = (t & 1) * SK_TROWS;
             if (rhalf >= na) continue;
             const int rbase = rhalf + rsub;
             float* outp = outb + (int64_t)rbase * ld + c;
             const int64_t ostep = 4 * ld;
-            unsigned mk[8];
-            if (rhalf + SK_TROWS <= na && (t >> 1) * SK_TCOLS + SK_TCOLS <= nb) {  // full tile: no bounds tests
+            unsigned mk0[8], mk1[8];
+            if (vec2_ok && rhalf + SK_TROWS <= na && (t >> 1) * SK_TCOLS + SK_TCOLS <= nb) {  // full tile: packed cull, no bounds tests
+                const f32x2 bx = pack2(b0.x, b1.x), by = pack2(b0.y, b1.y), br = pack2(b0.z, b1.z);
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const bool surv = cull_survives(sA[(rbase + 4 * k) * REC_F4 + REC_CULL], bcur);
-                    if (!surv) __stcs(outp, 0.f);  // culled: exactly +0.0, written once, coalesced
+                    const ulonglong2 axy = *reinterpret_cast<const ulonglong2*>(sDup + 2 * (rbase + 4 * k));  // (cx,cx), (cy,cy)
+                    const f32x2 ar = *reinterpret_cast<const f32x2*>(sDup + 2 * (rbase + 4 * k) + 1);         // (rad,rad)
+                    const f32x2 dx = sub2(axy.x, bx), dy = sub2(axy.y, by), rr = add2(ar, br);
+                    const f32x2 d2 = fma2(dx, dx, mul2(dy, dy)), r2 = mul2(rr, rr);
+                    float d2a, d2b, r2a, r2b;
+                    unpack2(d2, d2a, d2b);
+                    unpack2(r2, r2a, r2b);
+                    const bool s0 = !(d2a > r2a), s1 = !(d2b > r2b);  // NaN => keep: the polygon path decides
+                    if (!s0 && !s1) {
+                        __stcs(reinterpret_cast<float2*>(outp), make_float2(0.f, 0.f));  // culled: exactly +0.0, written once
+                    } else {
+                        if (!s0) __stcs(outp, 0.f);
+                        if (!s1) __stcs(outp + 1, 0.f);
+                    }
                     outp += ostep;
-                    mk[k] = __ballot_sync(0xffffffffu, surv);
+                    mk0[k] = __ballot_sync(0xffffffffu, s0);
+                    mk1[k] = __ballot_sync(0xffffffffu, s1);
                 }
             } else {
-                const bool cvalid = c < nb;
+                const bool v0 = c < nb, v1 = c + 1 < nb;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int r = rbase + 4 * k;
-                    bool surv = false;
-                    if (cvalid && r < na) {
-                        surv = cull_survives(sA[r * REC_F4 + REC_CULL], bcur);
-                        if (!surv) __stcs(outp, 0.f);
+                    bool s0 = false, s1 = false;
+                    if (r < na) {
+                        const float4 ac = sA[r * REC_F4 + REC_CULL];
+                        if (v0) {
+                            s0 = cull_survives(ac, b0);
+                            if (!s0) __stcs(outp, 0.f);
+                        }
+                        if (v1) {
+                            s1 = cull_survives(ac, b1);
+                            if (!s1) __stcs(outp + 1, 0.f);
+                        }
                     }
                     outp += ostep;
-                    mk[k] = __ballot_sync(0xffffffffu, surv);
+                    mk0[k] = __ballot_sync(0xffffffffu, s0);
+                    mk1[k] = __ballot_sync(0xffffffffu, s1);
                 }
             }
-            warp_push<SK_SHIFT, 8>(q, mk, lane, rbase, 4, c);
+            warp_push<SK_SHIFT, 8>(q, mk0, lane, rbase, 4, c);
+            warp_push<SK_SHIFT, 8>(q, mk1, lane, rbase, 4, c + 1);
         }
         while (q.count >= (last ? 1 : 32)) warp_round<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
         if (last) break;
@@ -285,7 +321,7 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
     if (want_m < 1) want_m = 1;
     int64_t cols = (m + want_m - 1) / want_m;
     cols = (cols + SK_TCOLS - 1) / SK_TCOLS * SK_TCOLS;
-    if (cols < 4 * SK_TCOLS) cols = 4 * SK_TCOLS;
+    if (cols < 2 * SK_TCOLS) cols = 2 * SK_TCOLS;
     if (cols > SK_MAX_COLS) cols = SK_MAX_COLS;
     const int64_t strips_m = (m + cols - 1) / cols;
     const int64_t strips = strips_n * strips_m;

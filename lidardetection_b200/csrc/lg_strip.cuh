@@ -96,11 +96,40 @@ __device__ __forceinline__ void drain_rare(const float4* __restrict__ sA, const 
     if (tid == 0) *rcount = 0;
 }
 
+// ---- packed FP32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE single-precision operations per issue slot) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // ---- warp-autonomous variant: every warp owns a private work list, no CTA barrier anywhere in the sweep ----
 // Used by the N x M IoU strip kernel, whose warps have nothing to exchange: a warp appends the survivors of its
 // own tile slice, runs the polygon path on full 32-entry rounds taken from the top of its list, and keeps the
 // (< 32) rest for the next tile.  Deferred pairs go to a small per-warp list that 8 lanes work off.
-constexpr int WQ_CAP = 31 + 256;  // leftover of the previous tiles + one tile slice (8 rows x 32 columns)
+constexpr int WQ_CAP = 31 + 512;  // leftover of the previous tiles + one tile slice (8 rows x 64 columns)
 constexpr int WR_CAP = 64;
 
 struct WarpQueue {
