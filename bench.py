@@ -155,7 +155,7 @@ class NmsWorkload(Workload):
         self.h_scores = torch.from_numpy(self.scores_np).pin_memory()
         self.launches_per_step = 2  # nms_prep_kernel, nms_lazy_kernel (torch.sort is not ours)
         self.h2d = self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
-        self.d2h = self.scores.numel() * 8 + self.units * 4
+        self.d2h = 0  # set by e2e_step from the tensors it copies
 
     def step(self):
         from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
@@ -168,7 +168,10 @@ class NmsWorkload(Workload):
         b = self.h_boxes.cuda(non_blocking=True)
         s = self.h_scores.cuda(non_blocking=True)
         keep, num = U.nms_gpu_batched(b, s, self.thresh)
-        return keep.cpu(), num.cpu()
+        num_h = num.cpu()  # the result a caller reads: the counts, then the kept indices (the padding stays on the device)
+        keep_h = keep[:, : int(num_h.max())].cpu()
+        self.d2h = num_h.numel() * 4 + keep_h.numel() * 8  # counted from the tensors copied
+        return keep_h, num_h
 
     def result_for_gather(self, out):
         return list(out)

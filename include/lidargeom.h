@@ -58,7 +58,8 @@ extern "C" {
 
 /* limits */
 #define LG_NMS_MAX_BOXES 65536 /* per NMS problem */
-#define LG_PIB_MAX_BOXES 4096  /* boxes per frame for lg_points_in_boxes (shared-memory resident) */
+#define LG_PIB_MAX_BOXES 2048  /* boxes per frame for lg_points_in_boxes (records are shared-memory resident);
+                                  frames of up to 254 boxes take the grid-culled path, larger ones test every box */
 
 LG_API int lg_version(void);
 LG_API const char *lg_last_error_string(void);

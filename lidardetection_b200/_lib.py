@@ -9,7 +9,7 @@ LG_FLAG_NONE = 0
 LG_FLAG_STRICT_FP32 = 1
 LG_FLAG_NMS_FULL_MASK = 2
 LG_NMS_MAX_BOXES = 65536
-LG_PIB_MAX_BOXES = 4096
+LG_PIB_MAX_BOXES = 2048
 
 _lib = None
 

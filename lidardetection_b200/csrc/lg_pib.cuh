@@ -73,13 +73,14 @@ struct PibGrid {
 
 // Grid over [X0, X1] x [Y0, Y1] with at most ncap cells; mean_ext = mean footprint half-extent of the boxes
 // (cells much smaller than the boxes only make the marking pass longer).
-__device__ __forceinline__ PibGrid pib_make_grid(float X0, float X1, float Y0, float Y1, float mean_ext, int ncap) {
+__device__ __forceinline__ PibGrid pib_make_grid(float X0, float X1, float Y0, float Y1, float mean_ext, int ncap,
+                                                 float min_cell_factor = 0.66f) {
     PibGrid g;
     g.x0 = X0;
     g.y0 = Y0;
     const float wx = fmaxf(X1 - X0, 1e-6f * (fabsf(X0) + fabsf(X1)) + 1e-20f);
     const float wy = fmaxf(Y1 - Y0, 1e-6f * (fabsf(Y0) + fabsf(Y1)) + 1e-20f);
-    float cell = fmaxf(sqrtf(wx * wy / (float)ncap), 0.66f * mean_ext);
+    float cell = fmaxf(sqrtf(wx * wy / (float)ncap), min_cell_factor * mean_ext);
     cell = fmaxf(cell, 1e-20f);
     int nx = (int)fminf(ceilf(wx / cell), (float)ncap);
     int ny = (int)fminf(ceilf(wy / cell), (float)ncap);
@@ -124,6 +125,30 @@ __device__ __forceinline__ bool pib_cell_touches(const float4 r0, const float4 r
     const float E = r1.z * ac + r1.w * as, F = r1.w * ac + r1.z * as;
     const float slack = 1e-4f * (E + F) + 4e-7f * (fabsf(r0.x) + fabsf(r0.y));
     return fabsf(lx) <= r1.z + slack + hx * ac + hy * as && fabsf(ly) <= r1.w + slack + hx * as + hy * ac;
+}
+
+// ---- compact candidate lists: one 32-bit word per cell ------------------------------------------
+// bytes 0..3 = up to four candidate box indices in ASCENDING order, 0xFF = empty slot.  A fifth candidate turns
+// byte 3 into the marker 0xFE: "more candidates exist, all with an index above byte 2" -- the point lookup then
+// tests bytes 0..2 and, if none contains the point, every box above byte 2 (exact, merely slower; such cells
+// are rare).  Box indices must be < 254.
+constexpr uint32_t PIB_CELL_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t PIB_ID_MORE = 0xFEu, PIB_ID_NONE = 0xFFu;
+constexpr int PIB_COMPACT_MAX_BOXES = 254;
+
+__device__ __forceinline__ uint32_t pib_compact_insert(const uint32_t w, uint32_t k) {
+    uint32_t a = w & 0xffu, b = (w >> 8) & 0xffu, c = (w >> 16) & 0xffu;
+    const uint32_t d = w >> 24;
+    uint32_t t;
+    if (k < a) { t = a; a = k; k = t; }
+    if (k < b) { t = b; b = k; k = t; }
+    if (k < c) { t = c; c = k; k = t; }
+    // a <= b <= c are the three smallest of the old (a, b, c) and k; k now holds the largest of the four
+    uint32_t top;
+    if (d == PIB_ID_MORE) top = PIB_ID_MORE;            // already overflowing: k (> c) joins the unnamed rest
+    else if (d == PIB_ID_NONE) top = k;                  // a free slot (k may itself be the 0xFF that bubbled up)
+    else top = PIB_ID_MORE;                              // five real candidates: keep the three smallest + marker
+    return a | (b << 8) | (c << 16) | (top << 24);
 }
 
 }  // namespace lg

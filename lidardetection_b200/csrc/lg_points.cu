@@ -7,11 +7,12 @@
 // Index form (B frames x M points x T boxes -> first containing box or -1): the reference does M*T predicate
 // evaluations with per-pair trigonometry; here a CTA
 //   1. builds the T 32-byte box records (trigonometry hoisted) and their conservative BEV footprints,
-//   2. lays a uniform grid over the frame's boxes in shared memory -- one bit mask of candidate boxes per cell
-//      (48 KB: 3072 cells at T <= 128) -- with one warp per box marking the cells its footprint touches,
+//   2. lays a uniform grid over the frame's boxes in shared memory -- per cell one 32-bit list of up to four
+//      candidate box indices in ascending order (48 KB: 12288 cells) -- all threads sharing the flattened
+//      (box, cell) pairs: separating-axis test, sorted insert by compare-and-swap,
 //   3. streams its points through shared memory with 1-D bulk async copies (TMA, cp.async.bulk + mbarrier,
-//      three 12 KB stages in flight per CTA) and, per point, tests only the boxes of the point's cell in
-//      ascending index order.
+//      three 12 KB stages in flight per CTA); points whose cell lists a candidate go to per-warp work lists
+//      and are tested on full warps against the (<= 4) boxes of their cell in ascending index order.
 // HBM traffic is the algorithmic 16 B per point (+ 28 T per CTA); the kernel is HBM-bound when the batch is
 // large enough to fill the machine.  Frames whose boxes have a non-finite footprint fall back to
 // testing every box.
@@ -21,10 +22,13 @@
 namespace lg {
 
 constexpr int PIB_THREADS = 256;
-constexpr int PIB_TILE = 1024;                 // points per stage (4 per thread)
+constexpr int PIB_TILE = 1024;                 // points per stage
 constexpr int PIB_STAGES = 3;
 constexpr int PIB_TILE_BYTES = PIB_TILE * 12;  // 12 KB
-constexpr int PIB_GRID_WORDS = 12288;          // 48 KB of cell masks
+constexpr int PIB_CELLS = 12288;               // 48 KB of 32-bit candidate lists (lg_pib.cuh)
+constexpr int PIB_WARPS = PIB_THREADS / 32;
+constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
+constexpr int PIB_WLIST = 31 + PIB_WPTS + 1;    // per-warp work list (float4 items): leftover + one tile, padded to 160
 
 // ---- mbarrier / bulk-copy wrappers (PTX ISA: cp.async.bulk, mbarrier) -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,31 +55,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
-constexpr int PIB_WARPS = PIB_THREADS / 32;
-constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
-constexpr int PIB_WLIST = 31 + PIB_WPTS + 1;    // per-warp work list (float4 items): leftover + one tile, padded to 160
-
 struct PibSmem {
-    // dynamic smem layout: [stages][grid][work lists][records]
+    // dynamic smem layout: [stages][cells][work lists][records][box cell ranges][prefix]
     static constexpr size_t stage_bytes = (size_t)PIB_STAGES * PIB_TILE_BYTES;
-    static constexpr size_t grid_bytes = (size_t)PIB_GRID_WORDS * sizeof(uint32_t);
+    static constexpr size_t cell_bytes = (size_t)PIB_CELLS * sizeof(uint32_t);
     static constexpr size_t list_bytes = (size_t)PIB_WARPS * PIB_WLIST * sizeof(float4);
-    static size_t total(int T) { return stage_bytes + grid_bytes + list_bytes + (size_t)T * 2 * sizeof(float4); }
-};
-
-template <int FL>
-__device__ __forceinline__ int first_box_in_cell(const uint32_t* __restrict__ cw, const int W, const float4* __restrict__ srec,
-                                                 const float x, const float y, const float z) {
-    for (int w = 0; w < W; w++) {
-        uint32_t bits = cw[w];
-        while (bits) {
-            const int k = (w << 5) + __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) return k;  // ascending index: lowest box wins
-        }
+    static size_t total(int T) {
+        const int tc = T < PIB_COMPACT_MAX_BOXES ? T : PIB_COMPACT_MAX_BOXES;
+        return stage_bytes + cell_bytes + list_bytes + (size_t)T * 2 * sizeof(float4) + (size_t)tc * sizeof(int4) + (size_t)(tc + 8) * sizeof(int);
     }
-    return -1;
-}
+};
 
 template <int FL>
 __global__ void __launch_bounds__(PIB_THREADS, 2)
@@ -84,13 +73,15 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
     constexpr int NT = PIB_THREADS;
     extern __shared__ float4 smem4[];
     float* stage = reinterpret_cast<float*>(smem4);
-    uint32_t* grid = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem4) + PibSmem::stage_bytes);
-    uint32_t* lists = grid + PIB_GRID_WORDS;
-    float4* srec = reinterpret_cast<float4*>(lists) + PIB_WARPS * PIB_WLIST;
+    uint32_t* cells = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem4) + PibSmem::stage_bytes);
+    float4* lists = reinterpret_cast<float4*>(cells + PIB_CELLS);
+    float4* srec = lists + PIB_WARPS * PIB_WLIST;
+    int4* srange = reinterpret_cast<int4*>(srec + 2 * T);  // per box: ix0, iy0, cells per row, cells
+    int* sprefix = reinterpret_cast<int*>(srange + min(T, PIB_COMPACT_MAX_BOXES));
     __shared__ uint64_t bars[PIB_STAGES];
     __shared__ float red[8][6];
     __shared__ PibGrid sgrid;
-    __shared__ int s_use_grid, s_nvalid;
+    __shared__ int s_use_grid, s_nvalid, s_total;
 
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p_begin = (int64_t)blockIdx.x * pts_per_cta;
@@ -154,9 +145,11 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
         red[warp][4] = sum_ext;
         red[warp][5] = all_bounded ? nvalid : -1e30f;  // poison: any unbounded box disables the grid
     }
-    for (int w = tid; w < PIB_GRID_WORDS; w += NT) grid[w] = 0u;
+    {
+        const uint4 e4 = make_uint4(PIB_CELL_EMPTY, PIB_CELL_EMPTY, PIB_CELL_EMPTY, PIB_CELL_EMPTY);
+        for (int w = tid; w < PIB_CELLS / 4; w += NT) reinterpret_cast<uint4*>(cells)[w] = e4;
+    }
     __syncthreads();
-    const int W = (T + 31) >> 5;
     if (tid == 0) {
         float a = INFINITY, bb = -INFINITY, c = INFINITY, d = -INFINITY, se = 0.f, nv = 0.f;
         for (int w = 0; w < NT / 32; w++) {
@@ -167,29 +160,73 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             se += red[w][4];
             nv += red[w][5];
         }
-        const bool ok = nv >= 0.f && W <= PIB_GRID_WORDS;  // (a frame with more than 393,216 boxes cannot get here)
+        const bool ok = nv >= 0.f && T <= PIB_COMPACT_MAX_BOXES;  // more boxes than the 8-bit lists can name: every box is tested
         s_use_grid = ok ? 1 : 0;
         s_nvalid = nv > 0.f ? 1 : 0;
-        if (ok && nv > 0.f) sgrid = pib_make_grid(a, bb, c, d, se / nv, PIB_GRID_WORDS / W);
+        if (ok && nv > 0.f) sgrid = pib_make_grid(a, bb, c, d, se / nv, PIB_CELLS, 0.5f);
     }
     __syncthreads();
     const bool use_grid = s_use_grid != 0, any_valid = s_nvalid != 0;
     const PibGrid g = sgrid;
 
-    // ---- 2. mark the cells each footprint touches: one warp per box
+    // ---- 2. candidate lists.  (a) one thread per box: the cell range of its footprint; (b) prefix sum of the cell
+    //         counts; (c) ALL threads share the flattened (box, cell) pairs: separating-axis test, sorted insert (CAS)
     if (use_grid && any_valid) {
-        for (int k = warp; k < T; k += NT / 32) {
+        for (int k = tid; k < T; k += NT) {
             const float4 r0 = srec[2 * k], r1 = srec[2 * k + 1];
             float ex, ey;
             bool dummy = true;
-            if (!pib_footprint(r0, r1, ex, ey, dummy)) continue;  // warp-uniform
-            const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
-            const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
-            const int ncx = ix1 - ix0 + 1, total = ncx * (iy1 - iy0 + 1);
-            const uint32_t bit = 1u << (k & 31);
-            for (int c = lane; c < total; c += 32) {
-                const int cy = c / ncx, cx = c - cy * ncx;
-                if (pib_cell_touches(r0, r1, g, ix0 + cx, iy0 + cy)) atomicOr(&grid[((iy0 + cy) * g.nx + ix0 + cx) * W + (k >> 5)], bit);
+            int4 rg = make_int4(0, 0, 1, 0);
+            if (pib_footprint(r0, r1, ex, ey, dummy)) {
+                const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
+                const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
+                rg = make_int4(ix0, iy0, ix1 - ix0 + 1, (ix1 - ix0 + 1) * (iy1 - iy0 + 1));
+            }
+            srange[k] = rg;
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive prefix over T <= 254 counts: 8 per lane
+            int loc[8], sum = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = lane * 8 + u;
+                loc[u] = sum;
+                sum += k < T ? srange[k].w : 0;
+            }
+            int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            const int excl = incl - sum;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = lane * 8 + u;
+                if (k <= T) sprefix[k] = excl + loc[u];
+            }
+            if (lane == 31) s_total = incl;
+        }
+        __syncthreads();
+        const int total = s_total;
+        for (int idx = tid; idx < total; idx += NT) {
+            int lo = 0, hi = T;  // the box whose pair range [prefix[k], prefix[k+1]) holds idx
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sprefix[mid] <= idx) lo = mid;
+                else hi = mid;
+            }
+            const int4 rg = srange[lo];
+            const int local = idx - sprefix[lo];
+            const int cy = local / rg.z, cx = local - cy * rg.z;
+            const int ix = rg.x + cx, iy = rg.y + cy;
+            if (pib_cell_touches(srec[2 * lo], srec[2 * lo + 1], g, ix, iy)) {
+                uint32_t* cw = cells + iy * g.nx + ix;
+                uint32_t old = *cw, assumed;
+                do {
+                    assumed = old;
+                    old = atomicCAS(cw, assumed, pib_compact_insert(assumed, (uint32_t)lo));
+                } while (old != assumed);
             }
         }
     }
@@ -199,45 +236,40 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
     //   step     one point per lane (conflict-free LDS): cell lookup; points whose cell lists a candidate box
     //            are appended -- coordinates, cell and output offset -- to the warp's work list;
     //   fill     the tile's results are pre-set to -1 with one 16-byte store per lane;
-    //   rounds   whenever the list holds 32 items, all 32 lanes test one item each against its cell's boxes in
-    //            ascending order and overwrite the -1 of a point that is inside one (first hit = lowest box).
+    //   rounds   whenever the list holds 32 items, all 32 lanes test one item each against its cell's (<= 4)
+    //            boxes in ascending order and overwrite the -1 of a point that is inside one (first hit = lowest box).
     // The list carries over from tile to tile, so the predicate always runs on full warps.
-    float4* wlist = reinterpret_cast<float4*>(lists) + warp * PIB_WLIST;
+    float4* wlist = lists + warp * PIB_WLIST;
     int wcount = 0;
     auto round = [&](const int n) {  // the top n (<= 32) items of the list
         const int idx = wcount - n + lane;
-        if (lane < n) {
-            const float4 e = wlist[idx];
-            const uint32_t code = __float_as_uint(e.w);
-            const uint32_t* cw = grid + (code >> 16) * W;
-            unsigned long long lo = cw[0], hi = 0ull;
-            if (W > 1) lo |= (unsigned long long)cw[1] << 32;
-            if (W > 2) hi = cw[2];
-            if (W > 3) hi |= (unsigned long long)cw[3] << 32;
-            int found = -1;
-            while (lo) {
-                const int k = __ffsll((long long)lo) - 1;
-                lo &= lo - 1;
-                if (pt_in_box<FL>(e.x, e.y, e.z, srec[2 * k], srec[2 * k + 1])) {
-                    found = k;
-                    lo = 0ull;
-                    hi = 0ull;
-                }
-            }
-            while (hi) {
-                const int k = 64 + __ffsll((long long)hi) - 1;
-                hi &= hi - 1;
-                if (pt_in_box<FL>(e.x, e.y, e.z, srec[2 * k], srec[2 * k + 1])) {
-                    found = k;
-                    hi = 0ull;
-                }
-            }
-            if (found >= 0) go[code & 0xffffu] = found;
+        const bool act = lane < n;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t ids = PIB_CELL_EMPTY;
+        if (act) {
+            e = wlist[idx];
+            ids = cells[__float_as_uint(e.w) >> 16];
         }
+        int found = -1;
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++) {
+            const uint32_t id = (ids >> (8 * sl)) & 0xffu;
+            const bool go_on = found < 0 && id < PIB_ID_MORE;
+            if (__any_sync(0xffffffffu, go_on)) {
+                if (go_on && pt_in_box<FL>(e.x, e.y, e.z, srec[2 * id], srec[2 * id + 1])) found = (int)id;
+            }
+        }
+        if (found < 0 && (ids >> 24) == PIB_ID_MORE) {  // rare: a cell with more than four candidates
+            for (int k = (int)((ids >> 16) & 0xffu) + 1; k < T; k++)
+                if (pt_in_box<FL>(e.x, e.y, e.z, srec[2 * k], srec[2 * k + 1])) {
+                    found = k;
+                    break;
+                }
+        }
+        if (found >= 0) go[__float_as_uint(e.w) & 0xffffu] = found;
         wcount -= n;
         __syncwarp();
     };
-    const bool fast = use_grid && W <= 4;
     for (int t = 0; t < ntiles; t++) {
         const int s = t % PIB_STAGES;
         float* sp = stage + (size_t)s * (PIB_TILE * 3);
@@ -250,9 +282,9 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             for (int i = tid; i < np * 3; i += NT) sp[i] = __ldg(src + i);
             __syncthreads();
         }
-        const int wbase = warp * PIB_WPTS;          // this warp's first point within the tile
-        const int tbase = t * PIB_TILE + wbase;     // ... within the CTA's chunk (< 65536)
-        if (fast) {
+        const int wbase = warp * PIB_WPTS;       // this warp's first point within the tile
+        const int tbase = t * PIB_TILE + wbase;  // ... within the CTA's chunk (< 65536)
+        if (use_grid) {
             // fill: -1 for the warp's 128 points (results of hits are written over it after the __syncwarp below)
             {
                 const int i0 = wbase + lane * 4;
@@ -273,16 +305,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
                 const int ix = __float2int_rd(pib_cellf(x, g.x0, g.invx)), iy = __float2int_rd(pib_cellf(y, g.y0, g.invy));
                 bool has = any_valid && wbase + p < np && (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny;
                 const int cell = has ? iy * g.nx + ix : 0;
-                const uint32_t* cw = grid + cell * W;
-                uint32_t any;
-                if (W == 4) {
-                    const uint4 m = *reinterpret_cast<const uint4*>(cw);
-                    any = m.x | m.y | m.z | m.w;
-                } else {
-                    any = cw[0];
-                    for (int w = 1; w < W; w++) any |= cw[w];
-                }
-                has = has && any != 0u;
+                has = has && cells[cell] != PIB_CELL_EMPTY;
                 const unsigned hm = __ballot_sync(0xffffffffu, has);
                 if (has) wlist[wcount + __popc(hm & ((1u << lane) - 1u))] = make_float4(x, y, z, __uint_as_float(((uint32_t)cell << 16) | (uint32_t)(tbase + p)));
                 wcount += __popc(hm);
@@ -290,33 +313,26 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             __syncwarp();  // orders the fill above, and the list writes, before the rounds
             while (wcount >= 32) round(32);
         } else {
-            // general path (T > 128, or a frame with an unbounded box): every lane resolves its point itself
+            // general path (more than 254 boxes, or a frame with an unbounded box): every box is tested, as the reference does
             for (int st = 0; st < PIB_WPTS / 32; st++) {
                 const int p = st * 32 + lane;
                 if (wbase + p >= np) continue;
                 const float* q = sp + (wbase + p) * 3;
                 const float x = q[0], y = q[1], z = q[2];
                 int r = -1;
-                if (use_grid) {
-                    const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
-                    if (any_valid && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny)
-                        r = first_box_in_cell<FL>(grid + ((int)fy * g.nx + (int)fx) * W, W, srec, x, y, z);
-                } else {
-                    for (int k = 0; k < T; k++)
-                        if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
-                            r = k;
-                            break;
-                        }
-                }
+                for (int k = 0; k < T; k++)
+                    if (pt_in_box<FL>(x, y, z, srec[2 * k], srec[2 * k + 1])) {
+                        r = k;
+                        break;
+                    }
                 go[tbase + p] = r;
             }
         }
         __syncthreads();  // everyone is done with this stage: refill it
         if (tid == 0 && t + PIB_STAGES < ntiles) issue(t + PIB_STAGES);
     }
-    if (fast && wcount > 0) round(wcount);
+    if (use_grid && wcount > 0) round(wcount);
 }
-
 
 constexpr int PIBM_BOXES = 32;  // boxes per CTA in the mask form
 

@@ -88,9 +88,9 @@ extern "C" int emu_debug_pair(const float* a, const float* b, float* verts /*[16
 
 #include <vector>
 
-// boxes (T,7), pts (M,3) -> out (M); grid_words = capacity of the cell-mask array (kernel: 12288).
+// boxes (T,7), pts (M,3) -> out (M); ncells = capacity of the cell array (kernel: 12288).
 // returns the number of (point, box) predicate evaluations performed (for the pruning statistics)
-extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float* pts, long long M, int32_t* out, int grid_words,
+extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float* pts, long long M, int32_t* out, int ncells,
                                          int* used_grid) {
     std::vector<float4> rec(2 * (size_t)T);
     float lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY, sum_ext = 0.f, nv = 0.f;
@@ -105,15 +105,14 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
             nv += 1.f;
         }
     }
-    const int W = (T + 31) >> 5;
-    const bool use_grid = bounded && W <= grid_words;
+    const bool use_grid = bounded && T <= PIB_COMPACT_MAX_BOXES;
     *used_grid = use_grid ? 1 : 0;
     long long tests = 0;
-    std::vector<uint32_t> grid((size_t)grid_words, 0u);
+    std::vector<uint32_t> cells((size_t)ncells, PIB_CELL_EMPTY);
     PibGrid g{};
     if (use_grid && nv > 0.f) {
-        g = pib_make_grid(lo_x, hi_x, lo_y, hi_y, sum_ext / nv, grid_words / W);
-        for (int k = 0; k < T; k++) {
+        g = pib_make_grid(lo_x, hi_x, lo_y, hi_y, sum_ext / nv, ncells, 0.5f);
+        for (int k = T - 1; k >= 0; k--) {  // any insertion order must give the same lists: go backwards on purpose
             float ex, ey;
             bool dummy = true;
             const float4 r0 = rec[2 * k], r1 = rec[2 * k + 1];
@@ -122,25 +121,27 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
             const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
             for (int iy = iy0; iy <= iy1; iy++)
                 for (int ix = ix0; ix <= ix1; ix++)
-                    if (pib_cell_touches(r0, r1, g, ix, iy)) grid[(size_t)(iy * g.nx + ix) * W + (k >> 5)] |= 1u << (k & 31);
+                    if (pib_cell_touches(r0, r1, g, ix, iy)) cells[(size_t)iy * g.nx + ix] = pib_compact_insert(cells[(size_t)iy * g.nx + ix], (uint32_t)k);
         }
     }
     for (long long p = 0; p < M; p++) {
         const float x = pts[3 * p], y = pts[3 * p + 1], z = pts[3 * p + 2];
         int r = -1;
         if (use_grid) {
-            const float fx = pib_cellf(x, g.x0, g.invx), fy = pib_cellf(y, g.y0, g.invy);
-            if (nv > 0.f && fx >= 0.f && fx < (float)g.nx && fy >= 0.f && fy < (float)g.ny) {
-                const uint32_t* cw = grid.data() + (size_t)((int)fy * g.nx + (int)fx) * W;
-                for (int w = 0; w < W && r < 0; w++) {
-                    uint32_t bits = cw[w];
-                    while (bits) {
-                        const int k = (w << 5) + __ffs(bits) - 1;
-                        bits &= bits - 1;
+            const int ix = __float2int_rd(pib_cellf(x, g.x0, g.invx)), iy = __float2int_rd(pib_cellf(y, g.y0, g.invy));
+            if (nv > 0.f && (unsigned)ix < (unsigned)g.nx && (unsigned)iy < (unsigned)g.ny) {
+                const uint32_t ids = cells[(size_t)iy * g.nx + ix];
+                for (int sl = 0; sl < 4 && r < 0; sl++) {
+                    const uint32_t id = (ids >> (8 * sl)) & 0xffu;
+                    if (id >= PIB_ID_MORE) break;
+                    tests++;
+                    if (pt_in_box<1>(x, y, z, rec[2 * id], rec[2 * id + 1])) r = (int)id;
+                }
+                if (r < 0 && (ids >> 24) == PIB_ID_MORE)
+                    for (int k = (int)((ids >> 16) & 0xffu) + 1; k < T; k++) {
                         tests++;
                         if (pt_in_box<1>(x, y, z, rec[2 * k], rec[2 * k + 1])) { r = k; break; }
                     }
-                }
             }
         } else {
             for (int k = 0; k < T; k++) {
@@ -151,27 +152,4 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
         out[p] = r;
     }
     return tests;
-}
-
-// diagnostics: classify pairs: 0 = zero/cnt<=2, 1 = fast path, 2 = deferred (cnt > 8), 3 = deferred (angular near-tie)
-extern "C" void emu_classify(const float* a, int64_t n, const float* b, int64_t m, int* hist /*[4]*/, unsigned tie_units) {
-    float4* ra = new float4[(size_t)n * REC_F4];
-    float4* rb = new float4[(size_t)m * REC_F4];
-    for (int64_t i = 0; i < n; i++) make_record<1>(a + i * 7, ra + i * REC_F4);
-    for (int64_t j = 0; j < m; j++) make_record<1>(b + j * 7, rb + j * REC_F4);
-    float2 slab[16];
-    for (int64_t i = 0; i < n; i++)
-        for (int64_t j = i + 1; j < m; j++) {
-            const float4 *A = ra + i * REC_F4, *B = rb + j * REC_F4;
-            if (!cull_survives(A[REC_CULL], B[REC_CULL])) { hist[0]++; continue; }
-            uint32_t xm, cm;
-            pair_masks<1>(A, B, xm, cm);
-            const int cnt = __popc(xm) + __popc(cm);
-            if (cnt <= 2) { hist[0]++; continue; }
-            if (cnt > 8) { hist[2]++; continue; }
-            const float v = overlap_area<1>(A, B, slab, 1, 1u);
-            hist[v < 0.f ? 3 : 1]++;
-        }
-    delete[] ra;
-    delete[] rb;
 }

@@ -231,6 +231,28 @@ def test_points_in_boxes_vs_oracle_and_golden(ggpu):
     assert np.array_equal(g, ggpu["pib_idx"])
 
 
+@pytest.mark.parametrize("T,M,spread", [(200, 12345, 0.08), (254, 5000, 1.0), (255, 3001, 1.0), (300, 2048, 1.0), (3, 70001, 1.0)])
+def test_points_grid_paths_vs_oracle(T, M, spread):
+    """compact cell lists incl. overflowing cells (tight cluster), the 254-box boundary, the test-every-box path,
+    point counts that are not multiples of 4 (fallback tile loads) and frames split over several CTAs"""
+    r = np.random.default_rng(T + M)
+    B = 3
+    boxes = np.stack([synth.gt_boxes(T, int(r.integers(1 << 30))) for _ in range(B)])
+    c = boxes[:, :, 0:2].mean(1, keepdims=True)
+    boxes[:, :, 0:2] = c + (boxes[:, :, 0:2] - c) * spread
+    pts = np.empty((B, M, 3), np.float32)
+    for b in range(B):
+        k = r.integers(0, T, M)
+        loc = r.uniform(-0.6, 0.6, (M, 3)) * boxes[b, k, 3:6]
+        co, si = np.cos(boxes[b, k, 6]), np.sin(boxes[b, k, 6])
+        pts[b, :, 0] = boxes[b, k, 0] + loc[:, 0] * co - loc[:, 1] * si
+        pts[b, :, 1] = boxes[b, k, 1] + loc[:, 0] * si + loc[:, 1] * co
+        pts[b, :, 2] = boxes[b, k, 2] + loc[:, 2]
+    got = PU.points_in_boxes_gpu(cu(pts), cu(boxes)).cpu().numpy()
+    want = O.points_in_boxes_idx(pts, boxes, O.FLAVOR_CUDA)
+    assert np.array_equal(got, want), f"{(got != want).sum()} of {got.size} differ"
+
+
 def test_points_edge_cases():
     # ragged sizes, padded all-zero boxes (dataset.py:172-177 pads GT with zeros; they are NOT skipped)
     pts = np.zeros((2, 1001, 3), np.float32)

@@ -116,10 +116,13 @@ def boundary_points(r, b, m):
     return np.stack([b[k, 0] + loc[:, 0] * c - loc[:, 1] * s, b[k, 1] + loc[:, 0] * s + loc[:, 1] * c, b[k, 2] + loc[:, 2]], 1).astype(np.float32)
 
 
-@pytest.mark.parametrize("T,M,scale", [(1, 3000, 1), (7, 8000, 0.2), (100, 16384, 1), (300, 10000, 3), (1000, 8000, 1), (4096, 4000, 1)])
-def test_grid_cull_of_points_in_boxes_is_exact(emu, T, M, scale):
+@pytest.mark.parametrize("T,M,scale,spread", [(1, 3000, 1, 1), (7, 8000, 0.2, 1), (100, 16384, 1, 1), (254, 10000, 3, 1), (200, 10000, 1, 0.08),
+                                               (255, 4000, 1, 1), (1000, 3000, 1, 1)])
+def test_grid_cull_of_points_in_boxes_is_exact(emu, T, M, scale, spread):
+    """spread = 0.08 packs 200 boxes into a few metres: most cells overflow their four list slots"""
     r = np.random.default_rng(T)
     b = synth.gt_boxes(T, int(r.integers(1 << 30)))
+    b[:, 0:2] = b[:, 0:2].mean(0) + (b[:, 0:2] - b[:, 0:2].mean(0)) * spread
     b[:, 3:6] *= scale
     p = boundary_points(r, b, M)
     if T >= 100:  # padded all-zero box, negative size, NaN heading, NaN centre: none may break the cull
@@ -129,8 +132,8 @@ def test_grid_cull_of_points_in_boxes_is_exact(emu, T, M, scale):
         b[9, 0] = np.nan
     got, tests, used = pib(emu, b, p)
     want = O.points_in_boxes_idx(p[None], b[None], O.FLAVOR_CUDA)[0]
-    assert used == 1 and np.array_equal(got, want)
-    assert tests < 0.3 * M * T or T < 8  # the grid prunes
+    assert used == (1 if T <= 254 else 0) and np.array_equal(got, want)
+    assert tests < 0.3 * M * T or T < 8 or T > 254  # the grid prunes
 
 
 def test_grid_cull_cfg3_and_fallbacks(emu):
