@@ -127,6 +127,28 @@ __device__ __forceinline__ bool pib_cell_touches(const float4 r0, const float4 r
     return fabsf(lx) <= r1.z + slack + hx * ac + hy * as && fabsf(ly) <= r1.w + slack + hx * as + hy * ac;
 }
 
+// The same test with everything that does not depend on the cell hoisted into a per-box constant block:
+//   m0 = (cosa, sina, tX, tY)   tX = tx + slack + hx|c| + hy|s|,  tY = ty + slack + hx|s| + hy|c|
+//   m1 = (x of the centre of cell column 0 minus cx, y of the centre of cell row 0 minus cy, cell width, cell height)
+// so that one (box, cell) pair costs ~10 instructions.
+__device__ __forceinline__ void pib_touch_consts(const float4 r0, const float4 r1, const PibGrid& g, float4& m0, float4& m1) {
+    const float wx = 1.0f / g.invx, wy = 1.0f / g.invy;
+    const float hx = 0.5f * wx * 1.0001f + 2e-6f * (fabsf(g.x0) + wx * (float)g.nx);
+    const float hy = 0.5f * wy * 1.0001f + 2e-6f * (fabsf(g.y0) + wy * (float)g.ny);
+    const float c = r1.x, s = r1.y, ac = fabsf(c), as = fabsf(s);
+    const float E = r1.z * ac + r1.w * as, F = r1.w * ac + r1.z * as;
+    const float slack = 1e-4f * (E + F) + 4e-7f * (fabsf(r0.x) + fabsf(r0.y));
+    m0 = make_float4(c, s, r1.z + slack + hx * ac + hy * as, r1.w + slack + hx * as + hy * ac);
+    m1 = make_float4(g.x0 + 0.5f * wx - r0.x, g.y0 + 0.5f * wy - r0.y, wx, wy);
+}
+__device__ __forceinline__ bool pib_cell_touches_fast(const float4 m0, const float4 m1, const int ix, const int iy) {
+    // centre of the cell relative to the box centre; it differs from pib_cell_touches' value only by rounding,
+    // which the 1e-4 relative inflation of the cell covers many times over
+    const float sx = m1.x + (float)ix * m1.z, sy = m1.y + (float)iy * m1.w;
+    const float lx = sx * m0.x - sy * m0.y, ly = sy * m0.x + sx * m0.y;
+    return fabsf(lx) <= m0.z && fabsf(ly) <= m0.w;
+}
+
 // ---- compact candidate lists: one 32-bit word per cell ------------------------------------------
 // bytes 0..3 = up to four candidate box indices in ASCENDING order, 0xFF = empty slot.  A fifth candidate turns
 // byte 3 into the marker 0xFE: "more candidates exist, all with an index above byte 2" -- the point lookup then

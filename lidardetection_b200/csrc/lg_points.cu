@@ -26,6 +26,7 @@ constexpr int PIB_TILE = 1024;                 // points per stage
 constexpr int PIB_STAGES = 3;
 constexpr int PIB_TILE_BYTES = PIB_TILE * 12;  // 12 KB
 constexpr int PIB_CELLS = 12288;               // 48 KB of 32-bit candidate lists (lg_pib.cuh)
+constexpr float PIB_MIN_CELL = 0.6f;            // cells no smaller than 0.6 x the mean footprint half-extent
 constexpr int PIB_WARPS = PIB_THREADS / 32;
 constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
 constexpr int PIB_WLIST = 31 + PIB_WPTS + 1;    // per-warp work list (float4 items): leftover + one tile, padded to 160
@@ -62,7 +63,8 @@ struct PibSmem {
     static constexpr size_t list_bytes = (size_t)PIB_WARPS * PIB_WLIST * sizeof(float4);
     static size_t total(int T) {
         const int tc = T < PIB_COMPACT_MAX_BOXES ? T : PIB_COMPACT_MAX_BOXES;
-        return stage_bytes + cell_bytes + list_bytes + (size_t)T * 2 * sizeof(float4) + (size_t)tc * sizeof(int4) + (size_t)(tc + 8) * sizeof(int);
+        return stage_bytes + cell_bytes + list_bytes + (size_t)T * 2 * sizeof(float4) + (size_t)tc * (sizeof(int4) + 2 * sizeof(float4)) +
+               (size_t)(tc + 8) * sizeof(int);
     }
 };
 
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
     float4* lists = reinterpret_cast<float4*>(cells + PIB_CELLS);
     float4* srec = lists + PIB_WARPS * PIB_WLIST;
     int4* srange = reinterpret_cast<int4*>(srec + 2 * T);  // per box: ix0, iy0, cells per row, cells
-    int* sprefix = reinterpret_cast<int*>(srange + min(T, PIB_COMPACT_MAX_BOXES));
+    float4* stouch = reinterpret_cast<float4*>(srange + min(T, PIB_COMPACT_MAX_BOXES));  // per box: pib_touch_consts
+    int* sprefix = reinterpret_cast<int*>(stouch + 2 * min(T, PIB_COMPACT_MAX_BOXES));
     __shared__ uint64_t bars[PIB_STAGES];
     __shared__ float red[8][6];
     __shared__ PibGrid sgrid;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
         const bool ok = nv >= 0.f && T <= PIB_COMPACT_MAX_BOXES;  // more boxes than the 8-bit lists can name: every box is tested
         s_use_grid = ok ? 1 : 0;
         s_nvalid = nv > 0.f ? 1 : 0;
-        if (ok && nv > 0.f) sgrid = pib_make_grid(a, bb, c, d, se / nv, PIB_CELLS, 0.5f);
+        if (ok && nv > 0.f) sgrid = pib_make_grid(a, bb, c, d, se / nv, PIB_CELLS, PIB_MIN_CELL);
     }
     __syncthreads();
     const bool use_grid = s_use_grid != 0, any_valid = s_nvalid != 0;
@@ -181,6 +184,10 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
                 const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
                 const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
                 rg = make_int4(ix0, iy0, ix1 - ix0 + 1, (ix1 - ix0 + 1) * (iy1 - iy0 + 1));
+                float4 m0, m1;
+                pib_touch_consts(r0, r1, g, m0, m1);
+                stouch[2 * k] = m0;
+                stouch[2 * k + 1] = m1;
             }
             srange[k] = rg;
         }
@@ -220,7 +227,7 @@ __global__ void __launch_bounds__(PIB_THREADS, 2)
             const int local = idx - sprefix[lo];
             const int cy = local / rg.z, cx = local - cy * rg.z;
             const int ix = rg.x + cx, iy = rg.y + cy;
-            if (pib_cell_touches(srec[2 * lo], srec[2 * lo + 1], g, ix, iy)) {
+            if (pib_cell_touches_fast(stouch[2 * lo], stouch[2 * lo + 1], ix, iy)) {
                 uint32_t* cw = cells + iy * g.nx + ix;
                 uint32_t old = *cw, assumed;
                 do {

@@ -111,7 +111,7 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
     std::vector<uint32_t> cells((size_t)ncells, PIB_CELL_EMPTY);
     PibGrid g{};
     if (use_grid && nv > 0.f) {
-        g = pib_make_grid(lo_x, hi_x, lo_y, hi_y, sum_ext / nv, ncells, 0.5f);
+        g = pib_make_grid(lo_x, hi_x, lo_y, hi_y, sum_ext / nv, ncells, 0.6f);
         for (int k = T - 1; k >= 0; k--) {  // any insertion order must give the same lists: go backwards on purpose
             float ex, ey;
             bool dummy = true;
@@ -119,9 +119,11 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
             if (!pib_footprint(r0, r1, ex, ey, dummy)) continue;
             const int ix0 = pib_cell_clamped(r0.x - ex, g.x0, g.invx, g.nx), ix1 = pib_cell_clamped(r0.x + ex, g.x0, g.invx, g.nx);
             const int iy0 = pib_cell_clamped(r0.y - ey, g.y0, g.invy, g.ny), iy1 = pib_cell_clamped(r0.y + ey, g.y0, g.invy, g.ny);
+            float4 m0, m1;
+            pib_touch_consts(r0, r1, g, m0, m1);
             for (int iy = iy0; iy <= iy1; iy++)
                 for (int ix = ix0; ix <= ix1; ix++)
-                    if (pib_cell_touches(r0, r1, g, ix, iy)) cells[(size_t)iy * g.nx + ix] = pib_compact_insert(cells[(size_t)iy * g.nx + ix], (uint32_t)k);
+                    if (pib_cell_touches_fast(m0, m1, ix, iy)) cells[(size_t)iy * g.nx + ix] = pib_compact_insert(cells[(size_t)iy * g.nx + ix], (uint32_t)k);
         }
     }
     for (long long p = 0; p < M; p++) {
