@@ -133,3 +133,48 @@ def test_synthetic_generators_are_seeded_and_shaped():
     assert x.shape == y.shape == (1000, 7)
     bb, ss = synth.cfg5(n_frames=2, n_classes=3, n_boxes=50)
     assert bb.shape == (2, 3, 50, 7) and ss.shape == (2, 3, 50)
+
+
+def test_sorting_networks_sort_every_input():
+    """0-1 principle over the compare-exchange lists parsed out of lg_geom.cuh"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("check_networks", os.path.join(ROOT, "tools", "check_networks.py"))
+    cn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cn)
+    nets = cn.networks()
+    assert set(nets) >= {"sort8", "sort16"}
+    for name, (n, net) in nets.items():
+        assert cn.sorts(n, net), name
+
+
+def test_compact_cell_list_insert_is_order_independent():
+    """lg_pib.cuh pib_compact_insert, restated: any insertion order yields the 3-4 smallest ids (+ overflow marker)"""
+    import itertools
+
+    def insert(w, k):
+        a, b, c, d = w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff, w >> 24
+        if k < a:
+            a, k = k, a
+        if k < b:
+            b, k = k, b
+        if k < c:
+            c, k = k, c
+        top = 0xFE if d == 0xFE else (k if d == 0xFF else 0xFE)
+        return a | (b << 8) | (c << 16) | (top << 24)
+
+    for ids in ([7], [3, 9], [1, 2, 3], [5, 1, 9, 4], [8, 6, 7, 5, 3], [10, 20, 30, 40, 50, 60]):
+        want = sorted(ids)
+        results = set()
+        for perm in itertools.permutations(ids):
+            w = 0xFFFFFFFF
+            for k in perm:
+                w = insert(w, k)
+            results.add(w)
+        assert len(results) == 1
+        w = results.pop()
+        got = [(w >> (8 * i)) & 0xff for i in range(4)]
+        if len(ids) <= 4:
+            assert got == want + [0xFF] * (4 - len(ids))
+        else:
+            assert got == want[:3] + [0xFE]
