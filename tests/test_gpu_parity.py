@@ -318,3 +318,56 @@ def test_live_against_reference_cuda_kernels():
     want = torch.full((4, 16384), -1, dtype=torch.int32, device=dev())
     roi.points_in_boxes_gpu(cu(rois), cu(pts), want)
     assert torch.equal(PU.points_in_boxes_gpu(cu(pts), cu(rois)), want)
+
+
+# ------------------------------------------------------------------------------------------ post-processing front end (8f-1)
+def _ref_class_agnostic_nms(box_scores, box_preds, cfg, score_thresh):
+    """the reference's model_nms_utils.class_agnostic_nms, restated around the ORACLE's NMS (numpy)"""
+    idx = np.nonzero(box_scores >= score_thresh)[0] if score_thresh is not None else np.arange(len(box_scores))
+    s, b = box_scores[idx], box_preds[idx]
+    if len(s) == 0:
+        return np.zeros(0, np.int64)
+    order = np.argsort(-s, kind="stable")[: min(cfg["NMS_PRE_MAXSIZE"], len(s))]
+    keep = O.nms(b[order][:, :7], s[order], cfg["NMS_THRESH"], normal=cfg["NMS_TYPE"] == "nms_normal_gpu", flavor=O.FLAVOR_CUDA)
+    return idx[order[keep[: cfg["NMS_POST_MAXSIZE"]]]]
+
+
+@pytest.mark.parametrize("nms_type", ["nms_gpu", "nms_normal_gpu"])
+def test_post_processing_front_end_batched_and_per_frame(nms_type):
+    from lidardetection_b200 import model_nms_utils as MU
+
+    cfg = {"NMS_TYPE": nms_type, "NMS_THRESH": 0.1, "NMS_PRE_MAXSIZE": 512, "NMS_POST_MAXSIZE": 40, "MULTI_CLASSES_NMS": False}
+    B, N = 5, 3000
+    boxes, scores = synth.nms_frames(B, N, seed=77)
+    boxes9 = np.concatenate([boxes, np.zeros((B, N, 2), np.float32)], 2)  # 7 + C columns, as the detectors pass them
+    scores[4] *= 0.05  # a frame where nothing passes the score threshold
+    tb, ts = cu(boxes9), cu(scores)
+    sel, num, sc = MU.class_agnostic_nms_batched(ts, tb, cfg, score_thresh=0.3)
+    assert sel.shape == (B, 40) and num.dtype == torch.int32
+    for f in range(B):
+        want = _ref_class_agnostic_nms(scores[f], boxes9[f], cfg, 0.3)
+        got = sel[f, : int(num[f])].cpu().numpy()
+        assert np.array_equal(got, want), f
+        assert bool((sel[f, int(num[f]):] == -1).all())
+        one, one_scores = MU.class_agnostic_nms(ts[f], tb[f], cfg, score_thresh=0.3)  # the reference's per-frame entry point
+        assert np.array_equal(one.cpu().numpy(), want)
+        assert torch.equal(one_scores, ts[f][one]) and torch.equal(sc[f, : int(num[f])], ts[f][one])
+    assert int(num[4]) == 0
+
+
+def test_multi_classes_nms_batched_matches_per_class_oracle():
+    from lidardetection_b200 import model_nms_utils as MU
+
+    cfg = {"NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.2, "NMS_PRE_MAXSIZE": 300, "NMS_POST_MAXSIZE": 25}
+    B, N, C = 2, 900, 3
+    boxes, _ = synth.nms_frames(B, N, seed=5)
+    r = np.random.default_rng(9)
+    cls = r.permuted(np.tile(np.linspace(0.01, 0.99, N * C, dtype=np.float32), (B, 1)), axis=1).reshape(B, N, C)
+    sel, num, _ = MU.multi_classes_nms_batched(cu(cls), cu(boxes), cfg, score_thresh=0.2)
+    for b in range(B):
+        for k in range(C):
+            want = _ref_class_agnostic_nms(cls[b, :, k], boxes[b], cfg, 0.2)
+            assert np.array_equal(sel[b, k, : int(num[b, k])].cpu().numpy(), want), (b, k)
+    ps, pl, pb = MU.multi_classes_nms(cu(cls[0]), cu(boxes[0]), cfg, score_thresh=0.2)  # the reference's per-frame signature
+    want_idx = np.concatenate([_ref_class_agnostic_nms(cls[0, :, k], boxes[0], cfg, 0.2) for k in range(C)])
+    assert np.array_equal(pb.cpu().numpy(), boxes[0][want_idx]) and len(ps) == len(pl) == len(want_idx)

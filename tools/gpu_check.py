@@ -207,6 +207,23 @@ if roi is not None:
     out = torch.full((64, pts.shape[1]), -1, dtype=torch.int32, device=dev)
     timed("ref  points 64x16384x100", lambda: roi.points_in_boxes_gpu(tr, tp, out))
 
+# post-processing front end: 64 frames x 70,400 candidates (SECOND KITTI head), score_thresh 0.1, 4096 -> 500
+from lidardetection_b200 import model_nms_utils as MU  # noqa: E402
+
+cfgp = {"NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.01, "NMS_PRE_MAXSIZE": 4096, "NMS_POST_MAXSIZE": 500}
+bx, sc = synth.cfg2(n_frames=64, n_boxes=4096)
+rr = np.random.default_rng(1)
+allb = np.concatenate([bx, synth.gt_boxes(64 * (70400 - 4096), 9).reshape(64, -1, 7)], 1)
+alls = np.concatenate([sc, rr.uniform(0.0, 0.099, (64, 70400 - 4096)).astype(np.float32)], 1)
+perm = rr.permutation(70400)
+tb_, ts_ = torch.from_numpy(allb[:, perm]).to(dev), torch.from_numpy(alls[:, perm]).to(dev)
+timed("ours post-proc batched 64x70400", lambda: MU.class_agnostic_nms_batched(ts_, tb_, cfgp, score_thresh=0.1))
+timed("ours post-proc per-frame loop (reference structure)", lambda: [MU.class_agnostic_nms(ts_[f], tb_[f], cfgp, score_thresh=0.1) for f in range(64)])
+selb, numb, _ = MU.class_agnostic_nms_batched(ts_, tb_, cfgp, score_thresh=0.1)
+okp = all(torch.equal(MU.class_agnostic_nms(ts_[f], tb_[f], cfgp, score_thresh=0.1)[0], selb[f, : int(numb[f])]) for f in range(0, 64, 7))
+print("post-proc batched == per-frame:", okp)
+res["post_processing_batched_equals_per_frame"] = bool(okp)
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "gpu_check.json"), "w") as f:
     json.dump(res, f, indent=1)
