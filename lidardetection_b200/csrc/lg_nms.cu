@@ -269,6 +269,7 @@ constexpr int LZ_QCAP = 8192;    // u32 codes: candidate << 16 | box
 constexpr int LZ_RARECAP = LZ_QCAP + 1024;
 constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
 constexpr int LZ_SWEEP = LZ_THREADS;  // columns per sweep of the 16 warps
+constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared memory per CTA on sm_100a, minus the static part
 
 struct LazyLayout {
     int words;         // alive words
@@ -515,7 +516,9 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes + NMS_STATS_BYTES);
     const bool strict = (flags & LG_FLAG_STRICT_FP32) != 0;
-    const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0;
+    // the lazy kernel keeps the alive bitmap and 8 suppression rows of a problem in shared memory: beyond ~50,000 boxes
+    // they no longer fit next to the queues, and the mask + sweep formulation takes over (same keep list)
+    const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0 || LazyLayout(nmax).total > LZ_SMEM_LIMIT;
     int rc;
     if (!normal) {
         if (phases & PHASE_RECORDS) {
@@ -570,7 +573,8 @@ extern "C" size_t lg_nms_workspace_bytes_ex(int P, int nmax, int normal, unsigne
     if (P <= 0 || nmax <= 0) return 0;
     const size_t cbk = ((size_t)nmax + 63) / 64;
     size_t b = lg::align_up((size_t)P * nmax * lg::REC_F4 * sizeof(float4), 256) + lg::NMS_STATS_BYTES + 16;
-    if (normal || (flags & LG_FLAG_NMS_FULL_MASK)) b += (size_t)P * nmax * cbk * sizeof(unsigned long long);
+    if (normal || (flags & LG_FLAG_NMS_FULL_MASK) || lg::LazyLayout(nmax).total > lg::LZ_SMEM_LIMIT)
+        b += (size_t)P * nmax * cbk * sizeof(unsigned long long);
     return b;
 }
 

@@ -176,6 +176,18 @@ def test_nms_lazy_equals_full_mask_equals_oracle(n, thresh, seed):
             print("near-duplicate frame differs from the CPU oracle:", explain_nms_mismatch(boxes[f][order], inv[got], inv[want], thresh, False))
 
 
+@pytest.mark.parametrize("n", [20000, 52000])
+def test_nms_large_problems(n):
+    """20,000 boxes: lazy kernel with the cull quads beyond its 4096-entry smem cache; 52,000: the alive / suppression
+    rows no longer fit in shared memory and the mask + sweep formulation takes over -- same keep list either way"""
+    boxes, scores = synth.nms_frames(1, n, seed=n, k_range=(200, 300))
+    tb, ts = cu(boxes[0]), cu(scores[0])
+    keep = U.nms_gpu(tb, ts, 0.05)[0].cpu().numpy()
+    order = ts.sort(0, descending=True)[1].cpu().numpy()
+    want = O.nms(boxes[0], scores[0], 0.05, flavor=O.FLAVOR_CUDA, order=order)
+    assert np.array_equal(keep, want), (len(keep), len(want))
+
+
 def test_nms_vs_golden_reference_cuda(ggpu):
     boxes, scores = ggpu["nms_boxes"], ggpu["nms_scores"]
     for f in range(boxes.shape[0]):
