@@ -86,6 +86,18 @@ LG_API int lg_boxes_iou_bev(const float *boxes_a, int64_t n, const float *boxes_
 LG_API int lg_boxes_iou3d(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, float *out, int64_t ld_out,
                    void *ws, size_t ws_bytes, unsigned flags, void *stream);
 
+/* Row / column maxima of the N x M matrix WITHOUT materialising it (the consumers' epilogue:
+ * proposal_target_layer.py:107 `torch.max(iou3d, dim=1)`, axis_aligned_target_assigner.py:150-169 argmax over both axes,
+ * detector3d_template.py:310-313; decisive at 200k x 200k, where the matrix is 160 GB).
+ *   kind: 0 = overlap_bev, 1 = iou_bev, 2 = iou3d (same arithmetic as the matrix entry points)
+ *   row_max[i] = max_j v(i, j), row_argmax[i] = the LOWEST j that attains it (torch.max's convention; 0 for an all-zero row);
+ *   col_max / col_argmax likewise over i.  Any of the four output pointers may be NULL.
+ * ws must hold lg_iou_reduce_workspace_bytes(n, m) bytes.  n, m < 2^32 - 1. */
+LG_API size_t lg_iou_reduce_workspace_bytes(int64_t n, int64_t m);
+LG_API int lg_boxes_iou_reduce(const float *boxes_a, int64_t n, const float *boxes_b, int64_t m, int kind, float *row_max,
+                               int64_t *row_argmax, float *col_max, int64_t *col_argmax, void *ws, size_t ws_bytes, unsigned flags,
+                               void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * NMS, rotated (nms_gpu: iou3d_nms.cpp:90-136, kernel.cu:267-311) and axis-aligned
  * (nms_normal_gpu: iou3d_nms.cpp:139-186, kernel.cu:314-372), batched over P independent problems.

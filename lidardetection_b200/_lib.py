@@ -38,6 +38,10 @@ def lib():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [vp, i64, vp, i64, vp, i64, vp, sz, u32, vp]
+    L.lg_iou_reduce_workspace_bytes.restype = sz
+    L.lg_iou_reduce_workspace_bytes.argtypes = [i64, i64]
+    L.lg_boxes_iou_reduce.restype = C.c_int
+    L.lg_boxes_iou_reduce.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, vp, vp, sz, u32, vp]
     L.lg_nms_workspace_bytes.restype = sz
     L.lg_nms_workspace_bytes.argtypes = [i32, i32]
     L.lg_nms_workspace_bytes_ex.restype = sz
@@ -66,7 +70,7 @@ def lib():
 
 EXPORTS = [
     "lg_version", "lg_last_error_string", "lg_check_device",
-    "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d",
+    "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d", "lg_iou_reduce_workspace_bytes", "lg_boxes_iou_reduce",
     "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
 ]

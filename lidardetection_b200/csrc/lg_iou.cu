@@ -63,11 +63,20 @@ struct StripSmem {
 // A tile is 32 rows x 128 columns; a warp owns 8 of its rows (rsub + 4k) x 64 columns, two adjacent columns per
 // lane.  The exact-zero cull of a full tile runs on packed FP32 pairs -- FADD2 / FMUL2 / FFMA2, the two columns of
 // a lane in one instruction -- and stores the two zeros of a culled pair with one 8-byte st.global.cs.
-template <int FL>
-__global__ void __launch_bounds__(ST_THREADS, 3)
+// key of (value, index) for atomicMax: a larger value wins, equal values keep the LOWER index (torch.max's "first maximal value")
+__device__ __forceinline__ unsigned long long max_key(float v, unsigned idx) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+
+// REDUCE = false: write the N x M matrix.  REDUCE = true: write nothing of it; keep per-row / per-column (max, argmax)
+// keys instead (what the target assigners and the evaluation actually consume) -- the 200k x 200k matrix
+// (160 GB) is then never materialised.
+template <int FL, bool REDUCE>
+__global__ void __launch_bounds__(ST_THREADS, REDUCE ? 2 : 3)
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
                      const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
-                     const int mode, const int cols_per_cta, const int64_t strips_m) {
+                     const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,
+                     unsigned long long* __restrict__ colkey) {
     constexpr int NT = ST_THREADS;
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
@@ -94,9 +103,17 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     const float4* const gcull = cull_b + col0;
     float* const outb = out + row0 * ld + col0;
     // 8-byte stores need an even pitch and an 8-byte aligned first element of every row of this CTA
-    const bool vec2_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(outb) & 7) == 0);
+    const bool vec2_ok = REDUCE || (((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(outb) & 7) == 0));
     auto emit = [&](int r, int c, float ov, const float4* A, const float4* B) {
-        __stcs(outb + (int64_t)r * ld + c, finish_pair(mode, ov, A, B));
+        const float v = finish_pair(mode, ov, A, B);
+        if (REDUCE) {
+            if (v > 0.f) {  // zeros never beat the initial key (0.0, index 0)
+                if (rowkey) atomicMax(rowkey + row0 + r, max_key(v, (unsigned)col0 + (unsigned)c));
+                if (colkey) atomicMax(colkey + col0 + c, max_key(v, (unsigned)row0 + (unsigned)r));
+            }
+        } else {
+            __stcs(outb + (int64_t)r * ld + c, v);
+        }
     };
     WarpQueue q;
     q.list = lists + warp * (WQ_CAP + 1 + WR_CAP);
@@ -136,13 +153,15 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
                     unpack2(d2, d2a, d2b);
                     unpack2(r2, r2a, r2b);
                     const bool s0 = !(d2a > r2a), s1 = !(d2b > r2b);  // NaN => keep: the polygon path decides
-                    if (!s0 && !s1) {
-                        __stcs(reinterpret_cast<float2*>(outp), make_float2(0.f, 0.f));  // culled: exactly +0.0, written once
-                    } else {
-                        if (!s0) __stcs(outp, 0.f);
-                        if (!s1) __stcs(outp + 1, 0.f);
+                    if (!REDUCE) {
+                        if (!s0 && !s1) {
+                            __stcs(reinterpret_cast<float2*>(outp), make_float2(0.f, 0.f));  // culled: exactly +0.0, written once
+                        } else {
+                            if (!s0) __stcs(outp, 0.f);
+                            if (!s1) __stcs(outp + 1, 0.f);
+                        }
+                        outp += ostep;
                     }
-                    outp += ostep;
                     mk0[k] = __ballot_sync(0xffffffffu, s0);
                     mk1[k] = __ballot_sync(0xffffffffu, s1);
                 }
@@ -156,11 +175,11 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
                         const float4 ac = sA[r * REC_F4 + REC_CULL];
                         if (v0) {
                             s0 = cull_survives(ac, b0);
-                            if (!s0) __stcs(outp, 0.f);
+                            if (!REDUCE && !s0) __stcs(outp, 0.f);
                         }
                         if (v1) {
                             s1 = cull_survives(ac, b1);
-                            if (!s1) __stcs(outp + 1, 0.f);
+                            if (!REDUCE && !s1) __stcs(outp + 1, 0.f);
                         }
                     }
                     outp += ostep;
@@ -329,10 +348,62 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
         return LG_ERR_TOO_LARGE;
     }
-    auto kern = iou_strip_kernel<FL>;
+    auto kern = iou_strip_kernel<FL, false>;
     if ((rc = set_smem(kern, StripSmem::total))) return rc;
-    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m);
+    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr);
     return check_launch("iou_strip_kernel");
+}
+
+__global__ void __launch_bounds__(256) key_init_kernel(unsigned long long* __restrict__ k, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) k[i] = 0x00000000FFFFFFFFull;  // (value 0.0, index 0)
+}
+
+__global__ void __launch_bounds__(256) key_unpack_kernel(const unsigned long long* __restrict__ k, int64_t count, float* __restrict__ vmax,
+                                                         int64_t* __restrict__ arg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const unsigned long long key = k[i];
+        if (vmax) vmax[i] = __uint_as_float((unsigned)(key >> 32));
+        if (arg) arg[i] = (int64_t)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    }
+}
+
+template <int FL>
+static int run_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, void* ws, int mode, float* row_max, int64_t* row_arg,
+                          float* col_max, int64_t* col_arg, cudaStream_t st) {
+    float4* ra = reinterpret_cast<float4*>(ws);
+    float4* rb = ra + n * REC_F4;
+    float4* cb = rb + m * REC_F4;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(cb + m);
+    const bool want_rows = row_max || row_arg, want_cols = col_max || col_arg;
+    unsigned long long* rowkey = want_rows ? keys : nullptr;
+    unsigned long long* colkey = want_cols ? keys + n : nullptr;
+    int rc;
+    prep_kernel<FL><<<(unsigned)((n + m + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb, cb);
+    if ((rc = check_launch("prep_kernel"))) return rc;
+    key_init_kernel<<<(unsigned)((n + m + 255) / 256), 256, 0, st>>>(keys, n + m);
+    if ((rc = check_launch("key_init_kernel"))) return rc;
+    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS;
+    int64_t want_m = (16 * 444 + strips_n - 1) / strips_n;
+    if (want_m < 1) want_m = 1;
+    int64_t cols = (m + want_m - 1) / want_m;
+    cols = (cols + SK_TCOLS - 1) / SK_TCOLS * SK_TCOLS;
+    if (cols < 2 * SK_TCOLS) cols = 2 * SK_TCOLS;
+    if (cols > SK_MAX_COLS) cols = SK_MAX_COLS;
+    const int64_t strips_m = (m + cols - 1) / cols;
+    const int64_t strips = strips_n * strips_m;
+    if (strips > 0x7fffffffLL) {
+        set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
+        return LG_ERR_TOO_LARGE;
+    }
+    auto kern = iou_strip_kernel<FL, true>;
+    if ((rc = set_smem(kern, StripSmem::total))) return rc;
+    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey);
+    if ((rc = check_launch("iou_strip_kernel<reduce>"))) return rc;
+    if (want_rows) key_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowkey, n, row_max, row_arg);
+    if (want_cols) key_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(colkey, m, col_max, col_arg);
+    return check_launch("key_unpack_kernel");
 }
 
 static int iou_entry(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, size_t ws_bytes,
@@ -349,6 +420,42 @@ static int iou_entry(const float* a, int64_t n, const float* b, int64_t m, float
 extern "C" size_t lg_iou_workspace_bytes(int64_t n, int64_t m) {
     if (n < 0 || m < 0) return 0;
     return (size_t)(n + m) * lg::REC_F4 * sizeof(float4) + (size_t)m * sizeof(float4) + 16;
+}
+
+extern "C" size_t lg_iou_reduce_workspace_bytes(int64_t n, int64_t m) {
+    if (n < 0 || m < 0) return 0;
+    return lg_iou_workspace_bytes(n, m) + (size_t)(n + m) * sizeof(unsigned long long);
+}
+
+extern "C" int lg_boxes_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, int kind, float* row_max, int64_t* row_argmax,
+                                   float* col_max, int64_t* col_argmax, void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+    using namespace lg;
+    if (n < 0 || m < 0 || kind < 0 || kind > 2) {
+        set_error("bad argument n=%lld m=%lld kind=%d", (long long)n, (long long)m, kind);
+        return LG_ERR_INVALID_ARG;
+    }
+    if (n >= 0xFFFFFFFFLL || m >= 0xFFFFFFFFLL) {
+        set_error("n=%lld m=%lld: indices are packed in 32 bits", (long long)n, (long long)m);
+        return LG_ERR_TOO_LARGE;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n == 0 || m == 0) {  // empty reductions: (0, 0) for whatever side has entries, as a matrix of no columns has no maximum
+        if (n > 0 && row_max) cudaMemsetAsync(row_max, 0, sizeof(float) * n, st);
+        if (n > 0 && row_argmax) cudaMemsetAsync(row_argmax, 0, sizeof(int64_t) * n, st);
+        if (m > 0 && col_max) cudaMemsetAsync(col_max, 0, sizeof(float) * m, st);
+        if (m > 0 && col_argmax) cudaMemsetAsync(col_argmax, 0, sizeof(int64_t) * m, st);
+        return check_launch("cudaMemsetAsync");
+    }
+    if (!a || !b) {
+        set_error("null pointer (boxes_a=%p boxes_b=%p)", (const void*)a, (const void*)b);
+        return LG_ERR_INVALID_ARG;
+    }
+    if (!ws || ws_bytes < lg_iou_reduce_workspace_bytes(n, m) || (reinterpret_cast<uintptr_t>(ws) & 15)) {
+        set_error("workspace %p of %zu B; need %zu B, 16-byte aligned", ws, ws_bytes, lg_iou_reduce_workspace_bytes(n, m));
+        return LG_ERR_WORKSPACE;
+    }
+    if (flags & LG_FLAG_STRICT_FP32) return run_iou_reduce<0>(a, n, b, m, ws, kind, row_max, row_argmax, col_max, col_argmax, st);
+    return run_iou_reduce<1>(a, n, b, m, ws, kind, row_max, row_argmax, col_max, col_argmax, st);
 }
 
 extern "C" int lg_boxes_overlap_bev(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws,

@@ -90,6 +90,39 @@ def boxes_iou3d_gpu(boxes_a, boxes_b):
     return _iou_call('lg_boxes_iou3d', boxes_a, boxes_b)
 
 
+_REDUCE_KINDS = {'overlap_bev': 0, 'iou_bev': 1, 'iou3d': 2}
+
+
+def boxes_iou_max(boxes_a, boxes_b, kind='iou3d', rows=True, cols=False):
+    """Row / column (max, argmax) of the N x M matrix `kind` without materialising it.
+
+    What the callers of boxes_iou3d_gpu go on to compute -- `torch.max(iou3d, dim=1)` (proposal_target_layer.py:107),
+    argmax over both axes (axis_aligned_target_assigner.py:150-169) -- in the same pass as the IoU; at 200k x 200k the
+    matrix would be 160 GB.  Values are bit-identical to the matrix entry points', argmax is the lowest index of the
+    maximum (torch.max's convention).
+    Returns (row_max (N,), row_argmax (N,)) and / or (col_max (M,), col_argmax (M,)), in that order.
+    """
+    a, b = _cuda_f32(boxes_a, 7), _cuda_f32(boxes_b, 7)
+    n, m = a.shape[0], b.shape[0]
+    dev = a.device
+    rmax = torch.zeros(n, dtype=torch.float32, device=dev) if rows else None
+    rarg = torch.zeros(n, dtype=torch.int64, device=dev) if rows else None
+    cmax = torch.zeros(m, dtype=torch.float32, device=dev) if cols else None
+    carg = torch.zeros(m, dtype=torch.int64, device=dev) if cols else None
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        ws = _workspace(L.lg_iou_reduce_workspace_bytes(n, m), dev)
+        rc = L.lg_boxes_iou_reduce(_lib.ptr(a), n, _lib.ptr(b), m, _REDUCE_KINDS[kind], _lib.ptr(rmax), _lib.ptr(rarg), _lib.ptr(cmax),
+                                   _lib.ptr(carg), _lib.ptr(ws), ws.numel(), _lib.LG_FLAG_NONE, _lib.stream_ptr(dev))
+    _lib.check(rc, 'lg_boxes_iou_reduce')
+    out = ()
+    if rows:
+        out += (rmax, rarg)
+    if cols:
+        out += (cmax, carg)
+    return out
+
+
 def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE):
     """boxes (P, N, 7) cuda f32 contiguous; order (P, N) int64 or None; counts (P,) int32 or None."""
     P, N = boxes.shape[0], boxes.shape[1]

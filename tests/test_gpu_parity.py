@@ -383,3 +383,38 @@ def test_multi_classes_nms_batched_matches_per_class_oracle():
     ps, pl, pb = MU.multi_classes_nms(cu(cls[0]), cu(boxes[0]), cfg, score_thresh=0.2)  # the reference's per-frame signature
     want_idx = np.concatenate([_ref_class_agnostic_nms(cls[0, :, k], boxes[0], cfg, 0.2) for k in range(C)])
     assert np.array_equal(pb.cpu().numpy(), boxes[0][want_idx]) and len(ps) == len(pl) == len(want_idx)
+
+
+# ------------------------------------------------------------------------------------------ fused row / column maxima (8f-4)
+@pytest.mark.parametrize("kind,fn", [("iou3d", "boxes_iou3d_gpu"), ("iou_bev", "boxes_iou_bev"), ("overlap_bev", "boxes_overlap_bev")])
+@pytest.mark.parametrize("n,m,sparse", [(300, 257, False), (1000, 20, True), (2500, 3100, True), (64, 1, False)])
+def test_iou_row_col_max_equals_torch_max_of_the_matrix(kind, fn, n, m, sparse):
+    if sparse:
+        a, b = synth.cfg4(max(n, m), seed=n + m)
+        a, b = a[:n], b[:m]
+    else:
+        a, b = synth.clustered_pairs(n, m, seed=n)
+    ta, tb = cu(a), cu(b)
+    mat = getattr(U, fn)(ta, tb)
+    rmax, rarg, cmax, carg = U.boxes_iou_max(ta, tb, kind=kind, rows=True, cols=True)
+    wr, wc = mat.max(1), mat.max(0)
+    assert torch.equal(rmax, wr.values) and torch.equal(cmax, wc.values)  # bit-identical values
+    # argmax = lowest index attaining the maximum (torch documents the same convention)
+    first_r = (mat == wr.values.unsqueeze(1)).int().argmax(1)
+    first_c = (mat == wc.values.unsqueeze(0)).int().argmax(0)
+    assert torch.equal(rarg, first_r) and torch.equal(carg, first_c)
+    only_rows = U.boxes_iou_max(ta, tb, kind=kind)
+    assert len(only_rows) == 2 and torch.equal(only_rows[0], rmax) and torch.equal(only_rows[1], rarg)
+
+
+def test_iou_row_max_at_a_size_whose_matrix_is_never_built():
+    """60,000 x 60,000 (a 14.4 GB matrix): reduce it, then check sampled rows against the matrix entry point"""
+    a, b = synth.cfg4(60000, seed=3)
+    ta, tb = cu(a), cu(b)
+    rmax, rarg = U.boxes_iou_max(ta, tb, kind="iou3d")
+    rows = torch.arange(0, 60000, 997, device=ta.device)
+    mat = U.boxes_iou3d_gpu(ta[rows], tb)
+    w = mat.max(1)
+    assert torch.equal(rmax[rows], w.values)
+    assert torch.equal(rarg[rows], (mat == w.values.unsqueeze(1)).int().argmax(1))
+    assert float((rmax > 0).float().mean()) > 0.4  # half of the second set are jittered copies of the first
