@@ -94,3 +94,33 @@ def points_in_boxes_sharded(points, boxes, gather=True, group=None, compute=None
     if gather:
         return _gather_rows(idx, B, group)
     return idx, (start, stop)
+
+
+def boxes_iou_max_sharded(boxes_a, boxes_b, kind="iou3d", group=None, compute=None):
+    """Row-sharded (max, argmax) of the N x M IoU matrix over both axes, the matrix itself never materialised
+    (SURVEY.md 8f-4).  Every rank passes the SAME boxes_a / boxes_b.
+
+    Rows split as in boxes_iou_sharded, so a rank's row maxima are final; the column maxima of the row shards are
+    combined with ONE all-reduce(MAX) of M packed 64-bit keys (value bits << 32 | ~global row index: a larger
+    value wins, equal values keep the lower row) -- the only real exchange step on this path.
+    Returns (row_max, row_argmax, (start, stop)) for this rank's rows and (col_max (M,), col_argmax (M,)) global.
+    """
+    if compute is None:
+        from .ops.iou3d_nms import iou3d_nms_utils as U
+
+        def compute(a, b):
+            return U.boxes_iou_max(a, b, kind=kind, rows=True, cols=True)
+    rank, world = _world(group)
+    n = boxes_a.shape[0]
+    start, stop = shard_range(n, rank, world)
+    rmax, rarg, cmax, carg = compute(boxes_a[start:stop], boxes_b)
+    if world > 1:
+        # IoU values are >= 0, so their float bits order like integers and the key fits a signed int64
+        key = (cmax.contiguous().view(torch.int32).to(torch.int64) << 32) | (0xFFFFFFFF - (carg + start))
+        if stop == start:  # a rank without rows contributes the neutral key (value 0.0, highest index)
+            key = torch.zeros_like(key)
+        dist.all_reduce(key, op=dist.ReduceOp.MAX, group=group)
+        cmax = (key >> 32).to(torch.int32).view(torch.float32)
+        carg = 0xFFFFFFFF - (key & 0xFFFFFFFF)
+        carg = torch.where(cmax > 0, carg, torch.zeros_like(carg))  # an all-zero column: index 0, as torch.max of the full matrix
+    return (rmax, rarg, (start, stop)), (cmax, carg)

@@ -38,6 +38,16 @@ def _pib_cpu(points, boxes):
     return torch.from_numpy(O.points_in_boxes_idx(points.numpy(), boxes.numpy(), O.FLAVOR_CUDA))
 
 
+def _max_cpu(a, b):
+    """stand-in for U.boxes_iou_max: (row max, row argmax, col max, col argmax) with lowest-index ties"""
+    mat = _iou_cpu(a, b)
+    if mat.shape[0] == 0:
+        z = torch.zeros(mat.shape[1])
+        return torch.zeros(0), torch.zeros(0, dtype=torch.int64), z, z.long()
+    r, c = mat.max(1), mat.max(0)
+    return r.values, (mat == r.values[:, None]).int().argmax(1), c.values, (mat == c.values[None, :]).int().argmax(0)
+
+
 def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,6 +65,14 @@ def _worker(rank, world, port, ret):
         pts, rois = synth.cfg3(n_frames=3, n_points=200, n_rois=12, seed=4)
         idx = sharded.points_in_boxes_sharded(torch.from_numpy(pts), torch.from_numpy(rois), compute=_pib_cpu)
         ok = ok and torch.equal(idx, _pib_cpu(torch.from_numpy(pts), torch.from_numpy(rois)))
+        # fused maxima: rows local, columns combined with one all-reduce(MAX) of packed keys
+        a2, b2 = synth.clustered_pairs(41, 29, 5)
+        b2[7] = [500, 500, 0, 1, 1, 1, 0]  # a column that overlaps nothing: (0.0, index 0)
+        ta2, tb2 = torch.from_numpy(a2), torch.from_numpy(b2)
+        (rmax, rarg, (s2, e2)), (cmax, carg) = sharded.boxes_iou_max_sharded(ta2, tb2, compute=_max_cpu)
+        wr, wra, wc, wca = _max_cpu(ta2, tb2)
+        ok = ok and torch.equal(rmax, wr[s2:e2]) and torch.equal(rarg, wra[s2:e2]) and torch.equal(cmax, wc) and torch.equal(carg, wca)
+        ok = ok and float(cmax[7]) == 0.0 and int(carg[7]) == 0
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

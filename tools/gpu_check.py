@@ -224,6 +224,22 @@ okp = all(torch.equal(MU.class_agnostic_nms(ts_[f], tb_[f], cfgp, score_thresh=0
 print("post-proc batched == per-frame:", okp)
 res["post_processing_batched_equals_per_frame"] = bool(okp)
 
+# fused row / column maxima against matrix + torch.max
+a, b = synth.cfg1()
+ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+
+
+def unfused(x, y):
+    m_ = U.boxes_iou3d_gpu(x, y)
+    return m_.max(1), m_.max(0)
+
+
+timed("ours iou3d + torch.max both axes, cfg1 321408x20", lambda: unfused(ta, tb))
+timed("ours boxes_iou_max both axes,     cfg1 321408x20", lambda: U.boxes_iou_max(ta, tb, rows=True, cols=True))
+a, b = synth.cfg4(200000)
+ta, tb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+timed("ours boxes_iou_max both axes, 200k x 200k (160 GB matrix never built)", lambda: U.boxes_iou_max(ta, tb, rows=True, cols=True), 4e10)
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "gpu_check.json"), "w") as f:
     json.dump(res, f, indent=1)
