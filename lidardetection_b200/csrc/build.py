@@ -29,7 +29,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    extra = os.environ.get("LG_EXTRA_NVCC_FLAGS", "").split()  # developer experiments only (e.g. -DLG_LZ_G=4)
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
     subprocess.check_call(cmd)
     return OUT
 
