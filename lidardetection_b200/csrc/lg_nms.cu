@@ -15,8 +15,12 @@
 //          the boxes that survive are then OR-reduced into the running `remv` words with independent,
 //          batched loads.  keep[] / num_keep[] are written on the device, mapped through `order`.
 // All P problems of a batch go through three launches in total, with no host synchronisation.
+#include <cooperative_groups.h>
+
 #include "lg_common.cuh"
 #include "lg_strip.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lg {
 
@@ -269,6 +273,7 @@ constexpr int LZ_QCAP = 8192;    // u32 codes: candidate << 16 | box
 constexpr int LZ_RARECAP = LZ_QCAP + 1024;
 constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
 constexpr int LZ_SWEEP = LZ_THREADS;  // columns per sweep of the 16 warps
+constexpr int LZ_MAX_CLUSTER = 8;     // portable cluster size limit
 constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared memory per CTA on sm_100a, minus the static part
 
 struct LazyLayout {
@@ -293,7 +298,7 @@ struct LazyLayout {
     }
 };
 
-template <int FL>
+template <int FL, bool CL>
 __global__ void __launch_bounds__(LZ_THREADS, 1)
     nms_lazy_kernel(const float4* __restrict__ rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
                     const int nmax, const float thresh, int64_t* __restrict__ keep, int32_t* __restrict__ num_keep,
@@ -311,8 +316,15 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s;
     __shared__ unsigned long long st_heavy;
+    __shared__ unsigned xch[LZ_MAX_CLUSTER][G];  // candidate-vs-candidate suppression bits, one row per CTA of the cluster
 
-    const int p = blockIdx.x;
+    // A problem may be spread over a thread-block cluster of C CTAs (C SMs): they keep identical copies of the alive bitmap
+    // and of the pass state, split the COLUMNS of every pass (interleaved 512-column sweeps), and exchange, through
+    // distributed shared memory, (a) the G x G candidate bits before the resolve and (b) the kill words after it.
+    // (CL = false compiles all of that out: one CTA per problem.)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = CL ? (int)cluster.num_blocks() : 1, crank = CL ? (int)cluster.block_rank() : 0;
+    const int p = blockIdx.x / C;
     const int n = problem_count(counts, p, nmax);
     const int W = (n + 31) / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -396,9 +408,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
                 if (done) break;
                 continue;
             }
-            const int sweeps = min(room / LZ_SWEEP, (n - jw + LZ_SWEEP - 1) / LZ_SWEEP);
+            const int sweeps = min(room / LZ_SWEEP, (n - jw + C * LZ_SWEEP - 1) / (C * LZ_SWEEP));
             for (int s = 0; s < sweeps; s++) {
-                const int jb = jw + s * LZ_SWEEP + warp * 32;  // this warp's 32-aligned word of columns
+                const int jb = jw + (s * C + crank) * LZ_SWEEP + warp * 32;  // this warp's 32-aligned word of this CTA's columns
                 if (jb >= n) break;
                 const unsigned word = alive[jb >> 5];
                 if (word == 0u) continue;  // warp-uniform
@@ -415,24 +427,41 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
                 // code = candidate << 16 | box: push_survivors' (row << SHIFT | col) with row = g, col = j
                 push_survivors<16, G>(mk, lane, 0, 1, j, &qcount, queue);
             }
-            jw += sweeps * LZ_SWEEP;
+            jw += sweeps * C * LZ_SWEEP;
         }
         __syncthreads();
         drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
         __syncthreads();
         // ---- resolve the speculation in score order (warp 0: lane h holds candidate h's row; at most G ballots)
+        if (CL && C > 1) {  // a candidate's column lives in ONE CTA of the cluster: share the candidate-vs-candidate bits
+            if (warp == 0) {
+                for (int g = 0; g < ng; g++) {
+                    const int j = group[g];
+                    const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
+                    const unsigned by = __ballot_sync(0xffffffffu, hit);
+                    if (lane < C) *cluster.map_shared_rank(&xch[crank][g], lane) = by;
+                }
+            }
+            cluster.sync();
+        }
         if (warp == 0) {
             const int jl = lane < ng ? group[lane] : 0;
             const int64_t ol = (lane < ng && order) ? order[base + jl] : (int64_t)jl;  // loads issued before the serial part
             unsigned km = 0u;
             for (int g = 0; g < ng; g++) {
-                const int j = group[g];
-                const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
-                const unsigned by = __ballot_sync(0xffffffffu, hit);  // earlier candidates whose row suppresses g
+                unsigned by;  // earlier candidates whose row suppresses g
+                if (CL && C > 1) {
+                    by = 0u;
+                    for (int r = 0; r < C; r++) by |= xch[r][g];
+                } else {
+                    const int j = group[g];
+                    const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
+                    by = __ballot_sync(0xffffffffu, hit);
+                }
                 if ((by & km) == 0u) km |= 1u << g;
             }
             const int nk = nk_s;
-            if ((km >> lane) & 1u) keep[base + nk + __popc(km & ((1u << lane) - 1u))] = ol;
+            if (crank == 0 && ((km >> lane) & 1u)) keep[base + nk + __popc(km & ((1u << lane) - 1u))] = ol;
             if (lane == 0) {
                 keptmask_s = (int)km;
                 nk_s = nk + __popc(km);
@@ -449,16 +478,25 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
                     sup[g * W + w] = 0u;
                 }
             }
-            alive[w] &= ~kill;
+            if (CL && C > 1) {
+                if (kill) {  // peers update the same words: atomics everywhere
+                    for (int r = 0; r < C; r++) atomicAnd(cluster.map_shared_rank(&alive[w], r), ~kill);
+                }
+            } else {
+                alive[w] &= ~kill;
+            }
         }
         __syncthreads();
         if (tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));  // candidates are decided either way
         cursor = group[ng - 1] + 1;
+        if (CL && C > 1) cluster.sync();  // every CTA's kill words have landed everywhere before the next candidates are chosen
     }
     // all threads left the loop together
     const int nk = nk_s;
-    if (tid == 0) num_keep[p] = nk;
-    for (int i = nk + tid; i < nmax; i += NT) keep[base + i] = -1;
+    if (crank == 0) {
+        if (tid == 0) num_keep[p] = nk;
+        for (int i = nk + tid; i < nmax; i += NT) keep[base + i] = -1;
+    }
     if (stats) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -536,12 +574,38 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
                 return (int)e;
             }
             const LazyLayout L(nmax);
-            if (strict) {
-                if ((rc = set_smem(nms_lazy_kernel<0>, L.total))) return rc;
-                nms_lazy_kernel<0><<<P, LZ_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
-            } else {
-                if ((rc = set_smem(nms_lazy_kernel<1>, L.total))) return rc;
-                nms_lazy_kernel<1><<<P, LZ_THREADS, L.total, st>>>(rec, order, counts, nmax, thresh, keep, num_keep, stats);
+            // cluster size: as many SMs per problem as leaves every CTA of the batch resident at once (the kernel is bound by
+            // one SM's instruction throughput per problem), and never fewer than 512 columns per CTA
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int csize = 1;
+            while (csize < LZ_MAX_CLUSTER && (int64_t)P * csize * 2 <= sms && nmax >= csize * 2 * LZ_SWEEP) csize *= 2;
+            if (flags & LG_FLAG_NMS_NO_CLUSTER) csize = 1;
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3((unsigned)(P * csize));
+            lc.blockDim = dim3(LZ_THREADS);
+            lc.dynamicSmemBytes = L.total;
+            lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)csize;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = csize > 1 ? 1 : 0;  // a plain launch when every problem gets one CTA
+            cudaError_t le;
+            auto launch = [&](auto kern) -> cudaError_t {
+                if ((rc = set_smem(kern, L.total))) return cudaSuccess;
+                return cudaLaunchKernelEx(&lc, kern, (const float4*)rec, order, counts, nmax, thresh, keep, num_keep, stats);
+            };
+            rc = 0;
+            if (strict) le = csize > 1 ? launch(nms_lazy_kernel<0, true>) : launch(nms_lazy_kernel<0, false>);
+            else le = csize > 1 ? launch(nms_lazy_kernel<1, true>) : launch(nms_lazy_kernel<1, false>);
+            if (rc) return rc;
+            if (le != cudaSuccess) {
+                set_error("nms_lazy_kernel (cluster of %d): %s", csize, cudaGetErrorString(le));
+                return (int)le;
             }
             return check_launch("nms_lazy_kernel");
         }

@@ -163,6 +163,9 @@ def test_nms_lazy_equals_full_mask_equals_oracle(n, thresh, seed):
     k_lazy, n_lazy = U.nms_gpu_batched(tb, ts, thresh)
     k_full, n_full = U.nms_gpu_batched(tb, ts, thresh, full_mask=True)
     assert torch.equal(n_lazy, n_full) and torch.equal(k_lazy, k_full)
+    # small batches spread every problem over a thread-block cluster (2-8 SMs, DSMEM exchange); one CTA per problem must agree
+    k_one, n_one = U._nms_batched('lg_nms_rotated_batched', tb, ts, thresh, None, flags=_lib.LG_FLAG_NMS_NO_CLUSTER)
+    assert torch.equal(n_lazy, n_one) and torch.equal(k_lazy, k_one)
     for f in range(3):
         order = ts[f].sort(0, descending=True)[1].cpu().numpy()
         want = O.nms(boxes[f], scores[f], thresh, flavor=O.FLAVOR_CUDA, order=order)
