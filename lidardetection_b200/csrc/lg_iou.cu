@@ -209,7 +209,7 @@ struct FlatSmem {
 
 template <int FL>
 __global__ void __launch_bounds__(ST_THREADS, 3)
-    iou_flat_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b, const int m,
+    iou_flat_kernel(const float* __restrict__ box_a, const int64_t n, const float* __restrict__ box_b, const int m,
                     float* __restrict__ out, const int64_t ld, const int mode, const unsigned inv_m /* ceil(2^20 / m) */) {
     constexpr int NT = ST_THREADS;
     extern __shared__ float4 smem4[];
@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * FLAT_ROWS;
     const int na = (int)min((int64_t)FLAT_ROWS, n - row0);
-    for (int e = tid; e < na * REC_F4; e += NT) sA[e] = __ldg(rec_a + row0 * REC_F4 + e);
-    for (int e = tid; e < m * REC_F4; e += NT) sB[e] = __ldg(rec_b + e);
+    // the records are built in place (no prep kernel, no 112-byte round trip through HBM: for a 20-column matrix that
+    // round trip would be three times the matrix itself); the M <= 64 column records are rebuilt by every CTA
+    if (tid < na) make_record<FL>(box_a + (row0 + tid) * 7, sA + tid * REC_F4);
+    if (tid < m) make_record<FL>(box_b + (int64_t)tid * 7, sB + tid * REC_F4);
     if (tid == 0) {
         qcount = 0;
         rcount = 0;
@@ -315,13 +317,7 @@ static int check_args(const float* a, int64_t n, const float* b, int64_t m, floa
 template <int FL>
 static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, int mode,
                    cudaStream_t st) {
-    float4* ra = reinterpret_cast<float4*>(ws);
-    float4* rb = ra + n * REC_F4;
-    float4* cb = rb + m * REC_F4;
-    const int64_t total = n + m;
-    prep_kernel<FL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb, cb);
-    int rc = check_launch("prep_kernel");
-    if (rc) return rc;
+    int rc;
     if (m <= FLAT_COLS) {
         const int64_t ctas = (n + FLAT_ROWS - 1) / FLAT_ROWS;
         if (ctas > 0x7fffffffLL) {
@@ -331,9 +327,15 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         auto kern = iou_flat_kernel<FL>;
         if ((rc = set_smem(kern, FlatSmem::total))) return rc;
         const unsigned inv_m = (unsigned)(((1u << 20) + (unsigned)m - 1u) / (unsigned)m);
-        kern<<<(unsigned)ctas, ST_THREADS, FlatSmem::total, st>>>(ra, n, rb, (int)m, out, ld, mode, inv_m);
+        kern<<<(unsigned)ctas, ST_THREADS, FlatSmem::total, st>>>(a, n, b, (int)m, out, ld, mode, inv_m);
         return check_launch("iou_flat_kernel");
     }
+    float4* ra = reinterpret_cast<float4*>(ws);
+    float4* rb = ra + n * REC_F4;
+    float4* cb = rb + m * REC_F4;
+    const int64_t total = n + m;
+    prep_kernel<FL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb, cb);
+    if ((rc = check_launch("prep_kernel"))) return rc;
     // columns per CTA: as long a run as still leaves >= ~16 CTAs per SM-slot for load balance (148 SMs x 3 CTAs)
     const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS;
     int64_t want_m = (16 * 444 + strips_n - 1) / strips_n;  // column splits wanted
