@@ -335,6 +335,69 @@ def test_live_against_reference_cuda_kernels():
     assert torch.equal(PU.points_in_boxes_gpu(cu(pts), cu(rois)), want)
 
 
+def _adversarial_boxes(r, n):
+    """extreme aspect ratios, tiny and huge boxes, far from the origin, headings at exact multiples of pi/2, exact duplicates,
+    exactly touching and nested boxes, near-duplicates a few ulp / mm apart"""
+    b = synth.gt_boxes(n, int(r.integers(1 << 30)), x_range=(-5, 5), y_range=(-5, 5))
+    k = n // 10
+    b[0 * k:1 * k, 3] = r.uniform(8, 30, k); b[0 * k:1 * k, 4] = r.uniform(0.05, 0.3, k)          # needles
+    b[1 * k:2 * k, 3:5] = r.uniform(0.02, 0.08, (k, 2))                                            # tiny (margin dominates)
+    b[2 * k:3 * k, 3:5] = r.uniform(40, 120, (k, 2))                                               # huge
+    b[3 * k:4 * k, 0:2] += np.array([1000.0, -2000.0], np.float32)                                # far away (coarse ulp)
+    b[4 * k:5 * k, 6] = r.integers(-4, 5, k) * np.float32(np.pi / 2)                               # axis aligned, on a 0.5 m lattice
+    b[4 * k:5 * k, 0:2] = np.round(b[4 * k:5 * k, 0:2] * 2) / 2
+    b[4 * k:5 * k, 3:5] = np.round(b[4 * k:5 * k, 3:5] * 2 + 1) / 2
+    b[5 * k:6 * k] = b[4 * k:5 * k]                                                                # exact duplicates of those
+    b[6 * k:7 * k] = b[0:k]
+    b[6 * k:7 * k, 0:2] += r.normal(0, 1e-3, (k, 2)).astype(np.float32)                           # near-duplicates (mm)
+    b[7 * k:8 * k] = b[k:2 * k]
+    b[7 * k:8 * k, 6] += r.normal(0, 1e-4, k).astype(np.float32)                                  # near-duplicates (angle)
+    b[8 * k:9 * k, 6] = 0.0
+    b[8 * k:9 * k, 0] = b[8 * k, 0] + np.arange(k) * b[8 * k, 3]                                   # a row of boxes touching edge to edge
+    b[8 * k:9 * k, 1] = b[8 * k, 1]
+    b[8 * k:9 * k, 3:5] = b[8 * k, 3:5]
+    return b.astype(np.float32)
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref (compiled reference) did not travel with this snapshot")
+def test_adversarial_boxes_live_against_reference_cuda_kernels():
+    """the reference CUDA kernels, run live on this GPU, are the authority: every entry bit-identical or a vertex-order tie"""
+    ref, roi = R.iou3d_nms_cuda(), R.roiaware_pool3d_cuda()
+    r = np.random.default_rng(2024)
+    a, b = _adversarial_boxes(r, 600), _adversarial_boxes(r, 500)
+    b[:200] = a[:200]  # shared boxes: identical, touching and nested pairs across the two sets
+    ta, tb = cu(a), cu(b)
+    want = torch.zeros((600, 500), device=dev())
+    ref.boxes_iou_bev_gpu(ta, tb, want)
+    got = U.boxes_iou_bev(ta, tb).cpu().numpy()
+    want = want.cpu().numpy()
+    assert np.array_equal(got == 0, want == 0), "zero pattern differs"
+    diff = bits(got) != bits(want)
+    # the only licensed difference: polygons with two vertices at (numerically) the same polar angle, whose order hangs on the
+    # last bit of atan2f -- libdevice's in the reference kernel, and also in ours (overlap_area_slow), so none is expected
+    assert int(diff.sum()) <= 3 and np.abs(got - want).max() <= 2e-3, (int(diff.sum()), float(np.abs(got - want).max()))
+    wov = torch.zeros((600, 500), device=dev())
+    ref.boxes_overlap_bev_gpu(ta, tb, wov)
+    gov = U.boxes_overlap_bev(ta, tb)
+    assert int((gov != wov).sum()) <= 3
+    # NMS on the adversarial set, rotated and axis aligned
+    sc = cu(r.permutation(np.linspace(0.1, 1.0, 600)).astype(np.float32))
+    order = sc.sort(0, descending=True)[1]
+    bs = ta[order].contiguous()
+    for thr, normal in ((0.05, False), (0.5, False), (0.9, False), (0.3, True)):
+        keep = torch.LongTensor(600)
+        nk = (ref.nms_normal_gpu if normal else ref.nms_gpu)(bs, keep, thr)
+        wantk = order[keep[:nk].to(dev())]
+        gotk = (U.nms_normal_gpu if normal else U.nms_gpu)(ta, sc, thr)[0]
+        assert torch.equal(gotk, wantk), (thr, normal, len(gotk), nk)
+    # points on and around the faces of adversarial boxes
+    boxes = a[:120][None]
+    pts = np.concatenate([r.uniform(-8, 8, (20000, 3)), boxes[0, r.integers(0, 120, 5000), 0:3] + r.normal(0, 0.5, (5000, 3))]).astype(np.float32)[None]
+    wantp = torch.full((1, pts.shape[1]), -1, dtype=torch.int32, device=dev())
+    roi.points_in_boxes_gpu(cu(boxes), cu(pts), wantp)
+    assert torch.equal(PU.points_in_boxes_gpu(cu(pts), cu(boxes)), wantp)
+
+
 # ------------------------------------------------------------------------------------------ post-processing front end (8f-1)
 def _ref_class_agnostic_nms(box_scores, box_preds, cfg, score_thresh):
     """the reference's model_nms_utils.class_agnostic_nms, restated around the ORACLE's NMS (numpy)"""
