@@ -286,7 +286,8 @@ class IouWorkload(Workload):
         self.pairs = a.shape[0] * b.shape[0]
         self.units = self.pairs / 1e9
         self.out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device="cuda")
-        self.launches_per_step = 1 if b.shape[0] <= 64 else 2  # iou_flat_kernel alone (M <= 64), else prep_kernel + iou_strip_kernel
+        # iou_flat_kernel alone (M <= 64); else prep_kernel + density_probe_kernel + the two iou_strip_kernel variants (one of them exits at once)
+        self.launches_per_step = 1 if b.shape[0] <= 64 else 4
         self.h2d = (a.size + b.size) * 4
         self.e2e_d2h_full = self.pairs * 4 <= (1 << 30)
         self.d2h = self.pairs * 4 if self.e2e_d2h_full else a.shape[0] * 8

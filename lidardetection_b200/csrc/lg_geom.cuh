@@ -397,6 +397,14 @@ __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, cons
     return res;
 }
 
+// the same as an out-of-line call: kernels whose main loop is something else (the N x M sweep: culling and storing zeros)
+// keep that loop's state in registers and pay the spills only around the call
+template <int FL>
+__device__ __noinline__ float overlap_area_call(const float4* __restrict__ A, const float4* __restrict__ B, float2* __restrict__ slab,
+                                                const int sstride, const unsigned wmask) {
+    return overlap_area<FL>(A, B, slab, sstride, wmask);
+}
+
 // ---- the pair, 9..16 vertices (near-coincident boxes; ~0.3 % of overlapping pairs) -----------------
 // Same construction as the fast path with 16 vertex slots and a 16-input network; returns -1 on an angular
 // near-tie (the caller then runs the literal path).  Called for the pairs the fast path deferred.

@@ -71,13 +71,18 @@ __device__ __forceinline__ unsigned long long max_key(float v, unsigned idx) {
 // REDUCE = false: write the N x M matrix.  REDUCE = true: write nothing of it; keep per-row / per-column (max, argmax)
 // keys instead (what the target assigners and the evaluation actually consume) -- the 200k x 200k matrix
 // (160 GB) is then never materialised.
-template <int FL, bool REDUCE>
-__global__ void __launch_bounds__(ST_THREADS, REDUCE ? 2 : 3)
+// DENSE = true : polygon path inlined, 80 registers, 3 CTAs/SM -- best when a large share of the pairs overlap;
+// DENSE = false: polygon path called out of line, 128 registers, 2 CTAs/SM, the sweep (cull + zero stores) stays in
+//                registers -- best for the usual, sparse matrix.  Both are launched; `dense_flag` (written by
+//                density_probe_kernel from a sample of the pairs, no host round trip) tells each whether it is its turn.
+template <int FL, bool REDUCE, bool DENSE>
+__global__ void __launch_bounds__(ST_THREADS, DENSE ? 3 : 2)
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
                      const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
                      const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,
-                     unsigned long long* __restrict__ colkey) {
+                     unsigned long long* __restrict__ colkey, const int* __restrict__ dense_flag) {
     constexpr int NT = ST_THREADS;
+    if (dense_flag && (*dense_flag != 0) != DENSE) return;
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
     float4* sDup = sA + SK_ROWS * REC_F4;  // per row: (cx, cx, cy, cy), (rad, rad, -, -)
@@ -140,7 +145,17 @@ __global__ void __launch_bounds__(ST_THREADS, REDUCE ? 2 : 3)
             const int rbase = rhalf + rsub;
             float* outp = outb + (int64_t)rbase * ld + c;
             const int64_t ostep = 4 * ld;
-            unsigned mk0[8], mk1[8];
+            // survivors go straight onto the warp's list (a warp-uniform, rarely taken branch when the matrix is sparse)
+            const unsigned lt = (1u << lane) - 1u;
+            auto push2 = [&](const int row, const bool s0, const bool s1) {
+                const unsigned m0 = __ballot_sync(0xffffffffu, s0), m1 = __ballot_sync(0xffffffffu, s1);
+                if (m0 | m1) {
+                    if (s0) q.list[q.count + __popc(m0 & lt)] = (uint32_t)((row << SK_SHIFT) | c);
+                    q.count += __popc(m0);
+                    if (s1) q.list[q.count + __popc(m1 & lt)] = (uint32_t)((row << SK_SHIFT) | (c + 1));
+                    q.count += __popc(m1);
+                }
+            };
             if (vec2_ok && rhalf + SK_TROWS <= na && (t >> 1) * SK_TCOLS + SK_TCOLS <= nb) {  // full tile: packed cull, no bounds tests
                 const f32x2 bx = pack2(b0.x, b1.x), by = pack2(b0.y, b1.y), br = pack2(b0.z, b1.z);
 #pragma unroll
@@ -162,8 +177,7 @@ __global__ void __launch_bounds__(ST_THREADS, REDUCE ? 2 : 3)
                         }
                         outp += ostep;
                     }
-                    mk0[k] = __ballot_sync(0xffffffffu, s0);
-                    mk1[k] = __ballot_sync(0xffffffffu, s1);
+                    push2(rbase + 4 * k, s0, s1);
                 }
             } else {
                 const bool v0 = c < nb, v1 = c + 1 < nb;
@@ -183,17 +197,32 @@ __global__ void __launch_bounds__(ST_THREADS, REDUCE ? 2 : 3)
                         }
                     }
                     outp += ostep;
-                    mk0[k] = __ballot_sync(0xffffffffu, s0);
-                    mk1[k] = __ballot_sync(0xffffffffu, s1);
+                    push2(r, s0, s1);
                 }
             }
-            warp_push<SK_SHIFT, 8>(q, mk0, lane, rbase, 4, c);
-            warp_push<SK_SHIFT, 8>(q, mk1, lane, rbase, 4, c + 1);
+            __syncwarp();
         }
-        while (q.count >= (last ? 1 : 32)) warp_round<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
+        while (q.count >= (last ? 1 : 32)) warp_round<FL, SK_SHIFT, DENSE>(q, sA, gB, slab_warp, NT, lane, emit);
         if (last) break;
     }
     if (q.rcount > 0) warp_drain_rare<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
+}
+
+// Survivor density of the exact-zero cull, estimated from 8192 pseudo-random pairs: flag = 1 when more than ~6 % survive.
+__global__ void __launch_bounds__(256) density_probe_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ cull_b,
+                                                             const int64_t m, int* __restrict__ flag) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int s = threadIdx.x; s < 8192; s += 256) {
+        const unsigned long long h = (unsigned long long)(s + 1) * 0x9E3779B97F4A7C15ull;
+        const int64_t i = (int64_t)((h >> 33) % (unsigned long long)n), j = (int64_t)(((h * 0xD1B54A32D192ED03ull) >> 33) % (unsigned long long)m);
+        mine += cull_survives(__ldg(rec_a + i * REC_F4 + REC_CULL), __ldg(cull_b + j)) ? 1 : 0;
+    }
+    atomicAdd(&cnt, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = cnt > 512 ? 1 : 0;
 }
 
 // ---- narrow matrices (M <= 64, e.g. anchors x GT): a CTA owns 256 rows x all M columns, flat pair index ----
@@ -350,9 +379,15 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
         return LG_ERR_TOO_LARGE;
     }
-    auto kern = iou_strip_kernel<FL, false>;
-    if ((rc = set_smem(kern, StripSmem::total))) return rc;
-    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr);
+    int* flag = reinterpret_cast<int*>(cb + m);
+    density_probe_kernel<<<1, 256, 0, st>>>(ra, n, cb, m, flag);
+    if ((rc = check_launch("density_probe_kernel"))) return rc;
+    auto ks = iou_strip_kernel<FL, false, false>;
+    auto kd = iou_strip_kernel<FL, false, true>;
+    if ((rc = set_smem(ks, StripSmem::total))) return rc;
+    if ((rc = set_smem(kd, StripSmem::total))) return rc;
+    ks<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag);
+    kd<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag);
     return check_launch("iou_strip_kernel");
 }
 
@@ -377,7 +412,7 @@ static int run_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, 
     float4* ra = reinterpret_cast<float4*>(ws);
     float4* rb = ra + n * REC_F4;
     float4* cb = rb + m * REC_F4;
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(cb + m);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(cb + m + 1);  // (the 16 bytes after cb are the matrix path's density flag)
     const bool want_rows = row_max || row_arg, want_cols = col_max || col_arg;
     unsigned long long* rowkey = want_rows ? keys : nullptr;
     unsigned long long* colkey = want_cols ? keys + n : nullptr;
@@ -399,9 +434,9 @@ static int run_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, 
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
         return LG_ERR_TOO_LARGE;
     }
-    auto kern = iou_strip_kernel<FL, true>;
+    auto kern = iou_strip_kernel<FL, true, false>;
     if ((rc = set_smem(kern, StripSmem::total))) return rc;
-    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey);
+    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey, nullptr);
     if ((rc = check_launch("iou_strip_kernel<reduce>"))) return rc;
     if (want_rows) key_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowkey, n, row_max, row_arg);
     if (want_cols) key_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(colkey, m, col_max, col_arg);
@@ -421,7 +456,7 @@ static int iou_entry(const float* a, int64_t n, const float* b, int64_t m, float
 
 extern "C" size_t lg_iou_workspace_bytes(int64_t n, int64_t m) {
     if (n < 0 || m < 0) return 0;
-    return (size_t)(n + m) * lg::REC_F4 * sizeof(float4) + (size_t)m * sizeof(float4) + 16;
+    return (size_t)(n + m) * lg::REC_F4 * sizeof(float4) + (size_t)m * sizeof(float4) + 16 /* density flag */ + 16;
 }
 
 extern "C" size_t lg_iou_reduce_workspace_bytes(int64_t n, int64_t m) {

@@ -181,7 +181,9 @@ __device__ __forceinline__ void warp_drain_rare(WarpQueue& q, const float4* __re
 }
 
 // run the polygon path on the top min(count, 32) entries of the warp's list
-template <int FL, int SHIFT, typename Emit>
+// INLINE_PATH: expand the polygon path in place (best when most pairs reach it) or call it out of line (keeps the
+// caller's sweep loop in registers: best when most pairs are culled)
+template <int FL, int SHIFT, bool INLINE_PATH, typename Emit>
 __device__ __forceinline__ void warp_round(WarpQueue& q, const float4* __restrict__ sA, const float4* __restrict__ sB,
                                            float2* __restrict__ slab_warp, const int sstride, const int lane, Emit emit) {
     const int n = min(q.count, 32);
@@ -195,7 +197,7 @@ __device__ __forceinline__ void warp_round(WarpQueue& q, const float4* __restric
         const int r = e >> SHIFT, c = e & ((1u << SHIFT) - 1u);
         const float4* A = sA + (size_t)r * REC_F4;
         const float4* B = sB + (size_t)c * REC_F4;
-        const float ov = overlap_area<FL>(A, B, slab_warp + lane, sstride, wm);
+        const float ov = INLINE_PATH ? overlap_area<FL>(A, B, slab_warp + lane, sstride, wm) : overlap_area_call<FL>(A, B, slab_warp + lane, sstride, wm);
         if (ov < 0.f) defer = true;
         else emit(r, c, ov, A, B);
     }
