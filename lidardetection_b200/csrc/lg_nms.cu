@@ -279,13 +279,13 @@ constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared me
 struct LazyLayout {
     int words;         // alive words
     size_t off_cull, off_slab, off_queue, off_rare, off_alive, off_sup, total;
-    __host__ __device__ explicit LazyLayout(int nmax) {
+    __host__ __device__ explicit LazyLayout(int nmax, int nt = LZ_THREADS) {
         words = (nmax + 31) / 32;
         size_t o = (size_t)LZ_G * REC_F4 * sizeof(float4);  // candidate records first
         off_cull = o;
         o += (size_t)(nmax < LZ_CACHE ? nmax : LZ_CACHE) * sizeof(float4);
         off_slab = o;
-        o += (size_t)8 * LZ_THREADS * sizeof(float2);
+        o += (size_t)8 * nt * sizeof(float2);
         off_queue = o;
         o += (size_t)LZ_QCAP * sizeof(uint32_t);
         off_rare = o;
@@ -298,14 +298,16 @@ struct LazyLayout {
     }
 };
 
-template <int FL, bool CL>
-__global__ void __launch_bounds__(LZ_THREADS, 1)
+// NT = 512 threads for one latency-bound problem per SM; NT = 256 (two CTAs per SM) when the batch has several small
+// problems per SM, so that one problem's serial phases (candidate search, resolve, barriers) overlap another's rounds
+template <int FL, bool CL, int NT>
+__global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     nms_lazy_kernel(const float4* __restrict__ rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
                     const int nmax, const float thresh, int64_t* __restrict__ keep, int32_t* __restrict__ num_keep,
                     unsigned long long* __restrict__ stats) {
-    constexpr int NT = LZ_THREADS, G = LZ_G;
+    constexpr int G = LZ_G, SWEEP = NT;  // columns per sweep of the CTA's warps
     extern __shared__ float4 smem4[];
-    const LazyLayout L(nmax);
+    const LazyLayout L(nmax, NT);
     char* sm = reinterpret_cast<char*>(smem4);
     float4* sA = smem4;
     float4* scull = reinterpret_cast<float4*>(sm + L.off_cull);
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
             __syncthreads();
             const int room = (LZ_QCAP - qn) / G;  // columns that cannot overflow the queue
             const bool done = jw >= n;
-            if (done || room < LZ_SWEEP) {  // single drain call site: mid-row when the queue is full, and at the end of the rows
+            if (done || room < SWEEP) {  // single drain call site: mid-row when the queue is full, and at the end of the rows
                 if (rn + qn > LZ_RARECAP) {
                     drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
                     __syncthreads();
@@ -408,9 +410,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
                 if (done) break;
                 continue;
             }
-            const int sweeps = min(room / LZ_SWEEP, (n - jw + C * LZ_SWEEP - 1) / (C * LZ_SWEEP));
+            const int sweeps = min(room / SWEEP, (n - jw + C * SWEEP - 1) / (C * SWEEP));
             for (int s = 0; s < sweeps; s++) {
-                const int jb = jw + (s * C + crank) * LZ_SWEEP + warp * 32;  // this warp's 32-aligned word of this CTA's columns
+                const int jb = jw + (s * C + crank) * SWEEP + warp * 32;  // this warp's 32-aligned word of this CTA's columns
                 if (jb >= n) break;
                 const unsigned word = alive[jb >> 5];
                 if (word == 0u) continue;  // warp-uniform
@@ -427,7 +429,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
                 // code = candidate << 16 | box: push_survivors' (row << SHIFT | col) with row = g, col = j
                 push_survivors<16, G>(mk, lane, 0, 1, j, &qcount, queue);
             }
-            jw += sweeps * C * LZ_SWEEP;
+            jw += sweeps * C * SWEEP;
         }
         __syncthreads();
         drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
@@ -573,18 +575,21 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
                 set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
                 return (int)e;
             }
-            const LazyLayout L(nmax);
             // cluster size: as many SMs per problem as leaves every CTA of the batch resident at once (the kernel is bound by
-            // one SM's instruction throughput per problem), and never fewer than 512 columns per CTA
+            // one SM's instruction throughput per problem), and never fewer than 1024 columns per CTA
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             int csize = 1;
             while (csize < LZ_MAX_CLUSTER && (int64_t)P * csize * 2 <= sms && nmax >= csize * 2 * LZ_SWEEP) csize *= 2;
             if (flags & LG_FLAG_NMS_NO_CLUSTER) csize = 1;
+            // many small problems: 256-thread CTAs, two per SM
+            const bool small = csize == 1 && nmax <= 1536 && (int64_t)P >= 2 * sms;
+            const int nt = small ? 256 : LZ_THREADS;
+            const LazyLayout L(nmax, nt);
             cudaLaunchConfig_t lc = {};
             lc.gridDim = dim3((unsigned)(P * csize));
-            lc.blockDim = dim3(LZ_THREADS);
+            lc.blockDim = dim3((unsigned)nt);
             lc.dynamicSmemBytes = L.total;
             lc.stream = st;
             cudaLaunchAttribute at[1];
@@ -600,8 +605,8 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
                 return cudaLaunchKernelEx(&lc, kern, (const float4*)rec, order, counts, nmax, thresh, keep, num_keep, stats);
             };
             rc = 0;
-            if (strict) le = csize > 1 ? launch(nms_lazy_kernel<0, true>) : launch(nms_lazy_kernel<0, false>);
-            else le = csize > 1 ? launch(nms_lazy_kernel<1, true>) : launch(nms_lazy_kernel<1, false>);
+            if (strict) le = csize > 1 ? launch(nms_lazy_kernel<0, true, 512>) : (small ? launch(nms_lazy_kernel<0, false, 256>) : launch(nms_lazy_kernel<0, false, 512>));
+            else le = csize > 1 ? launch(nms_lazy_kernel<1, true, 512>) : (small ? launch(nms_lazy_kernel<1, false, 256>) : launch(nms_lazy_kernel<1, false, 512>));
             if (rc) return rc;
             if (le != cudaSuccess) {
                 set_error("nms_lazy_kernel (cluster of %d): %s", csize, cudaGetErrorString(le));

@@ -8,10 +8,11 @@
 // evaluations with per-pair trigonometry; here a CTA
 //   1. builds the T 32-byte box records (trigonometry hoisted) and their conservative BEV footprints,
 //   2. lays a uniform grid over the frame's boxes in shared memory -- per cell one 32-bit list of up to four
-//      candidate box indices in ascending order (48 KB: 12288 cells) -- all threads sharing the flattened
+//      candidate box indices in ascending order (16 KB: 4096 cells) -- all threads sharing the flattened
 //      (box, cell) pairs: separating-axis test, sorted insert by compare-and-swap,
 //   3. streams its points through shared memory with 1-D bulk async copies (TMA, cp.async.bulk + mbarrier,
-//      three 12 KB stages in flight per CTA); points whose cell lists a candidate go to per-warp work lists
+//      two 12 KB stages per CTA, three CTAs per SM -- the sizes were swept on the B200: occupancy matters more here than
+//      grid resolution or pipeline depth); points whose cell lists a candidate go to per-warp work lists
 //      and are tested on full warps against the (<= 4) boxes of their cell in ascending index order.
 // HBM traffic is the algorithmic 16 B per point (+ 28 T per CTA); the kernel is HBM-bound when the batch is
 // large enough to fill the machine.  Frames whose boxes have a non-finite footprint fall back to
@@ -22,10 +23,22 @@
 namespace lg {
 
 constexpr int PIB_THREADS = 256;
-constexpr int PIB_TILE = 1024;                 // points per stage
-constexpr int PIB_STAGES = 3;
+#ifndef LG_PIB_TILE
+#define LG_PIB_TILE 1024
+#endif
+constexpr int PIB_TILE = LG_PIB_TILE;          // points per stage
+#ifndef LG_PIB_STAGES
+#define LG_PIB_STAGES 2
+#endif
+#ifndef LG_PIB_CELLS
+#define LG_PIB_CELLS 4096
+#endif
+#ifndef LG_PIB_MINB
+#define LG_PIB_MINB 3
+#endif
+constexpr int PIB_STAGES = LG_PIB_STAGES;
 constexpr int PIB_TILE_BYTES = PIB_TILE * 12;  // 12 KB
-constexpr int PIB_CELLS = 12288;               // 48 KB of 32-bit candidate lists (lg_pib.cuh)
+constexpr int PIB_CELLS = LG_PIB_CELLS;         // 16 KB of 32-bit candidate lists (lg_pib.cuh)
 constexpr float PIB_MIN_CELL = 0.6f;            // cells no smaller than 0.6 x the mean footprint half-extent
 constexpr int PIB_WARPS = PIB_THREADS / 32;
 constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
@@ -69,7 +82,7 @@ struct PibSmem {
 };
 
 template <int FL>
-__global__ void __launch_bounds__(PIB_THREADS, 2)
+__global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
     pib_grid_kernel(const float* __restrict__ boxes, const float* __restrict__ pts, int32_t* __restrict__ out, const int T,
                     const int64_t M, const int64_t pts_per_cta) {
     constexpr int NT = PIB_THREADS;

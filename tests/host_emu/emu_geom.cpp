@@ -88,7 +88,7 @@ extern "C" int emu_debug_pair(const float* a, const float* b, float* verts /*[16
 
 #include <vector>
 
-// boxes (T,7), pts (M,3) -> out (M); ncells = capacity of the cell array (kernel: 12288).
+// boxes (T,7), pts (M,3) -> out (M); ncells = capacity of the cell array (kernel: 4096).
 // returns the number of (point, box) predicate evaluations performed (for the pruning statistics)
 extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float* pts, long long M, int32_t* out, int ncells,
                                          int* used_grid) {

@@ -96,7 +96,7 @@ def test_known_answers_through_the_device_code(emu):
 
 
 # ------------------------------------------------------------------------------------------ points
-def pib(L, boxes, pts, grid_words=12288):
+def pib(L, boxes, pts, grid_words=4096):
     boxes, pts = np.ascontiguousarray(boxes, np.float32), np.ascontiguousarray(pts, np.float32)
     out, used = np.empty(len(pts), np.int32), C.c_int(0)
     tests = L.emu_points_in_boxes(boxes.ctypes.data_as(fp), len(boxes), pts.ctypes.data_as(fp), len(pts), out.ctypes.data_as(ip),
