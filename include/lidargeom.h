@@ -62,6 +62,7 @@ extern "C" {
 #define LG_NMS_MAX_BOXES 65536 /* per NMS problem */
 #define LG_PIB_MAX_BOXES 2048  /* boxes per frame for lg_points_in_boxes (records are shared-memory resident);
                                   frames of up to 254 boxes take the grid-culled path, larger ones test every box */
+#define LG_ROIPOINT_MAX_SAMPLES 2048 /* sampled points per box for lg_roipoint_pool3d_forward (reference default: 512) */
 
 LG_API int lg_version(void);
 LG_API const char *lg_last_error_string(void);
@@ -161,6 +162,34 @@ LG_API int lg_points_in_boxes(const float *boxes, const float *pts, int32_t *out
                        void *ws, size_t ws_bytes, unsigned flags, void *stream);
 LG_API int lg_points_in_boxes_mask(const float *boxes, int64_t n, const float *pts, int64_t m, int32_t *out, float margin,
                             unsigned flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The other users of check_pt_in_box3d ("next" rows).
+ *   lg_roiaware_pool3d_forward  <- roiaware_pool3d_gpu (roiaware_pool3d.cpp:25-62; launcher kernel.cu:186-226)
+ *       rois (N, 7), pts (M, 3), pts_feature (M, C) -> pooled_features (N, ox, oy, oz, C) f32,
+ *       argmax (N, ox, oy, oz, C) i32 (max pooling: point index or -1; may be NULL for avg pooling, else zero-filled),
+ *       pts_idx_of_voxels (N, ox, oy, oz, max_pts) i32: [0] = count (<= max_pts - 1), then the voxel's first points in
+ *       ascending index, zeros after.  pool_method 0 = max, 1 = avg.  Every output element is written by the library
+ *       (the reference needs its wrapper to zero-fill all three, roiaware_pool3d_utils.py:84-86).  1 <= ox, oy, oz <= 255
+ *       (the reference packs voxel coordinates into 8 bits each), ox*oy*oz <= 2^22.
+ *   lg_roiaware_pool3d_backward <- roiaware_pool3d_gpu_backward (roiaware_pool3d.cpp:64-95; kernel.cu:229-310)
+ *       ACCUMULATES into grad_in (num_pts, C) with float atomics like the reference: the caller zero-fills it
+ *       (roiaware_pool3d_utils.py:104).  pts_idx_of_voxels / argmax are the forward's.
+ *   lg_roipoint_pool3d_forward  <- roipool3d_gpu (roipoint_pool3d.cpp:24-58; kernel.cu:38-164)
+ *       xyz (B, N, 3), boxes3d (B, M, 7) (already enlarged by the caller, roipoint_pool3d_utils.py:53), pts_feature (B, N, C)
+ *       -> pooled_features (B, M, S, 3 + C): the first S inside points of every box in ascending index, repeated
+ *       cyclically when fewer (zeros when none), pooled_empty_flag (B, M) i32 0/1.  Both fully written.
+ */
+LG_API int lg_roiaware_pool3d_forward(const float *rois, int num_rois, const float *pts, int num_pts, const float *pts_feature,
+                                      int channels, int out_x, int out_y, int out_z, int max_pts_each_voxel, int pool_method,
+                                      float *pooled_features, int32_t *argmax, int32_t *pts_idx_of_voxels, unsigned flags,
+                                      void *stream);
+LG_API int lg_roiaware_pool3d_backward(const int32_t *pts_idx_of_voxels, const int32_t *argmax, const float *grad_out, float *grad_in,
+                                       int num_rois, int out_x, int out_y, int out_z, int channels, int max_pts_each_voxel,
+                                       int pool_method, unsigned flags, void *stream);
+LG_API int lg_roipoint_pool3d_forward(const float *xyz, const float *boxes3d, const float *pts_feature, int batch, int num_pts,
+                                      int num_boxes, int channels, int num_sampled, float *pooled_features,
+                                      int32_t *pooled_empty_flag, unsigned flags, void *stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,12 @@ def lib():
     L.lg_points_in_boxes.argtypes = [vp, vp, vp, i32, i32, i64, vp, sz, u32, vp]
     L.lg_points_in_boxes_mask.restype = C.c_int
     L.lg_points_in_boxes_mask.argtypes = [vp, i64, vp, i64, vp, f32, u32, vp]
+    L.lg_roiaware_pool3d_forward.restype = C.c_int
+    L.lg_roiaware_pool3d_forward.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, u32, vp]
+    L.lg_roiaware_pool3d_backward.restype = C.c_int
+    L.lg_roiaware_pool3d_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, u32, vp]
+    L.lg_roipoint_pool3d_forward.restype = C.c_int
+    L.lg_roipoint_pool3d_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, u32, vp]
     _lib = L
     return L
 
@@ -74,6 +80,7 @@ EXPORTS = [
     "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d", "lg_iou_reduce_workspace_bytes", "lg_boxes_iou_reduce",
     "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
+    "lg_roiaware_pool3d_forward", "lg_roiaware_pool3d_backward", "lg_roipoint_pool3d_forward",
 ]
 
 

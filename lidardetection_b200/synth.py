@@ -171,3 +171,10 @@ def clustered_pairs(n, m, seed, centre=(35.0, 17.5), priors=KITTI_PRIORS, sigma=
         return b.astype(np.float32)
 
     return mk(n), mk(m)
+
+
+def pool_case(n_points=16384, n_rois=128, channels=128, seed=SEEDS["cfg3"] + 7):
+    """Part-A2 / PointRCNN RoI pooling: one frame of cfg3-shaped points and ROIs plus (n_points, C) features."""
+    pts, rois = cfg3(1, n_points, n_rois, seed)
+    feat = _rng(seed + 1).standard_normal((n_points, channels)).astype(np.float32)
+    return pts[0], rois[0], feat

@@ -7,6 +7,7 @@ setup.py -- and writes only into the git-ignored directory oracle/_ref/:
 
   oracle/_ref/iou3d_nms_cuda/iou3d_nms_cuda.so          (pcdet/ops/iou3d_nms/src/*.{cpp,cu})
   oracle/_ref/roiaware_pool3d_cuda/roiaware_pool3d_cuda.so (pcdet/ops/roiaware_pool3d/src/*.{cpp,cu})
+  oracle/_ref/roipoint_pool3d_cuda/roipoint_pool3d_cuda.so (pcdet/ops/roipoint_pool3d/src/*.{cpp,cu}; "next" row 8f-3)
 
 They are the reference's pybind11 torch extensions, compiled for sm_100a, and serve as
   * tier B oracle (CPU functions boxes_iou_bev_cpu / points_in_boxes_cpu, runnable without GPU),
@@ -36,6 +37,10 @@ EXTS = {
     "roiaware_pool3d_cuda": [
         "pcdet/ops/roiaware_pool3d/src/roiaware_pool3d.cpp",
         "pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu",
+    ],
+    "roipoint_pool3d_cuda": [
+        "pcdet/ops/roipoint_pool3d/src/roipoint_pool3d.cpp",
+        "pcdet/ops/roipoint_pool3d/src/roipoint_pool3d_kernel.cu",
     ],
 }
 

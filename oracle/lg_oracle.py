@@ -48,6 +48,13 @@ def lib():
         L.lgo_points_in_boxes_mask.argtypes = [fp, C.c_int64, fp, C.c_int64, ip, C.c_float, C.c_int]
         L.lgo_point_in_box.restype = C.c_int
         L.lgo_point_in_box.argtypes = [fp, fp, C.c_float, C.c_int]
+        L.lgo_roiaware_pool3d_forward.restype = None
+        L.lgo_roiaware_pool3d_forward.argtypes = [fp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                  fp, ip, ip, C.c_int]
+        L.lgo_roiaware_pool3d_backward.restype = None
+        L.lgo_roiaware_pool3d_backward.argtypes = [ip, ip, fp, fp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int]
+        L.lgo_roipoint_pool3d_forward.restype = None
+        L.lgo_roipoint_pool3d_forward.argtypes = [fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, ip, C.c_int]
         _lib = L
     return _lib
 
@@ -165,3 +172,49 @@ def points_in_boxes_mask(points, boxes, margin=1e-2, flavor=FLAVOR_CPU):
     if out.size:
         lib().lgo_points_in_boxes_mask(_p(bx, C.c_float), bx.shape[0], _p(pts, C.c_float), pts.shape[0], _p(out, C.c_int32), margin, flavor)
     return out
+
+
+def roiaware_pool3d_forward(rois, pts, pts_feature, out_size, max_pts_each_voxel=128, pool_method="max", flavor=FLAVOR_CUDA):
+    """RoIAwarePool3dFunction.forward (roiaware_pool3d_utils.py:57-93): rois (N,7), pts (M,3), pts_feature (M,C) ->
+    pooled (N,ox,oy,oz,C) f32, argmax (N,ox,oy,oz,C) i32, pts_idx_of_voxels (N,ox,oy,oz,max_pts) i32."""
+    rois, pts = _f32(rois, 7), _f32(pts, 3)
+    feat = np.ascontiguousarray(np.asarray(pts_feature, dtype=np.float32))
+    ox, oy, oz = (out_size,) * 3 if isinstance(out_size, int) else out_size
+    n, m, c = rois.shape[0], pts.shape[0], feat.shape[1]
+    pooled = np.zeros((n, ox, oy, oz, c), dtype=np.float32)
+    argmax = np.zeros((n, ox, oy, oz, c), dtype=np.int32)
+    pts_idx = np.zeros((n, ox, oy, oz, max_pts_each_voxel), dtype=np.int32)
+    if n:
+        lib().lgo_roiaware_pool3d_forward(_p(rois, C.c_float), n, _p(pts, C.c_float), m, _p(feat, C.c_float), c, ox, oy, oz,
+                                          max_pts_each_voxel, {"max": 0, "avg": 1}[pool_method], _p(pooled, C.c_float),
+                                          _p(argmax, C.c_int32), _p(pts_idx, C.c_int32), flavor)
+    return pooled, argmax, pts_idx
+
+
+def roiaware_pool3d_backward(pts_idx_of_voxels, argmax, grad_out, num_pts, pool_method="max"):
+    """RoIAwarePool3dFunction.backward (roiaware_pool3d_utils.py:95-107) -> grad_in (num_pts, C)."""
+    pts_idx = np.ascontiguousarray(pts_idx_of_voxels, dtype=np.int32)
+    argmax = np.ascontiguousarray(argmax, dtype=np.int32)
+    g = np.ascontiguousarray(grad_out, dtype=np.float32)
+    n, c, max_pts = pts_idx.shape[0], g.shape[-1], pts_idx.shape[-1]
+    V = int(np.prod(pts_idx.shape[1:4]))
+    grad_in = np.zeros((num_pts, c), dtype=np.float32)
+    if n:
+        lib().lgo_roiaware_pool3d_backward(_p(pts_idx, C.c_int32), _p(argmax, C.c_int32), _p(g, C.c_float), _p(grad_in, C.c_float),
+                                           n, V, c, max_pts, {"max": 0, "avg": 1}[pool_method])
+    return grad_in
+
+
+def roipoint_pool3d_forward(points, point_features, boxes3d, num_sampled_points=512, flavor=FLAVOR_CUDA):
+    """roipool3d_gpu (roipoint_pool3d.cpp:24-58) on already enlarged boxes: points (B,N,3), point_features (B,N,C),
+    boxes3d (B,M,7) -> pooled (B,M,S,3+C) f32, empty flag (B,M) i32."""
+    xyz, bx = _f32(points, 3), _f32(boxes3d, 7)
+    feat = np.ascontiguousarray(np.asarray(point_features, dtype=np.float32))
+    B, n, _ = xyz.shape
+    m, c = bx.shape[1], feat.shape[2]
+    pooled = np.zeros((B, m, num_sampled_points, 3 + c), dtype=np.float32)
+    flag = np.zeros((B, m), dtype=np.int32)
+    if B and m:
+        lib().lgo_roipoint_pool3d_forward(_p(xyz, C.c_float), _p(bx, C.c_float), _p(feat, C.c_float), B, n, m, c,
+                                          num_sampled_points, _p(pooled, C.c_float), _p(flag, C.c_int32), flavor)
+    return pooled, flag

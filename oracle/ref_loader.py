@@ -35,5 +35,9 @@ def roiaware_pool3d_cuda():
     return _load("roiaware_pool3d_cuda")
 
 
+def roipoint_pool3d_cuda():
+    return _load("roipoint_pool3d_cuda")
+
+
 def available():
     return iou3d_nms_cuda() is not None and roiaware_pool3d_cuda() is not None

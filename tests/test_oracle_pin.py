@@ -177,3 +177,71 @@ def test_points_first_hit_and_margins():
     assert idx.tolist() == [0, 0, -1, 0, -1, -1]  # x open with 1e-5 margin, z closed without margin
     m = O.points_in_boxes_mask(pts[0], box[0], 1e-2, O.FLAVOR_CPU)
     assert m[:, 5].tolist() == [1, 1]  # 1 cm margin of the CPU form
+
+
+# ---- "next" row 8f-3: RoI-aware pooling / RoI point pooling -------------------------------------------------------
+def test_pool_oracle_hand_checked_case():
+    """One axis-aligned box, four points whose voxels can be read off by hand (out 2x2x2 over a 4 x 2 x 2 box)."""
+    rois = np.array([[0, 0, 0, 4, 2, 2, 0]], np.float32)
+    pts = np.array([[-1.5, -0.5, -0.5],   # voxel (0, 0, 0)
+                    [1.0, 0.5, 0.5],      # voxel (1, 1, 1)
+                    [1.9, 0.9, 0.9],      # voxel (1, 1, 1) again
+                    [0.0, 0.0, 1.5],      # outside in z
+                    [2.000005, -0.5, -0.5]  # inside only by the 1e-5 margin: (x + dx/2) / res = 2.0000025 -> clamped to voxel 1
+                    ], np.float32)
+    feat = np.array([[1, 10], [2, 30], [3, 20], [9, 99], [4, 5]], np.float32)
+    pooled, argmax, pidx = O.roiaware_pool3d_forward(rois, pts, feat, 2, 3, "max")
+    assert pidx[0, 0, 0, 0].tolist() == [1, 0, 0]
+    assert pidx[0, 1, 1, 1].tolist() == [2, 1, 2]
+    assert pidx[0, 1, 1, 0].tolist() == [0, 0, 0] and pidx[0, 1, 1, 1, 0] == 2
+    assert pidx[0, 1, 1, 1, 0] + pidx[0, 0, 0, 0, 0] + pidx[0, 1, 1, 0, 0] + pidx[0, 1, 0, 1, 0] + pidx[0, 1, 0, 0, 0] == int(pidx[..., 0].sum())
+    assert pooled[0, 1, 1, 1].tolist() == [3, 30] and argmax[0, 1, 1, 1].tolist() == [2, 1]
+    assert argmax[0, 0, 1, 0].tolist() == [-1, -1] and pooled[0, 0, 1, 0].tolist() == [0, 0]
+    assert int(pidx[..., 0].sum()) == 4  # the margin point is in, the z-outlier is not
+    avg, _, _ = O.roiaware_pool3d_forward(rois, pts, feat, 2, 3, "avg")
+    assert avg[0, 1, 1, 1].tolist() == [2.5, 25.0]
+    # max_pts 2 keeps one point per voxel: the FIRST in point order (kernel.cu:96-99)
+    p2, a2, i2 = O.roiaware_pool3d_forward(rois, pts, feat, 2, 2, "max")
+    assert i2[0, 1, 1, 1].tolist() == [1, 1] and p2[0, 1, 1, 1].tolist() == [2, 30]
+    g = np.ones_like(pooled)
+    gin = O.roiaware_pool3d_backward(pidx, argmax, g, 5, "max")
+    assert gin.tolist() == [[1, 1], [0, 1], [1, 0], [0, 0], [1, 1]]
+    gin = O.roiaware_pool3d_backward(pidx, argmax, g, 5, "avg")
+    assert gin.tolist() == [[1, 1], [0.5, 0.5], [0.5, 0.5], [0, 0], [1, 1]]
+    # RoI point pooling: first S inside points in order, cyclic repeat, empty flag
+    boxes = np.stack([rois[0], rois[0] + np.array([100, 0, 0, 0, 0, 0, 0], np.float32)])[None]
+    pooled, flag = O.roipoint_pool3d_forward(pts[None], feat[None], boxes, 6)
+    assert flag.tolist() == [[0, 1]]
+    assert pooled[0, 0, :, 3].tolist() == [1, 2, 3, 4, 1, 2] and pooled[0, 0, 1, :3].tolist() == pts[1].tolist()
+    assert not pooled[0, 1].any()
+    pooled, flag = O.roipoint_pool3d_forward(pts[None], feat[None], boxes, 2)
+    assert pooled[0, 0, :, 3].tolist() == [1, 2]
+
+
+def test_pool_oracle_equals_reference_cuda_golden():
+    """The reference has no CPU build of these functions: the restatement is pinned against outputs of the reference
+    CUDA kernels on a B200 (tests/golden/make_golden_gpu_pool.py)."""
+    import sys
+
+    p = os.path.join(HERE, "golden", "golden_gpu_pool.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden_gpu_pool.npz not generated yet (tests/golden/make_golden_gpu_pool.py via gpurun)")
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden_gpu_pool as GP
+
+    g = np.load(p)
+    for name, pts, rois, feat, out, mp, s in GP.cases():
+        for method in ("max", "avg"):
+            pooled, argmax, pidx = O.roiaware_pool3d_forward(rois, pts, feat, out, mp, method)
+            assert np.array_equal(pidx, g[f"{name}_pts_idx"]), name
+            assert np.array_equal(bits(pooled), bits(g[f"{name}_{method}_pooled"])), (name, method)
+            if method == "max":
+                assert np.array_equal(argmax, g[f"{name}_argmax"]), name
+            go = np.random.default_rng(7).standard_normal(pooled.shape).astype(np.float32)
+            gin = O.roiaware_pool3d_backward(pidx, g[f"{name}_argmax"], go, pts.shape[0], method)
+            want = g[f"{name}_{method}_grad_in"]  # float atomics: unordered sums
+            assert np.abs(gin - want).max() <= 1e-5 * max(1.0, float(np.abs(want).max())), (name, method)
+        big = rois.copy()
+        big[:, 3:6] += np.float32(0.2)
+        pf, fl = O.roipoint_pool3d_forward(pts[None], feat[None], big[None], s)
+        assert np.array_equal(fl, g[f"{name}_rp_flag"]) and np.array_equal(bits(pf), bits(g[f"{name}_rp_pooled"])), name
