@@ -407,6 +407,104 @@ class PibWorkload(Workload):
         return n / dt, f"points_in_boxes_cpu on {n} frames of 16,384 points x 100 boxes (one frame per task)"
 
 
+class RoiPoolWorkload(Workload):
+    """SURVEY 8f-3.  roiaware_partA2: the two RoIAwarePool3d calls per frame of PartA2Head.roiaware_pool (partA2_head.py:131-143;
+    PartA2.yaml: 128 ROIs, 12^3 voxels, 128 points per voxel): avg over 4 part-location channels + max over 128 RPN channels.
+    roipoint_pointrcnn: RoIPointPool3d of PointRCNNHead.roipool3d_gpu (pointrcnn_head.py:117-121; 128 ROIs, 512 samples,
+    128 + 2 feature channels, batch 4)."""
+    dtype = "f32"
+    cpu_kind = "port"
+
+    def __init__(self, torch, which, rank):
+        from lidardetection_b200 import synth
+        from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU
+        from lidardetection_b200.ops.roipoint_pool3d import roipoint_pool3d_utils as RU
+
+        self.torch, self.which = torch, which
+        B, M, N = 4, 16384, 128
+        self.units = B
+        frames = [synth.pool_case(M, N, 130, seed=9000 + 16 * rank + f) for f in range(B)]
+        self.np_pts = np.stack([f[0] for f in frames])
+        self.np_rois = np.stack([f[1] for f in frames])
+        feat = np.stack([f[2] for f in frames])
+        if which == "roiaware_partA2":
+            self.np_feats = [np.ascontiguousarray(feat[..., :4]), np.ascontiguousarray(feat[..., 2:130])]
+            self.layer = PU.RoIAwarePool3d(out_size=12, max_pts_each_voxel=128)
+            V = 12 ** 3
+            self.name = "Part-A2 KITTI RoI-aware pooling: 16,384 points x 128 ROIs, 12^3 voxels x 128 points, avg (C=4) + max (C=128) call per frame, 4 frames per GPU"
+            self.metric, self.unit = "RoI-aware pooling frames/s (128 ROIs, 12^3 voxels)", "frames/s"
+            # algorithmic bytes per frame: inputs once per call; outputs: voxel lists twice (one per call), pooled, argmax (max call)
+            self.bytes_per_frame = 2 * (28.0 * N + 12.0 * M) + 4.0 * M * (4 + 128) + 2 * 4.0 * N * V * 128 + 4.0 * N * V * (4 + 128 + 128)
+            self.formula = "2*(28N + 12M) + 4M(4+128) + 2*4*N*V*max_pts + 4*N*V*(4 + 128 + 128)"
+            self.kernel = "memset + roiaware_collect_kernel + roiaware_pool_kernel, both calls"
+            self.launches_per_step = 4 * B
+            self.d2h = B * 4 * N * V * (4 + 128)
+        else:
+            self.np_feats = [feat]
+            self.layer = RU.RoIPointPool3d(num_sampled_points=512, pool_extra_width=(0.0, 0.0, 0.0))
+            self.name = "PointRCNN KITTI RoI point pooling: 16,384 points x 128 ROIs x 512 samples, 130 channels, batch 4 in one call"
+            self.metric, self.unit = "RoI point pooling frames/s (128 ROIs x 512 samples)", "frames/s"
+            self.bytes_per_frame = 28.0 * N + 12.0 * M + 4.0 * M * 130 + 4.0 * N * 512 * 133 + 4.0 * N
+            self.formula = "28N + 12M + 4*M*C + 4*N*S*(3+C) + 4N"
+            self.kernel = "roipoint_pool_kernel"
+            self.launches_per_step = 1
+            self.d2h = B * (4 * N * 512 * 133 + 4 * N)
+        cu = lambda x: torch.from_numpy(x).cuda()  # noqa: E731
+        pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
+        self.pts, self.rois, self.feats = cu(self.np_pts), cu(self.np_rois), [cu(f) for f in self.np_feats]
+        self.h_pts, self.h_rois, self.h_feats = pin(self.np_pts), pin(self.np_rois), [pin(f) for f in self.np_feats]
+        self.h2d = 4 * (self.np_pts.size + self.np_rois.size + sum(f.size for f in self.np_feats))
+
+    def _run(self, pts, rois, feats):
+        if self.which == "roiaware_partA2":
+            outs = []
+            for b in range(pts.shape[0]):  # the reference's own per-frame loop (partA2_head.py:131)
+                outs.append(self.layer(rois[b], pts[b], feats[0][b], pool_method="avg"))
+                outs.append(self.layer(rois[b], pts[b], feats[1][b], pool_method="max"))
+            return outs
+        return list(self.layer(pts, feats[0], rois))
+
+    def step(self):
+        return self._run(self.pts, self.rois, self.feats)
+
+    def e2e_step(self):
+        outs = self._run(self.h_pts.cuda(non_blocking=True), self.h_rois.cuda(non_blocking=True), [f.cuda(non_blocking=True) for f in self.h_feats])
+        return [o.cpu() for o in outs]
+
+    def result_for_gather(self, out):
+        return []
+
+    def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
+        torch = self.torch
+        ts = []
+        for _ in range(max(3, steps)):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.step()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = float(np.mean(ts)) * 1e-3
+        byts = self.units * self.bytes_per_frame
+        ach = byts / t / 1e9
+        return {"bound": "hbm", "kernel": self.kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                "peak_source": hbm_src, "algorithmic": {"bytes_per_step": byts, "formula": self.formula, "bytes_per_frame": self.bytes_per_frame,
+                                                        "note": "timed over the whole step (all launches of the frames' calls), not one kernel"}}
+
+    def cpu_sample(self, pool):
+        n = pool.workers
+        B = self.np_pts.shape[0]
+        if self.which == "roiaware_partA2":
+            jobs = [(self.np_pts[i % B], self.np_rois[i % B], self.np_feats[0][i % B], self.np_feats[1][i % B], 12, 128) for i in range(n)]
+            dt = pool.roiaware_frames(jobs)
+            what = "RoI-aware pooling"
+        else:
+            jobs = [(self.np_pts[i % B], self.np_rois[i % B], self.np_feats[0][i % B], 512) for i in range(n)]
+            dt = pool.roipoint_frames(jobs)
+            what = "RoI point pooling"
+        return n / dt, f"C restatement of the reference CUDA kernels ({what}; the reference has no CPU build of it), {n} frames, one per core"
+
+
 class PostProcWorkload(Workload):
     """the post-processing front end of SECOND KITTI (second.yaml:94-99): 70,400 candidates per frame,
     SCORE_THRESH 0.1 -> top 4096 -> rotated NMS (0.01) -> 500, 64 frames per GPU, one batched call."""
@@ -574,6 +672,8 @@ def make_workload(torch, which, rank, world):
         return IouWorkload(torch, which, rank, world)
     if which == "pib_cfg3":
         return PibWorkload(torch, rank)
+    if which in ("roiaware_partA2", "roipoint_pointrcnn"):
+        return RoiPoolWorkload(torch, which, rank)
     raise SystemExit(f"unknown workload {which}")
 
 
@@ -585,7 +685,7 @@ def run_reference(args, rank):
     from oracle.cpu_baseline import CpuPool
 
     pool = CpuPool(prefer_reference=True)
-
+    kind_override = None
 
     from lidardetection_b200 import synth
 
@@ -619,6 +719,23 @@ def run_reference(args, rank):
 
         def one(i):
             return pool.iou_matrix(a, bb), a.shape[0] * bb.shape[0] / 1e9
+    elif which in ("roiaware_partA2", "roipoint_pointrcnn"):
+        # the reference has no CPU build of these functions: the C restatement of its CUDA kernels (kind "port")
+        frames = [synth.pool_case(16384, 128, 130, seed=9000 + f) for f in range(4)]
+        kind_override = "port"
+        if which == "roiaware_partA2":
+            jobs = [(f[0], f[1], np.ascontiguousarray(f[2][:, :4]), np.ascontiguousarray(f[2][:, 2:130]), 12, 128) for f in frames]
+            metric, unit, name = "RoI-aware pooling frames/s (128 ROIs, 12^3 voxels)", "frames/s", "Part-A2 KITTI RoI-aware pooling: 16,384 points x 128 ROIs, 12^3 voxels x 128 points, avg (C=4) + max (C=128) call per frame"
+            run = pool.roiaware_frames
+        else:
+            jobs = [(f[0], f[1], f[2], 512) for f in frames]
+            metric, unit, name = "RoI point pooling frames/s (128 ROIs x 512 samples)", "frames/s", "PointRCNN KITTI RoI point pooling: 16,384 points x 128 ROIs x 512 samples, 130 channels"
+            run = pool.roipoint_frames
+        jobs = [jobs[i % 4] for i in range(pool.workers)]
+        sample = f"C restatement of the reference CUDA kernels, {len(jobs)} frames per step, one per core"
+
+        def one(i):
+            return run(jobs), float(len(jobs))
     else:
         p, r = synth.cfg3(n_frames=4 * pool.workers)
         metric, unit = "points-in-boxes frames/s (16,384 pts x 100 ROIs)", "frames/s"
@@ -639,7 +756,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (seeded, SURVEY.md 8d shapes)", "config": {"workload": name},
-            "cpu_baseline": {"value": val, "unit": unit, "cores": pool.workers, "kind": pool.kind, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": unit, "cores": pool.workers, "kind": kind_override or pool.kind, "sample": sample},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -654,7 +771,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="nms_cfg2", choices=["nms_cfg2", "nms_cfg5", "iou_dense", "iou_cfg1", "iou_cfg4", "pib_cfg3", "post_cfg2", "iou_max_cfg4"])
+    ap.add_argument("--workload", default="nms_cfg2", choices=["nms_cfg2", "nms_cfg5", "iou_dense", "iou_cfg1", "iou_cfg4", "pib_cfg3", "post_cfg2", "iou_max_cfg4", "roiaware_partA2", "roipoint_pointrcnn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -687,7 +804,7 @@ def main():
     cpu_baseline = None
     if cpu_pool is not None:
         v, sample = wl.cpu_sample(cpu_pool)
-        cpu_baseline = {"value": v, "unit": wl.unit, "cores": cpu_pool.workers, "kind": cpu_pool.kind, "sample": sample}
+        cpu_baseline = {"value": v, "unit": wl.unit, "cores": cpu_pool.workers, "kind": getattr(wl, "cpu_kind", cpu_pool.kind), "sample": sample}
         cpu_pool.close()
         log("cpu_baseline", cpu_baseline)
 

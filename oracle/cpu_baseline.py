@@ -66,6 +66,19 @@ def _pib_block(args):
     return int(_STATE["orc"].points_in_boxes_mask(pts, boxes, 1e-2, 0).sum())
 
 
+def _roiaware_frame(args):
+    pts, rois, feat_part, feat_rpn, out, max_pts = args
+    o = _STATE["orc"]
+    a = o.roiaware_pool3d_forward(rois, pts, feat_part, out, max_pts, "avg")[0]
+    b = o.roiaware_pool3d_forward(rois, pts, feat_rpn, out, max_pts, "max")[0]
+    return float(a.sum()) + float(b.sum())
+
+
+def _roipoint_frame(args):
+    pts, boxes, feat, s = args
+    return float(_STATE["orc"].roipoint_pool3d_forward(pts[None], feat[None], boxes[None], s)[0].sum())
+
+
 class CpuPool:
     def __init__(self, prefer_reference=True, workers=None):
         from oracle import ref_loader
@@ -127,6 +140,18 @@ class CpuPool:
         """frames of points_in_boxes_cpu; pts (B,M,3), boxes (B,T,7); returns seconds"""
         t0 = time.perf_counter()
         self._map(_pib_block, [(pts[f], boxes[f]) for f in range(pts.shape[0])])
+        return time.perf_counter() - t0
+
+
+    def roiaware_frames(self, frames):
+        """Part-A2 RoI-aware pooling (avg + max call) per frame; the reference has no CPU build of it: always the port"""
+        t0 = time.perf_counter()
+        self._map(_roiaware_frame, frames)
+        return time.perf_counter() - t0
+
+    def roipoint_frames(self, frames):
+        t0 = time.perf_counter()
+        self._map(_roipoint_frame, frames)
         return time.perf_counter() - t0
 
 

@@ -44,5 +44,16 @@ elif op == "pib":
     tp, tr = cu(p), cu(r)
     for _ in range(iters):
         PU.points_in_boxes_gpu(tp, tr)
+elif op in ("roiaware", "roipoint"):
+    from lidardetection_b200.ops.roipoint_pool3d import roipoint_pool3d_utils as RU
+
+    pts, rois, feat = synth.pool_case(16384, 128, 128)
+    tp, tr, tf = cu(pts), cu(rois), cu(feat)
+    for _ in range(iters):
+        if op == "roiaware":
+            po, am, pi = PU.roiaware_pool3d_forward(tr, tp, tf, 12, 128, "max")
+            PU.roiaware_pool3d_backward(pi, am, po, 16384, "max")
+        else:
+            RU.roipoint_pool3d_forward(tp[None], tr[None], tf[None], 512)
 torch.cuda.synchronize()
 print("ok", op)
