@@ -505,6 +505,81 @@ class RoiPoolWorkload(Workload):
         return n / dt, f"C restatement of the reference CUDA kernels ({what}; the reference has no CPU build of it), {n} frames, one per core"
 
 
+class KittiEvalWorkload(Workload):
+    """the overlap half of one KITTI val evaluation -- calculate_iou_partly for metric 1 (bev) and metric 2 (3d)
+    (eval.py:340-414 as called from eval_class, eval.py:473) on 3769 synthetic frames in 51 parts (28.1 M pairs per metric).
+    The reference does, per part and metric, H2D -> numba.cuda kernel -> D2H (-> numba CPU pass for 3d); here each metric is
+    ONE launch of lg_kitti_overlaps_parts over all parts."""
+    dtype = "f32 geometry / f64 area sum and ratio"
+    cpu_kind = "port"
+
+    def __init__(self, torch, rank):
+        from lidardetection_b200 import synth
+        from lidardetection_b200.datasets.kitti.kitti_object_eval_python import eval as E
+
+        self.torch, self.E = torch, E
+        self.gts, self.dts = synth.kitti_eval_frames(3769, 5000 + rank)
+        parts = E.get_split_parts(3769, 50)
+        self.gc, self.dc, i = [], [], 0
+        for n in parts:
+            self.gc.append(sum(len(x) for x in self.gts[i:i + n]))
+            self.dc.append(sum(len(x) for x in self.dts[i:i + n]))
+            i += n
+        self.parts = parts
+        self.G, self.D = np.concatenate(self.gts), np.concatenate(self.dts)
+        self.g, self.d = torch.from_numpy(self.G).cuda(), torch.from_numpy(self.D).cuda()
+        mk = lambda fr: [{"name": np.zeros(len(f)), "location": f[:, 0:3], "dimensions": f[:, 3:6], "rotation_y": f[:, 6]} for f in fr]  # noqa: E731
+        self.ga, self.da = mk(self.gts), mk(self.dts)
+        self.pairs = int(sum(a * b for a, b in zip(self.gc, self.dc)))
+        self.units = 2 * self.pairs / 1e9
+        self.metric, self.unit = "KITTI-eval rotated overlap Gpairs/s (bev + 3d)", "Gpairs/s"
+        self.name = (f"KITTI val evaluation overlaps: calculate_iou_partly metric 1 (bev) + metric 2 (3d), 3769 frames in {len(parts)} parts, "
+                     f"{self.pairs} pairs per metric, per GPU")
+        self.launches_per_step = 6  # per metric: 2 x kitti_prep_kernel + kitti_pair_kernel
+        self.h2d = 2 * 56 * (len(self.G) + len(self.D))
+        self.d2h = 2 * 4 * self.pairs
+        self.bytes_per_step = 2.0 * (4.0 * self.pairs + 56.0 * (len(self.G) + len(self.D)))
+
+    def step(self):
+        return [self.E.kitti_overlaps_parts_cuda(self.g, self.d, self.gc, self.dc, m)[0] for m in (1, 2)]
+
+    def e2e_step(self):
+        return [self.E.calculate_iou_partly(self.ga, self.da, m)[1] for m in (1, 2)]
+
+    def result_for_gather(self, out):
+        return []
+
+    def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
+        torch = self.torch
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        ts = []
+        for _ in range(max(3, steps)):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.step()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        t = float(np.mean(ts)) * 1e-3
+        ach = self.bytes_per_step / t / 1e9
+        return {"bound": "hbm", "kernel": "kitti_pair_kernel (+2 x kitti_prep_kernel), both metrics", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "algorithmic": {"bytes_per_step": self.bytes_per_step, "formula": "2 metrics x (4 B x pairs + 56 B x boxes)",
+                                "note": "99.5 % of the pairs are exactly 0 (culled): the output write is the algorithmic traffic; timed over the whole step"}}
+
+    def cpu_sample(self, pool):
+        n = min(pool.workers, len(self.parts))
+        jobs, i = [], 0
+        for p in range(n):
+            jobs.append((np.concatenate(self.gts[i:i + self.parts[p]]), np.concatenate(self.dts[i:i + self.parts[p]])))
+            i += self.parts[p]
+        dt = pool.kitti_parts(jobs)
+        pairs = sum(len(g) * len(d) for g, d in jobs)
+        return 2 * pairs / dt / 1e9, (f"C restatement of the reference numba.cuda kernel + d3_box_overlap_kernel (the reference has no CPU build of the "
+                                      f"rotated part), {n} evaluation parts (bev + 3d), one per core")
+
+
 class PostProcWorkload(Workload):
     """the post-processing front end of SECOND KITTI (second.yaml:94-99): 70,400 candidates per frame,
     SCORE_THRESH 0.1 -> top 4096 -> rotated NMS (0.01) -> 500, 64 frames per GPU, one batched call."""
@@ -674,6 +749,8 @@ def make_workload(torch, which, rank, world):
         return PibWorkload(torch, rank)
     if which in ("roiaware_partA2", "roipoint_pointrcnn"):
         return RoiPoolWorkload(torch, which, rank)
+    if which == "kitti_eval":
+        return KittiEvalWorkload(torch, rank)
     raise SystemExit(f"unknown workload {which}")
 
 
@@ -736,6 +813,23 @@ def run_reference(args, rank):
 
         def one(i):
             return run(jobs), float(len(jobs))
+    elif which == "kitti_eval":
+        from lidardetection_b200.datasets.kitti.kitti_object_eval_python.eval import get_split_parts
+
+        kind_override = "port"  # the reference's rotated overlap exists only as a numba.cuda kernel
+        gts, dts = synth.kitti_eval_frames(3769, 5000)
+        parts = get_split_parts(3769, 50)
+        jobs, i0 = [], 0
+        for p in range(min(pool.workers, len(parts))):
+            jobs.append((np.concatenate(gts[i0:i0 + parts[p]]), np.concatenate(dts[i0:i0 + parts[p]])))
+            i0 += parts[p]
+        metric, unit = "KITTI-eval rotated overlap Gpairs/s (bev + 3d)", "Gpairs/s"
+        name = "KITTI val evaluation overlaps: calculate_iou_partly metric 1 (bev) + metric 2 (3d), 3769 frames in 51 parts"
+        npairs = sum(len(g) * len(d) for g, d in jobs)
+        sample = f"C restatement of the reference numba.cuda kernel + d3_box_overlap_kernel, {len(jobs)} evaluation parts (bev + 3d) per step, one per core"
+
+        def one(i):
+            return pool.kitti_parts(jobs), 2 * npairs / 1e9
     else:
         p, r = synth.cfg3(n_frames=4 * pool.workers)
         metric, unit = "points-in-boxes frames/s (16,384 pts x 100 ROIs)", "frames/s"
@@ -771,7 +865,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="nms_cfg2", choices=["nms_cfg2", "nms_cfg5", "iou_dense", "iou_cfg1", "iou_cfg4", "pib_cfg3", "post_cfg2", "iou_max_cfg4", "roiaware_partA2", "roipoint_pointrcnn"])
+    ap.add_argument("--workload", default="nms_cfg2", choices=["nms_cfg2", "nms_cfg5", "iou_dense", "iou_cfg1", "iou_cfg4", "pib_cfg3", "post_cfg2", "iou_max_cfg4", "roiaware_partA2", "roipoint_pointrcnn", "kitti_eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

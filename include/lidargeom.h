@@ -191,6 +191,37 @@ LG_API int lg_roipoint_pool3d_forward(const float *xyz, const float *boxes3d, co
                                       int num_boxes, int channels, int num_sampled, float *pooled_features,
                                       int32_t *pooled_empty_flag, unsigned flags, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * KITTI evaluation overlaps.  NOT the conventions of the ops above: 5-parameter boxes
+ * (cx, cy, x_d, y_d, angle) with the angle clockwise-positive, no margin, closed containment, and
+ * out[n * k_total + k] = f(query_boxes[k], boxes[n]); criterion -1: inter / (area_q + area_b - inter), 0: inter / area_q,
+ * 1: inter / area_b, anything else: inter (rotate_iou.py:246-258).  Arithmetic: that of the reference's numba.cuda kernel
+ * as numba / NVVM / ptxas 12.9 build it for sm_100a (float32 geometry, float64 area sum and ratio); LG_FLAG_STRICT_FP32
+ * drops the FMA contraction.  The reference's 8-point polygon buffer (undefined behaviour beyond) is 24 points here.
+ *
+ *   lg_rotate_iou_eval      <- rotate_iou_gpu_eval + rotate_iou_kernel_eval (kitti_object_eval_python/rotate_iou.py:260-330);
+ *                              bev_box_overlap (eval.py:111-113) is this call.  boxes (N, 5) f32, query_boxes (K, 5) f32.
+ *   lg_d3_box_overlap       <- d3_box_overlap + d3_box_overlap_kernel (eval.py:116-155): float64 CAMERA boxes
+ *                              (x, y, z, l, h, w, ry); BEV overlap of columns [0, 2, 3, 5, 6] cast to float32, height overlap
+ *                              and ratio in float64, result float32 -- one pass instead of GPU kernel + D2H + CPU pass.
+ *   lg_kitti_overlaps_parts <- the per-part loop of calculate_iou_partly (eval.py:340-395): num_parts independent
+ *                              (gt part) x (dt part) problems in ONE launch.  gt_boxes (num_gt, 7) / dt_boxes (num_dt, 7)
+ *                              float64 camera boxes of all parts end to end; gt_off / dt_off / out_off: (num_parts + 1)
+ *                              int64 DEVICE arrays of row offsets and of output offsets (out_off[p + 1] - out_off[p] =
+ *                              rows_gt(p) * rows_dt(p)); part p's matrix is out[out_off[p] ..) row-major (gt x dt).
+ *                              metric 1 = bev (bev_box_overlap of columns [0,2,3,5,6]), 2 = 3d (d3_box_overlap).
+ * ws must hold lg_kitti_workspace_bytes(rows of boxes, rows of query boxes) bytes.
+ */
+LG_API size_t lg_kitti_workspace_bytes(int64_t num_boxes, int64_t num_query_boxes);
+LG_API int lg_rotate_iou_eval(const float *boxes, int64_t n, const float *query_boxes, int64_t k, float *out, int criterion, void *ws,
+                              size_t ws_bytes, unsigned flags, void *stream);
+LG_API int lg_d3_box_overlap(const double *boxes, int64_t n, const double *qboxes, int64_t k, float *out, int criterion, void *ws,
+                             size_t ws_bytes, unsigned flags, void *stream);
+LG_API int lg_kitti_overlaps_parts(const double *gt_boxes, int64_t num_gt, const double *dt_boxes, int64_t num_dt,
+                                   const int64_t *gt_off, const int64_t *dt_off, const int64_t *out_off, int num_parts,
+                                   int64_t num_out, int metric, int criterion, float *out, void *ws, size_t ws_bytes, unsigned flags,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,14 @@ def lib():
     L.lg_roiaware_pool3d_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, u32, vp]
     L.lg_roipoint_pool3d_forward.restype = C.c_int
     L.lg_roipoint_pool3d_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, u32, vp]
+    L.lg_kitti_workspace_bytes.restype = sz
+    L.lg_kitti_workspace_bytes.argtypes = [i64, i64]
+    L.lg_rotate_iou_eval.restype = C.c_int
+    L.lg_rotate_iou_eval.argtypes = [vp, i64, vp, i64, vp, i32, vp, sz, u32, vp]
+    L.lg_d3_box_overlap.restype = C.c_int
+    L.lg_d3_box_overlap.argtypes = [vp, i64, vp, i64, vp, i32, vp, sz, u32, vp]
+    L.lg_kitti_overlaps_parts.restype = C.c_int
+    L.lg_kitti_overlaps_parts.argtypes = [vp, i64, vp, i64, vp, vp, vp, i32, i64, i32, i32, vp, vp, sz, u32, vp]
     _lib = L
     return L
 
@@ -81,6 +89,7 @@ EXPORTS = [
     "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
     "lg_roiaware_pool3d_forward", "lg_roiaware_pool3d_backward", "lg_roipoint_pool3d_forward",
+    "lg_kitti_workspace_bytes", "lg_rotate_iou_eval", "lg_d3_box_overlap", "lg_kitti_overlaps_parts",
 ]
 
 

@@ -1,0 +1,440 @@
+// lg_kitti.cu -- SURVEY 8f-2: the KITTI evaluation's rotated overlaps.
+//
+// Replaces, behind the C ABI,
+//   rotate_iou_gpu_eval / rotate_iou_kernel_eval   pcdet/datasets/kitti/kitti_object_eval_python/rotate_iou.py:260-330 (numba.cuda)
+//   bev_box_overlap, d3_box_overlap(+_kernel)      pcdet/datasets/kitti/kitti_object_eval_python/eval.py:111-155
+//   the per-part loop of calculate_iou_partly      eval.py:340-414 (one H2D + launch + D2H + numba-CPU pass per part)
+//
+// Conventions of that code (NOT those of iou3d_nms): 5-parameter boxes (cx, cy, x_d, y_d, angle), angle clockwise, no
+// margin, closed containment, iou[n, k] = f(query_boxes[k], boxes[n]), `criterion` -1 / 0 / 1 / other.
+//
+// Arithmetic contract: the operation order, operand types (numba types python float literals as float64) and FMA
+// contraction of the reference kernel as numba 0.65 -> NVVM -> ptxas 12.9 build it for sm_100a; see the block comment in
+// oracle/lg_oracle.c ("Next row 8f-2") for the list, read off that build's PTX / SASS.  LG_FLAG_STRICT_FP32 evaluates the
+// same statements without contraction.  Every float operation below is an explicit _rn intrinsic: nvcc never re-contracts
+// those.
+//
+// Structure: a prep kernel turns every box into a 48-byte record (rotated corners, centre, circum-radius, area) -- the
+// reference recomputes sin/cos and the corners for every PAIR.  The pair kernel works on chunks of 2048 consecutive
+// output elements per 256-thread CTA: phase 1 puts every pair to an exact-zero test (circum-circles apart by a slack
+// that dwarfs any rounding of the reference's predicates => the reference collects < 3 polygon points => its area is
+// exactly 0.0) and stores those results coalesced; the survivors (~0.5 % of a KITTI part) are queued in shared memory
+// and phase 2 runs the polygon path on the queue with full warps.  Several evaluation "parts" (independent N_p x K_p
+// problems, eval.py:356-395) are laid end to end in one launch.
+#include "lg_common.cuh"
+
+namespace lg {
+namespace kitti {
+
+constexpr int THREADS = 256;
+constexpr int PER_THREAD = 8;
+constexpr int CHUNK = THREADS * PER_THREAD;
+constexpr int MAXPTS = 24;  // 8 corners + 16 crossings; the reference's buffer holds 8 (undefined beyond, see oracle)
+
+struct Rec {        // 48 bytes
+    float c[8];     // rotated corners x0 y0 .. x3 y3 (rbbox_to_corners)
+    float cx, cy;   // centre
+    float r;        // half diagonal
+    float area;     // x_d * y_d
+};
+struct RecZ {       // d3_box_overlap: float64 camera-frame extras
+    double y, ybot, vol;
+};
+
+template <int FL>
+__device__ __forceinline__ float msub(float a, float b, float c, float d) {  // a*b - c*d
+    if (FL) return __fmaf_rn(a, b, -__fmul_rn(c, d));
+    return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+template <int FL>
+__device__ __forceinline__ float madd(float a, float b, float c, float d) {  // a*b + c*d, first product fused
+    if (FL) return __fmaf_rn(a, b, __fmul_rn(c, d));
+    return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+
+// rbbox_to_corners (rotate_iou.py:201-227) + the per-box constants
+template <int FL>
+__device__ __forceinline__ void make_rec(float bx, float by, float xd, float yd, float ang, Rec& R) {
+    const float a_cos = cosf(ang), a_sin = sinf(ang);
+    const float cxs[4] = {__fmul_rn(xd, -0.5f), __fmul_rn(xd, -0.5f), __fmul_rn(xd, 0.5f), __fmul_rn(xd, 0.5f)};
+    const float cys[4] = {__fmul_rn(yd, -0.5f), __fmul_rn(yd, 0.5f), __fmul_rn(yd, 0.5f), __fmul_rn(yd, -0.5f)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (FL) {
+            R.c[2 * i] = __fadd_rn(bx, __fmaf_rn(a_cos, cxs[i], __fmul_rn(a_sin, cys[i])));
+            R.c[2 * i + 1] = __fadd_rn(by, __fmaf_rn(a_cos, cys[i], -__fmul_rn(a_sin, cxs[i])));
+        } else {
+            R.c[2 * i] = __fadd_rn(__fadd_rn(__fmul_rn(a_cos, cxs[i]), __fmul_rn(a_sin, cys[i])), bx);
+            R.c[2 * i + 1] = __fadd_rn(__fadd_rn(__fmul_rn(-a_sin, cxs[i]), __fmul_rn(a_cos, cys[i])), by);
+        }
+    }
+    R.cx = bx;
+    R.cy = by;
+    R.r = 0.5f * sqrtf(xd * xd + yd * yd);
+    // A quadrilateral with a zero-length side (dims of 0, or below the ulp of the centre) makes point_in_quadrilateral's
+    // tests along that side read 0 >= 0 >= 0: it "contains" an infinite strip, so distance proves nothing.  Such a box is
+    // never culled (infinite radius => the exact-zero test is false for every pair it takes part in).
+    const float e0 = __fsub_rn(R.c[2], R.c[0]), e1 = __fsub_rn(R.c[3], R.c[1]), f0 = __fsub_rn(R.c[6], R.c[0]), f1 = __fsub_rn(R.c[7], R.c[1]);
+    if (!(e0 * e0 + e1 * e1 >= 1e-30f && f0 * f0 + f1 * f1 >= 1e-30f)) R.r = __int_as_float(0x7f800000);
+    R.area = __fmul_rn(xd, yd);
+}
+
+// in_f32 != nullptr: rows of 5 floats; else in_f64: rows of 7 doubles (x, y, z, l, h, w, ry) -> columns [0, 2, 3, 5, 6]
+template <int FL>
+__global__ void __launch_bounds__(256) kitti_prep_kernel(const float* __restrict__ in_f32, const double* __restrict__ in_f64, int64_t n,
+                                                         Rec* __restrict__ rec, RecZ* __restrict__ recz) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float bx, by, xd, yd, ang;
+    if (in_f32) {
+        const float* b = in_f32 + 5 * i;
+        bx = b[0], by = b[1], xd = b[2], yd = b[3], ang = b[4];
+    } else {
+        const double* b = in_f64 + 7 * i;
+        bx = __double2float_rn(b[0]), by = __double2float_rn(b[2]), xd = __double2float_rn(b[3]), yd = __double2float_rn(b[5]);
+        ang = __double2float_rn(b[6]);
+        if (recz) {
+            RecZ z;
+            z.y = b[1];
+            z.ybot = __dsub_rn(b[1], b[4]);
+            z.vol = __dmul_rn(__dmul_rn(b[3], b[4]), b[5]);
+            recz[i] = z;
+        }
+    }
+    Rec R;
+    make_rec<FL>(bx, by, xd, yd, ang, R);
+    float4* o = reinterpret_cast<float4*>(rec + i);
+    o[0] = make_float4(R.c[0], R.c[1], R.c[2], R.c[3]);
+    o[1] = make_float4(R.c[4], R.c[5], R.c[6], R.c[7]);
+    o[2] = make_float4(R.cx, R.cy, R.r, R.area);
+}
+
+// point_in_quadrilateral (rotate_iou.py:155-173)
+template <int FL>
+__device__ __forceinline__ bool in_quad(float px, float py, const float* c) {
+    const float ab0 = __fsub_rn(c[2], c[0]), ab1 = __fsub_rn(c[3], c[1]), ad0 = __fsub_rn(c[6], c[0]), ad1 = __fsub_rn(c[7], c[1]);
+    const float ap0 = __fsub_rn(px, c[0]), ap1 = __fsub_rn(py, c[1]);
+    float abab, abap, adad, adap;
+    if (FL) {
+        abab = __fmaf_rn(ab0, ab0, __fmul_rn(ab1, ab1));
+        abap = __fmaf_rn(ab1, ap1, __fmul_rn(ab0, ap0));
+        adad = __fmaf_rn(ad0, ad0, __fmul_rn(ad1, ad1));
+        adap = __fmaf_rn(ad1, ap1, __fmul_rn(ad0, ap0));
+    } else {
+        abab = __fadd_rn(__fmul_rn(ab0, ab0), __fmul_rn(ab1, ab1));
+        abap = __fadd_rn(__fmul_rn(ab0, ap0), __fmul_rn(ab1, ap1));
+        adad = __fadd_rn(__fmul_rn(ad0, ad0), __fmul_rn(ad1, ad1));
+        adap = __fadd_rn(__fmul_rn(ad0, ap0), __fmul_rn(ad1, ap1));
+    }
+    return abab >= abap && abap >= 0.0f && adad >= adap && adap >= 0.0f;
+}
+
+// inter() (rotate_iou.py:230-243): quadrilateral_intersection + sort_vertex_in_convex_polygon + area; c1 = first argument
+template <int FL>
+__device__ __noinline__ double inter_area(const float* __restrict__ c1, const float* __restrict__ c2) {
+    float pts[2 * MAXPTS], vs[MAXPTS];
+    int n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (in_quad<FL>(c1[2 * i], c1[2 * i + 1], c2)) {
+            pts[2 * n] = c1[2 * i], pts[2 * n + 1] = c1[2 * i + 1];
+            ++n;
+        }
+        if (in_quad<FL>(c2[2 * i], c2[2 * i + 1], c1)) {
+            pts[2 * n] = c2[2 * i], pts[2 * n + 1] = c2[2 * i + 1];
+            ++n;
+        }
+    }
+    // line_segment_intersection (rotate_iou.py:77-116), A->B an edge of c1, C->D an edge of c2
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float A0 = c1[2 * i], A1 = c1[2 * i + 1], B0 = c1[2 * ((i + 1) & 3)], B1 = c1[2 * ((i + 1) & 3) + 1];
+        const float BA0 = __fsub_rn(B0, A0), BA1 = __fsub_rn(B1, A1);
+        const float ABBA = msub<FL>(A0, B1, B0, A1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float C0 = c2[2 * j], C1 = c2[2 * j + 1], D0 = c2[2 * ((j + 1) & 3)], D1 = c2[2 * ((j + 1) & 3) + 1];
+            const float DA0 = __fsub_rn(D0, A0), CA0 = __fsub_rn(C0, A0), DA1 = __fsub_rn(D1, A1), CA1 = __fsub_rn(C1, A1);
+            const bool acd = __fmul_rn(DA1, CA0) > __fmul_rn(CA1, DA0);
+            const bool bcd = __fmul_rn(__fsub_rn(D1, B1), __fsub_rn(C0, B0)) > __fmul_rn(__fsub_rn(C1, B1), __fsub_rn(D0, B0));
+            if (acd != bcd) {
+                const bool abc = __fmul_rn(CA1, BA0) > __fmul_rn(BA1, CA0);
+                const bool abd = __fmul_rn(DA1, BA0) > __fmul_rn(BA1, DA0);
+                if (abc != abd) {
+                    const float DC0 = __fsub_rn(D0, C0), DC1 = __fsub_rn(D1, C1);
+                    const float CDDC = msub<FL>(C0, D1, D0, C1);
+                    const float DH = msub<FL>(BA1, DC0, BA0, DC1);
+                    const float Dx = msub<FL>(ABBA, DC0, BA0, CDDC);
+                    const float Dy = msub<FL>(ABBA, DC1, BA1, CDDC);
+                    pts[2 * n] = __fdiv_rn(Dx, DH), pts[2 * n + 1] = __fdiv_rn(Dy, DH);
+                    ++n;
+                }
+            }
+        }
+    }
+    if (n > 0) {  // sort_vertex_in_convex_polygon (rotate_iou.py:36-74)
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int i = 0; i < n; ++i) s0 = __fadd_rn(s0, pts[2 * i]), s1 = __fadd_rn(s1, pts[2 * i + 1]);
+        const double dn = (double)n;
+        const float m0 = __double2float_rn(__ddiv_rn((double)s0, dn)), m1 = __double2float_rn(__ddiv_rn((double)s1, dn));
+        for (int i = 0; i < n; ++i) {
+            float v0 = __fsub_rn(pts[2 * i], m0), v1 = __fsub_rn(pts[2 * i + 1], m1);
+            const float d = __fsqrt_rn(FL ? __fmaf_rn(v0, v0, __fmul_rn(v1, v1)) : __fadd_rn(__fmul_rn(v0, v0), __fmul_rn(v1, v1)));
+            v0 = __fdiv_rn(v0, d);
+            v1 = __fdiv_rn(v1, d);
+            if (v1 < 0.0f) v0 = __fsub_rn(-2.0f, v0);
+            vs[i] = v0;
+        }
+        for (int i = 1; i < n; ++i) {
+            if (vs[i - 1] > vs[i]) {
+                const float temp = vs[i], tx = pts[2 * i], ty = pts[2 * i + 1];
+                int j = i;
+                while (j > 0 && vs[j - 1] > temp) {
+                    vs[j] = vs[j - 1];
+                    pts[2 * j] = pts[2 * j - 2];
+                    pts[2 * j + 1] = pts[2 * j - 1];
+                    --j;
+                }
+                vs[j] = temp;
+                pts[2 * j] = tx;
+                pts[2 * j + 1] = ty;
+            }
+        }
+    }
+    double area = 0.0;  // area() / trangle_area() (rotate_iou.py:17-33): float cross product, halved / abs / summed in double
+    for (int i = 0; i < n - 2; ++i) {
+        const float a0 = pts[0], a1 = pts[1], b0 = pts[2 * i + 2], b1 = pts[2 * i + 3], c0 = pts[2 * i + 4], cc1 = pts[2 * i + 5];
+        float t;
+        if (FL)
+            t = __fmaf_rn(__fsub_rn(a0, c0), __fsub_rn(b1, cc1), -__fmul_rn(__fsub_rn(a1, cc1), __fsub_rn(b0, c0)));
+        else
+            t = __fsub_rn(__fmul_rn(__fsub_rn(a0, c0), __fsub_rn(b1, cc1)), __fmul_rn(__fsub_rn(a1, cc1), __fsub_rn(b0, c0)));
+        area = __dadd_rn(area, fabs(__dmul_rn((double)t, 0.5)));
+    }
+    return area;
+}
+
+// devRotateIoUEval (rotate_iou.py:246-258); area1 belongs to the FIRST argument (the query box)
+__device__ __forceinline__ float finish_bev(double ai, float area1, float area2, int criterion) {
+    double r;
+    if (criterion == -1)
+        r = __ddiv_rn(ai, __dsub_rn((double)__fadd_rn(area1, area2), ai));
+    else if (criterion == 0)
+        r = __ddiv_rn(ai, (double)area1);
+    else if (criterion == 1)
+        r = __ddiv_rn(ai, (double)area2);
+    else
+        r = ai;
+    return __double2float_rn(r);
+}
+
+// d3_box_overlap_kernel (eval.py:116-147) applied to rinc = float32(BEV intersection area); b = box, q = query box
+__device__ __forceinline__ float finish_d3(float rinc, const RecZ& b, const RecZ& q, int criterion) {
+    if (!(rinc > 0.0f)) return rinc;
+    const double iw = __dsub_rn(fmin(b.y, q.y), fmax(b.ybot, q.ybot));
+    if (!(iw > 0.0)) return 0.0f;
+    const double inc = __dmul_rn(iw, (double)rinc);
+    double ua;
+    if (criterion == -1)
+        ua = __dsub_rn(__dadd_rn(b.vol, q.vol), inc);
+    else if (criterion == 0)
+        ua = b.vol;
+    else if (criterion == 1)
+        ua = q.vol;
+    else
+        ua = inc;
+    return __double2float_rn(__ddiv_rn(inc, ua));
+}
+
+struct Parts {
+    const int64_t* box_off;  // [P + 1] or nullptr (single part)
+    const int64_t* q_off;
+    const int64_t* out_off;
+    int num_parts;
+    int64_t n, k;  // single part
+    int64_t total;
+};
+
+// element e of the concatenated outputs -> (box row, query row), both as global record indices
+__device__ __forceinline__ void locate(const Parts& P, int64_t e, int& hint, int64_t& bi, int64_t& qi) {
+    if (!P.box_off) {
+        bi = e / P.k;
+        qi = e - bi * P.k;
+        return;
+    }
+    int p = hint;
+    if (!(P.out_off[p] <= e && e < P.out_off[p + 1])) {
+        int lo = 0, hi = P.num_parts - 1;
+        while (lo < hi) {  // last part whose first element is <= e; empty parts have equal offsets and are skipped
+            const int mid = (lo + hi + 1) >> 1;
+            if (P.out_off[mid] <= e) lo = mid;
+            else hi = mid - 1;
+        }
+        p = lo;
+        hint = p;
+    }
+    const int64_t kp = P.q_off[p + 1] - P.q_off[p];
+    const int64_t r = e - P.out_off[p];
+    const int64_t i = r / kp;
+    bi = P.box_off[p] + i;
+    qi = P.q_off[p] + (r - i * kp);
+}
+
+template <int FL, int D3>
+__global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restrict__ rec_b, const Rec* __restrict__ rec_q,
+                                                             const RecZ* __restrict__ z_b, const RecZ* __restrict__ z_q, Parts P,
+                                                             int criterion, float* __restrict__ out) {
+    __shared__ int s_queue[CHUNK];
+    __shared__ int s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * CHUNK;
+    int hint = 0;
+#pragma unroll 2
+    for (int u = 0; u < PER_THREAD; ++u) {
+        const int loc = u * THREADS + threadIdx.x;
+        const int64_t e = base + loc;
+        if (e >= P.total) break;
+        int64_t bi, qi;
+        locate(P, e, hint, bi, qi);
+        const float4 fb = reinterpret_cast<const float4*>(rec_b + bi)[2];
+        const float4 fq = reinterpret_cast<const float4*>(rec_q + qi)[2];
+        // exact-zero test: centres further apart than the circum-radii plus a slack far above the rounding of the
+        // reference's predicates (a few ulp of the coordinates) => < 3 polygon points => area exactly 0.0
+        const float dx = fb.x - fq.x, dy = fb.y - fq.y;
+        const float d2 = dx * dx + dy * dy;
+        const float R = (fb.z + fq.z) * 1.01f + 1e-4f * (fabsf(fb.x) + fabsf(fb.y) + fabsf(fq.x) + fabsf(fq.y)) + 1e-6f;
+        if (d2 > R * R && d2 < 3.0e38f) {
+            out[e] = D3 ? 0.0f : finish_bev(0.0, fq.w, fb.w, criterion);
+        } else {
+            s_queue[atomicAdd(&s_count, 1)] = loc;
+        }
+    }
+    __syncthreads();
+    const int cnt = s_count;
+    for (int t = threadIdx.x; t < cnt; t += THREADS) {
+        const int64_t e = base + s_queue[t];
+        int64_t bi, qi;
+        locate(P, e, hint, bi, qi);
+        float cb[8], cq[8];
+        const float4* pb = reinterpret_cast<const float4*>(rec_b + bi);
+        const float4* pq = reinterpret_cast<const float4*>(rec_q + qi);
+        const float4 b0 = pb[0], b1 = pb[1], b2 = pb[2], q0 = pq[0], q1 = pq[1], q2 = pq[2];
+        cb[0] = b0.x, cb[1] = b0.y, cb[2] = b0.z, cb[3] = b0.w, cb[4] = b1.x, cb[5] = b1.y, cb[6] = b1.z, cb[7] = b1.w;
+        cq[0] = q0.x, cq[1] = q0.y, cq[2] = q0.z, cq[3] = q0.w, cq[4] = q1.x, cq[5] = q1.y, cq[6] = q1.z, cq[7] = q1.w;
+        const double ai = inter_area<FL>(cq, cb);  // the query box is the kernel's first argument (rotate_iou.py:289-291)
+        float r;
+        if (D3) r = finish_d3(__double2float_rn(ai), z_b[bi], z_q[qi], criterion);
+        else r = finish_bev(ai, q2.w, b2.w, criterion);
+        out[e] = r;
+    }
+}
+
+inline size_t ws_bytes(int64_t nb, int64_t nq) {
+    return align_up((size_t)nb * sizeof(Rec), 256) + align_up((size_t)nq * sizeof(Rec), 256) + align_up((size_t)nb * sizeof(RecZ), 256) +
+           align_up((size_t)nq * sizeof(RecZ), 256);
+}
+
+static int run(const float* b32, const float* q32, const double* b64, const double* q64, int64_t nb, int64_t nq, Parts P, int d3,
+               int criterion, float* out, void* ws, size_t wsb, unsigned flags, void* stream) {
+    if (!ws || wsb < ws_bytes(nb, nq)) {
+        set_error("workspace too small: need %zu bytes, got %zu", ws_bytes(nb, nq), wsb);
+        return LG_ERR_WORKSPACE;
+    }
+    if (P.total > (int64_t)CHUNK * 2147483647LL) {
+        set_error("%lld output elements exceed the grid limit; split the call", (long long)P.total);
+        return LG_ERR_TOO_LARGE;
+    }
+    char* w = static_cast<char*>(ws);
+    Rec* rb = reinterpret_cast<Rec*>(w);
+    w += align_up((size_t)nb * sizeof(Rec), 256);
+    Rec* rq = reinterpret_cast<Rec*>(w);
+    w += align_up((size_t)nq * sizeof(Rec), 256);
+    RecZ* zb = reinterpret_cast<RecZ*>(w);
+    w += align_up((size_t)nb * sizeof(RecZ), 256);
+    RecZ* zq = reinterpret_cast<RecZ*>(w);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool strict = flags & LG_FLAG_STRICT_FP32;
+    const unsigned gb = (unsigned)((nb + 255) / 256), gq = (unsigned)((nq + 255) / 256);
+    if (strict) {
+        kitti_prep_kernel<0><<<gb, 256, 0, st>>>(b32, b64, nb, rb, d3 ? zb : nullptr);
+        kitti_prep_kernel<0><<<gq, 256, 0, st>>>(q32, q64, nq, rq, d3 ? zq : nullptr);
+    } else {
+        kitti_prep_kernel<1><<<gb, 256, 0, st>>>(b32, b64, nb, rb, d3 ? zb : nullptr);
+        kitti_prep_kernel<1><<<gq, 256, 0, st>>>(q32, q64, nq, rq, d3 ? zq : nullptr);
+    }
+    int rc = check_launch("kitti_prep_kernel");
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((P.total + CHUNK - 1) / CHUNK);
+    if (strict) {
+        if (d3) kitti_pair_kernel<0, 1><<<grid, THREADS, 0, st>>>(rb, rq, zb, zq, P, criterion, out);
+        else kitti_pair_kernel<0, 0><<<grid, THREADS, 0, st>>>(rb, rq, zb, zq, P, criterion, out);
+    } else {
+        if (d3) kitti_pair_kernel<1, 1><<<grid, THREADS, 0, st>>>(rb, rq, zb, zq, P, criterion, out);
+        else kitti_pair_kernel<1, 0><<<grid, THREADS, 0, st>>>(rb, rq, zb, zq, P, criterion, out);
+    }
+    return check_launch("kitti_pair_kernel");
+}
+
+}  // namespace kitti
+}  // namespace lg
+
+extern "C" size_t lg_kitti_workspace_bytes(int64_t num_boxes, int64_t num_query_boxes) {
+    if (num_boxes < 0 || num_query_boxes < 0) return 0;
+    return lg::kitti::ws_bytes(num_boxes, num_query_boxes);
+}
+
+extern "C" int lg_rotate_iou_eval(const float* boxes, int64_t n, const float* query_boxes, int64_t k, float* out, int criterion,
+                                  void* ws, size_t ws_bytes, unsigned flags, void* stream) {
+    using namespace lg;
+    if (n < 0 || k < 0) {
+        set_error("negative size n=%lld k=%lld", (long long)n, (long long)k);
+        return LG_ERR_INVALID_ARG;
+    }
+    if (n == 0 || k == 0) return LG_OK;
+    if (!boxes || !query_boxes || !out) {
+        set_error("null pointer (boxes=%p query_boxes=%p out=%p)", (const void*)boxes, (const void*)query_boxes, (void*)out);
+        return LG_ERR_INVALID_ARG;
+    }
+    kitti::Parts P{nullptr, nullptr, nullptr, 1, n, k, n * k};
+    return kitti::run(boxes, query_boxes, nullptr, nullptr, n, k, P, 0, criterion, out, ws, ws_bytes, flags, stream);
+}
+
+extern "C" int lg_d3_box_overlap(const double* boxes, int64_t n, const double* qboxes, int64_t k, float* out, int criterion, void* ws,
+                                 size_t ws_bytes, unsigned flags, void* stream) {
+    using namespace lg;
+    if (n < 0 || k < 0) {
+        set_error("negative size n=%lld k=%lld", (long long)n, (long long)k);
+        return LG_ERR_INVALID_ARG;
+    }
+    if (n == 0 || k == 0) return LG_OK;
+    if (!boxes || !qboxes || !out) {
+        set_error("null pointer (boxes=%p qboxes=%p out=%p)", (const void*)boxes, (const void*)qboxes, (void*)out);
+        return LG_ERR_INVALID_ARG;
+    }
+    kitti::Parts P{nullptr, nullptr, nullptr, 1, n, k, n * k};
+    return kitti::run(nullptr, nullptr, boxes, qboxes, n, k, P, 1, criterion, out, ws, ws_bytes, flags, stream);
+}
+
+extern "C" int lg_kitti_overlaps_parts(const double* gt_boxes, int64_t num_gt, const double* dt_boxes, int64_t num_dt,
+                                       const int64_t* gt_off, const int64_t* dt_off, const int64_t* out_off, int num_parts,
+                                       int64_t num_out, int metric, int criterion, float* out, void* ws, size_t ws_bytes,
+                                       unsigned flags, void* stream) {
+    using namespace lg;
+    if (num_gt < 0 || num_dt < 0 || num_parts < 0 || num_out < 0) {
+        set_error("negative size (num_gt=%lld num_dt=%lld num_parts=%d num_out=%lld)", (long long)num_gt, (long long)num_dt, num_parts,
+                  (long long)num_out);
+        return LG_ERR_INVALID_ARG;
+    }
+    if (metric != 1 && metric != 2) {
+        set_error("metric must be 1 (bev) or 2 (3d), got %d (metric 0, image boxes, has no rotated overlap)", metric);
+        return LG_ERR_INVALID_ARG;
+    }
+    if (num_parts == 0 || num_out == 0) return LG_OK;
+    if (!gt_boxes || !dt_boxes || !gt_off || !dt_off || !out_off || !out) {
+        set_error("null pointer");
+        return LG_ERR_INVALID_ARG;
+    }
+    kitti::Parts P{gt_off, dt_off, out_off, num_parts, 0, 0, num_out};
+    return kitti::run(nullptr, nullptr, gt_boxes, dt_boxes, num_gt, num_dt, P, metric == 2, criterion, out, ws, ws_bytes, flags, stream);
+}

@@ -178,3 +178,50 @@ def pool_case(n_points=16384, n_rois=128, channels=128, seed=SEEDS["cfg3"] + 7):
     pts, rois = cfg3(1, n_points, n_rois, seed)
     feat = _rng(seed + 1).standard_normal((n_points, channels)).astype(np.float32)
     return pts[0], rois[0], feat
+
+
+def kitti_eval_frames(n_frames, seed, gt_range=(2, 12), fp_range=(2, 14)):
+    """KITTI-evaluation shaped annotations in CAMERA coordinates (kitti_object_eval_python/eval.py:340-414 consumes them):
+    per frame float64 boxes (x, y, z, l, h, w, rotation_y) with x right, y down (bottom face), z forward.
+    Ground truth is rounded to 2 decimals (label_2 text files), detections to 4 (the reference's result writer);
+    detections = jittered ground truth (90 % recall) + false positives.  Returns (list of gt (G_f,7), list of dt (D_f,7))."""
+    r = _rng(seed)
+    pri = KITTI_PRIORS.astype(np.float64)  # (l, w, h) lidar order
+    gts, dts = [], []
+    for _ in range(n_frames):
+        g = int(r.integers(gt_range[0], gt_range[1] + 1))
+        cls = r.choice(3, size=g, p=KITTI_PRIOR_P)
+        dims = pri[cls] * (1.0 + 0.1 * r.standard_normal((g, 3)))
+        dims = np.maximum(dims, 0.3)
+        gt = np.empty((g, 7))
+        gt[:, 0] = r.uniform(-35.0, 35.0, g)
+        gt[:, 1] = r.normal(1.65, 0.25, g)
+        gt[:, 2] = r.uniform(3.0, 68.0, g)
+        gt[:, 3] = dims[:, 0]
+        gt[:, 4] = dims[:, 2]
+        gt[:, 5] = dims[:, 1]
+        gt[:, 6] = r.uniform(-np.pi, np.pi, g)
+        gt = np.round(gt, 2)
+        hit = gt[r.random(g) < 0.9]
+        det = hit.copy()
+        n = len(det)
+        det[:, 0] += r.normal(0, 0.15, n)
+        det[:, 1] += r.normal(0, 0.05, n)
+        det[:, 2] += r.normal(0, 0.15, n)
+        det[:, 3:6] *= 1.0 + 0.05 * r.standard_normal((n, 3))
+        det[:, 6] += r.normal(0, 0.08, n)
+        f = int(r.integers(fp_range[0], fp_range[1] + 1))
+        cls = r.choice(3, size=f, p=KITTI_PRIOR_P)
+        fdim = pri[cls] * (1.0 + 0.1 * r.standard_normal((f, 3)))
+        fp = np.empty((f, 7))
+        fp[:, 0] = r.uniform(-35.0, 35.0, f)
+        fp[:, 1] = r.normal(1.65, 0.25, f)
+        fp[:, 2] = r.uniform(3.0, 68.0, f)
+        fp[:, 3] = fdim[:, 0]
+        fp[:, 4] = fdim[:, 2]
+        fp[:, 5] = fdim[:, 1]
+        fp[:, 6] = r.uniform(-np.pi, np.pi, f)
+        dt = np.round(np.concatenate([det, fp], 0), 4)
+        gts.append(gt)
+        dts.append(dt[r.permutation(len(dt))])
+    return gts, dts

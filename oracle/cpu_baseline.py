@@ -74,6 +74,14 @@ def _roiaware_frame(args):
     return float(a.sum()) + float(b.sum())
 
 
+def _kitti_part(args):
+    g, d = args  # float64 camera boxes of one evaluation part: BEV overlap + 3-D overlap, as eval.py:370-393 computes them
+    o = _STATE["orc"]
+    a = o.bev_box_overlap(g[:, [0, 2, 3, 5, 6]], d[:, [0, 2, 3, 5, 6]], -1, 0)
+    b = o.d3_box_overlap(g, d, -1, 0)
+    return float(a.sum()) + float(b.sum())
+
+
 def _roipoint_frame(args):
     pts, boxes, feat, s = args
     return float(_STATE["orc"].roipoint_pool3d_forward(pts[None], feat[None], boxes[None], s)[0].sum())
@@ -147,6 +155,12 @@ class CpuPool:
         """Part-A2 RoI-aware pooling (avg + max call) per frame; the reference has no CPU build of it: always the port"""
         t0 = time.perf_counter()
         self._map(_roiaware_frame, frames)
+        return time.perf_counter() - t0
+
+    def kitti_parts(self, parts):
+        """KITTI-eval overlaps (bev + 3d) of evaluation parts; the reference's kernel is numba.cuda only: always the port"""
+        t0 = time.perf_counter()
+        self._map(_kitti_part, parts)
         return time.perf_counter() - t0
 
     def roipoint_frames(self, frames):

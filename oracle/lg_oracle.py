@@ -55,6 +55,15 @@ def lib():
         L.lgo_roiaware_pool3d_backward.argtypes = [ip, ip, fp, fp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int]
         L.lgo_roipoint_pool3d_forward.restype = None
         L.lgo_roipoint_pool3d_forward.argtypes = [fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, ip, C.c_int]
+        dp = C.POINTER(C.c_double)
+        L.lgo_rotate_iou_eval_pair.restype = C.c_float
+        L.lgo_rotate_iou_eval_pair.argtypes = [fp, fp, C.c_int, C.c_int]
+        L.lgo_rotate_iou_eval_cnt.restype = C.c_int
+        L.lgo_rotate_iou_eval_cnt.argtypes = [fp, fp, C.c_int]
+        L.lgo_rotate_iou_eval.restype = None
+        L.lgo_rotate_iou_eval.argtypes = [fp, C.c_int64, fp, C.c_int64, fp, C.c_int, C.c_int]
+        L.lgo_d3_box_overlap.restype = None
+        L.lgo_d3_box_overlap.argtypes = [dp, C.c_int64, dp, C.c_int64, fp, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -218,3 +227,37 @@ def roipoint_pool3d_forward(points, point_features, boxes3d, num_sampled_points=
         lib().lgo_roipoint_pool3d_forward(_p(xyz, C.c_float), _p(bx, C.c_float), _p(feat, C.c_float), B, n, m, c,
                                           num_sampled_points, _p(pooled, C.c_float), _p(flag, C.c_int32), flavor)
     return pooled, flag
+
+
+# ---- "next" row 8f-2: KITTI-eval rotated IoU (kitti_object_eval_python/rotate_iou.py, eval.py:111-155) ----
+def rotate_iou_eval(boxes, query_boxes, criterion=-1, flavor=FLAVOR_CUDA):
+    """(N,5), (K,5) -> (N,K) float32; iou[n,k] = devRotateIoUEval(query_boxes[k], boxes[n], criterion)"""
+    b, q = _f32(np.asarray(boxes).reshape(-1, 5), 5), _f32(np.asarray(query_boxes).reshape(-1, 5), 5)
+    out = np.zeros((b.shape[0], q.shape[0]), np.float32)
+    if out.size:
+        lib().lgo_rotate_iou_eval(_p(b, C.c_float), b.shape[0], _p(q, C.c_float), q.shape[0], _p(out, C.c_float), int(criterion), flavor)
+    return out
+
+
+def rotate_iou_eval_cnt(boxes, query_boxes, flavor=FLAVOR_CUDA):
+    """number of polygon points the reference collects per pair ((N,K) int32); > 8 overflows the reference's buffer"""
+    b, q = _f32(np.asarray(boxes).reshape(-1, 5), 5), _f32(np.asarray(query_boxes).reshape(-1, 5), 5)
+    out = np.zeros((b.shape[0], q.shape[0]), np.int32)
+    for i in range(b.shape[0]):
+        for j in range(q.shape[0]):
+            out[i, j] = lib().lgo_rotate_iou_eval_cnt(_p(q[j], C.c_float), _p(b[i], C.c_float), flavor)
+    return out
+
+
+def d3_box_overlap(boxes, qboxes, criterion=-1, flavor=FLAVOR_CUDA):
+    """float64 camera boxes (N,7), (K,7) -> (N,K) float32 (eval.py:150-155)"""
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 7))
+    q = np.ascontiguousarray(np.asarray(qboxes, dtype=np.float64).reshape(-1, 7))
+    out = np.zeros((b.shape[0], q.shape[0]), np.float32)
+    if out.size:
+        lib().lgo_d3_box_overlap(_p(b, C.c_double), b.shape[0], _p(q, C.c_double), q.shape[0], _p(out, C.c_float), int(criterion), flavor)
+    return out
+
+
+def bev_box_overlap(boxes, qboxes, criterion=-1, flavor=FLAVOR_CUDA):
+    return rotate_iou_eval(boxes, qboxes, criterion, flavor)

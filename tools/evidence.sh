@@ -13,7 +13,7 @@ if [ "$WHAT" != ncu ]; then
 timeout 600 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 timeout 600 python tools/gpu_check.py > $O/gpu_check.log 2>&1; echo "gpu_check rc=$?"
 : > $O/bench_lines.jsonl
-for w in nms_cfg2 nms_cfg5 iou_dense iou_cfg1 iou_cfg4 pib_cfg3 post_cfg2 iou_max_cfg4 roiaware_partA2 roipoint_pointrcnn; do
+for w in nms_cfg2 nms_cfg5 iou_dense iou_cfg1 iou_cfg4 pib_cfg3 post_cfg2 iou_max_cfg4 roiaware_partA2 roipoint_pointrcnn kitti_eval; do
     timeout 300 python bench.py --workload $w 2> $O/bench_$w.err | tail -1 >> $O/bench_lines.jsonl; echo "bench $w rc=$?"
 done
 timeout 400 python bench.py --impl reference 2> $O/bench_reference.err | tail -1 >> $O/bench_lines.jsonl; echo "bench reference rc=$?"
