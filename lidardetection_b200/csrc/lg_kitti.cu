@@ -290,13 +290,36 @@ __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restri
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * CHUNK;
     int hint = 0;
+    // walk this thread's elements base + tid, + THREADS, ... keeping (part, row, column) incrementally: one search and one
+    // 64-bit division per thread instead of one per element
+    int part = 0;
+    int64_t row0 = 0, col0 = 0, nrows = P.n, ncols = P.k, i = 0, j = 0;
+    {
+        const int64_t e = base + threadIdx.x;
+        if (e < P.total) {
+            if (P.box_off) {
+                int lo = 0, hi = P.num_parts - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (P.out_off[mid] <= e) lo = mid;
+                    else hi = mid - 1;
+                }
+                part = lo;
+                row0 = P.box_off[part], col0 = P.q_off[part];
+                nrows = P.box_off[part + 1] - row0, ncols = P.q_off[part + 1] - col0;
+                const int64_t r = e - P.out_off[part];
+                i = r / ncols, j = r - i * ncols;
+            } else {
+                i = e / ncols, j = e - i * ncols;
+            }
+        }
+    }
 #pragma unroll 2
     for (int u = 0; u < PER_THREAD; ++u) {
         const int loc = u * THREADS + threadIdx.x;
         const int64_t e = base + loc;
         if (e >= P.total) break;
-        int64_t bi, qi;
-        locate(P, e, hint, bi, qi);
+        const int64_t bi = row0 + i, qi = col0 + j;
         const float4 fb = reinterpret_cast<const float4*>(rec_b + bi)[2];
         const float4 fq = reinterpret_cast<const float4*>(rec_q + qi)[2];
         // exact-zero test: centres further apart than the circum-radii plus a slack far above the rounding of the
@@ -308,6 +331,20 @@ __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restri
             out[e] = D3 ? 0.0f : finish_bev(0.0, fq.w, fb.w, criterion);
         } else {
             s_queue[atomicAdd(&s_count, 1)] = loc;
+        }
+        // advance by THREADS elements
+        j += THREADS;
+        while (j >= ncols) {
+            j -= ncols;
+            if (++i >= nrows) {  // next non-empty part (the last element is guarded by e >= total above)
+                if (!P.box_off || e + THREADS >= P.total) break;
+                do {
+                    ++part;
+                    row0 = P.box_off[part], col0 = P.q_off[part];
+                    nrows = P.box_off[part + 1] - row0, ncols = P.q_off[part + 1] - col0;
+                } while (nrows == 0 || ncols == 0);
+                i = 0;
+            }
         }
     }
     __syncthreads();
