@@ -44,6 +44,28 @@ elif op == "pib":
     tp, tr = cu(p), cu(r)
     for _ in range(iters):
         PU.points_in_boxes_gpu(tp, tr)
+elif op == "pib4096":  # the bench's shape: one CTA per frame
+    import numpy as np
+
+    p, r = synth.cfg3(64)
+    tp, tr = cu(np.tile(p, (64, 1, 1))), cu(np.tile(r, (64, 1, 1)))
+    for _ in range(iters):
+        PU.points_in_boxes_gpu(tp, tr)
+elif op == "kitti":
+    import numpy as np
+
+    from lidardetection_b200.datasets.kitti.kitti_object_eval_python import eval as E
+
+    gts, dts = synth.kitti_eval_frames(3769, 5000)
+    parts = E.get_split_parts(3769, 50)
+    gc, dc, i = [], [], 0
+    for n in parts:
+        gc.append(sum(len(x) for x in gts[i:i + n]))
+        dc.append(sum(len(x) for x in dts[i:i + n]))
+        i += n
+    g, d = cu(np.concatenate(gts)), cu(np.concatenate(dts))
+    for _ in range(iters):
+        E.kitti_overlaps_parts_cuda(g, d, gc, dc, 2)
 elif op in ("roiaware", "roipoint"):
     from lidardetection_b200.ops.roipoint_pool3d import roipoint_pool3d_utils as RU
 
