@@ -100,6 +100,20 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)", 1965.0
 
 
+def ncu_traffic(workload):
+    """DRAM bytes (read + write) per launch of the workload's dominant kernel, from the committed `ncu --set full` capture at
+    the bench shape (profiles/r01_ncu_traffic.json, written by tools/make_profiles.py --traffic); None when there is none."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None, None
+    if not rec:
+        return None, None
+    return rec["dram_bytes_read"] + rec["dram_bytes_write"], f"{rec['kernel']}: dram__bytes_read.sum + dram__bytes_write.sum, {rec['how']} ({rec['report']})"
+
+
 def fp32_peak_tflops(torch):
     """unrolled-FFMA microbenchmark (tools/peak_fp32.cu): measured non-tensor FP32 peak of this GPU"""
     import ctypes as C
@@ -963,6 +977,10 @@ def main():
     dev_ms, e2e_s = float(tt[0]), float(tt[1])
 
     roofline = wl.roofline(args.steps, hbm_peak, hbm_src, fp32_peak) if rank == 0 else None
+    if roofline is not None:
+        tr, src = ncu_traffic(args.workload)
+        if tr is not None:
+            roofline["traffic"], roofline["traffic_source"] = tr, src
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

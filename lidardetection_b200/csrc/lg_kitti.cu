@@ -15,7 +15,7 @@
 // those.
 //
 // Structure: a prep kernel turns every box into a 48-byte record (rotated corners, centre, circum-radius, area) -- the
-// reference recomputes sin/cos and the corners for every PAIR.  The pair kernel works on chunks of 2048 consecutive
+// reference recomputes sin/cos and the corners for every PAIR.  The pair kernel works on chunks of 8192 consecutive
 // output elements per 256-thread CTA: phase 1 puts every pair to an exact-zero test (circum-circles apart by a slack
 // that dwarfs any rounding of the reference's predicates => the reference collects < 3 polygon points => its area is
 // exactly 0.0) and stores those results coalesced; the survivors (~0.5 % of a KITTI part) are queued in shared memory
@@ -27,7 +27,7 @@ namespace lg {
 namespace kitti {
 
 constexpr int THREADS = 256;
-constexpr int PER_THREAD = 8;
+constexpr int PER_THREAD = 32;  // 8192 pairs per CTA: ~40 queue entries at KITTI density, so phase 2 runs on (nearly) full warps
 constexpr int CHUNK = THREADS * PER_THREAD;
 constexpr int MAXPTS = 24;  // 8 corners + 16 crossings; the reference's buffer holds 8 (undefined beyond, see oracle)
 
@@ -228,6 +228,21 @@ __device__ __forceinline__ float finish_bev(double ai, float area1, float area2,
     return __double2float_rn(r);
 }
 
+// finish_bev(0.0, ...) without the double division: 0.0 / x is +0 for x > 0, -0 for x < 0 and NaN for x == 0 or NaN
+// (float -> double is exact, so the sign test on the float operand decides the same way)
+__device__ __forceinline__ float zero_bev(float area1, float area2, int criterion) {
+    float x;
+    if (criterion == -1)
+        x = __fadd_rn(area1, area2);
+    else if (criterion == 0)
+        x = area1;
+    else if (criterion == 1)
+        x = area2;
+    else
+        return 0.0f;
+    return x > 0.0f ? 0.0f : (x < 0.0f ? -0.0f : __int_as_float(0x7fffffff));
+}
+
 // d3_box_overlap_kernel (eval.py:116-147) applied to rinc = float32(BEV intersection area); b = box, q = query box
 __device__ __forceinline__ float finish_d3(float rinc, const RecZ& b, const RecZ& q, int criterion) {
     if (!(rinc > 0.0f)) return rinc;
@@ -284,7 +299,7 @@ template <int FL, int D3>
 __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restrict__ rec_b, const Rec* __restrict__ rec_q,
                                                              const RecZ* __restrict__ z_b, const RecZ* __restrict__ z_q, Parts P,
                                                              int criterion, float* __restrict__ out) {
-    __shared__ int s_queue[CHUNK];
+    __shared__ uint16_t s_queue[CHUNK];
     __shared__ int s_count;
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
@@ -328,9 +343,9 @@ __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restri
         const float d2 = dx * dx + dy * dy;
         const float R = (fb.z + fq.z) * 1.01f + 1e-4f * (fabsf(fb.x) + fabsf(fb.y) + fabsf(fq.x) + fabsf(fq.y)) + 1e-6f;
         if (d2 > R * R && d2 < 3.0e38f) {
-            out[e] = D3 ? 0.0f : finish_bev(0.0, fq.w, fb.w, criterion);
+            out[e] = D3 ? 0.0f : zero_bev(fq.w, fb.w, criterion);
         } else {
-            s_queue[atomicAdd(&s_count, 1)] = loc;
+            s_queue[atomicAdd(&s_count, 1)] = (uint16_t)loc;
         }
         // advance by THREADS elements
         j += THREADS;
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restri
     __syncthreads();
     const int cnt = s_count;
     for (int t = threadIdx.x; t < cnt; t += THREADS) {
-        const int64_t e = base + s_queue[t];
+        const int64_t e = base + (int)s_queue[t];
         int64_t bi, qi;
         locate(P, e, hint, bi, qi);
         float cb[8], cq[8];

@@ -4,7 +4,7 @@
 # report per dominant kernel (each only after the same command has exited 0 without ncu).  Everything lands in
 # gpurun_out/; tools/make_profiles.py turns the reports into profiles/rNN_*.txt afterwards.
 #   gpurun --timeout 1500 -- 'bash tools/evidence.sh [run|ncu|all]'
-# gpurun brings back at most 64 MiB: every ncu capture is limited to its kernel (-k) and two launches (-c).
+# gpurun brings back at most 64 MiB: every ncu capture is limited to its kernel (-k) and one launch (-c).
 set -u
 O=gpurun_out
 mkdir -p $O
@@ -12,6 +12,7 @@ WHAT=${1:-all}
 if [ "$WHAT" != ncu ]; then
 timeout 600 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 timeout 600 python tools/gpu_check.py > $O/gpu_check.log 2>&1; echo "gpu_check rc=$?"
+timeout 300 python tools/kitti_check.py > $O/kitti_check.log 2>&1; echo "kitti_check rc=$?"
 : > $O/bench_lines.jsonl
 for w in nms_cfg2 nms_cfg5 iou_dense iou_cfg1 iou_cfg4 pib_cfg3 post_cfg2 iou_max_cfg4 roiaware_partA2 roipoint_pointrcnn kitti_eval; do
     timeout 300 python bench.py --workload $w 2> $O/bench_$w.err | tail -1 >> $O/bench_lines.jsonl; echo "bench $w rc=$?"
@@ -23,10 +24,10 @@ if timeout 200 python bench.py --steps 2 --warmup 1 > $O/plain_bench.log 2>&1; t
 fi
 fi
 if [ "$WHAT" != run ]; then
-for tk in nms64:nms_lazy_kernel nms_full:nms_mask_kernel iou_dense:iou_strip_kernel iou_sparse:iou_strip_kernel pib:pib_grid_kernel; do
+for tk in nms64:nms_lazy_kernel nms_cfg5:nms_lazy_kernel nms_full:nms_mask_kernel iou_dense16k:iou_strip_kernel iou_cfg4:iou_strip_kernel iou_cfg1:iou_flat_kernel pib4096:pib_grid_kernel kitti:kitti_pair_kernel roiaware:roiaware_collect_kernel roipoint:roipoint_pool_kernel; do
     t=${tk%%:*}; k=${tk##*:}
     if timeout 120 python tools/prof_target.py $t 3 > $O/plain_$t.log 2>&1; then
-        timeout 500 ncu --set full --clock-control none --import-source on -k regex:$k -c 2 -f -o $O/final_$t \
+        timeout 500 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o $O/final_$t \
             python tools/prof_target.py $t 2 > $O/ncu_$t.log 2>&1; echo "ncu $t rc=$?"
     else
         echo "plain $t failed"

@@ -43,7 +43,35 @@ def raw_metrics(rep, kernel):
     raise SystemExit(f"{kernel} not in {rep}")
 
 
+def traffic(tag, specs):
+    """profiles/<tag>_ncu_traffic.json: DRAM bytes per launch of the dominant kernel at the BENCH shape of each workload
+    (bench.py copies them into roofline.traffic).  specs: workload=<report.ncu-rep>:<kernel substring>"""
+    import json
+
+    out = {}
+    for spec in specs:
+        wl, rest = spec.split("=", 1)
+        rep, kernel = rest.split(":")[:2]
+        met, kname = raw_metrics(rep, kernel)
+        d = {k: v for k, v, _ in met}
+        units = {k: u for k, _, u in met}
+
+        def to_bytes(key):
+            v, u = float(d[key].replace(",", "")), units[key].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}[u]
+
+        out[wl] = {"kernel": kname.split("(")[0], "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
+                   "duration_us_under_ncu": float(d["gpu__time_duration.sum"].replace(",", "")) * {"us": 1, "usecond": 1, "ns": 1e-3, "nsecond": 1e-3, "ms": 1e3, "msecond": 1e3}.get(units["gpu__time_duration.sum"], 1),
+                   "report": os.path.basename(rep), "how": "ncu --set full --clock-control none, one launch at the bench shape (tools/prof_target.py)"}
+    path = os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", path)
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[2], sys.argv[3:])
     tag = sys.argv[1]
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     for spec in sys.argv[2:]:

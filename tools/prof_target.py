@@ -39,6 +39,27 @@ elif op == "iou_sparse":
     ta, tb = cu(a), cu(b)
     for _ in range(iters):
         U.boxes_iou3d_gpu(ta, tb)
+elif op == "iou_dense16k":  # bench shape of iou_dense
+    a, b = synth.dense_overlap(16384, 16384)
+    ta, tb = cu(a), cu(b)
+    for _ in range(iters):
+        U.boxes_iou_bev(ta, tb)
+elif op == "iou_cfg4":  # bench shape: one 25,000-row shard x 200,000 boxes, fused 3-D IoU (20 GB of output)
+    a, b = synth.cfg4(200_000)
+    ta, tb = cu(a[:25000]), cu(b)
+    for _ in range(iters):
+        out = U.boxes_iou3d_gpu(ta, tb)
+        del out
+elif op == "iou_cfg1":
+    a, b = synth.cfg1()
+    ta, tb = cu(a), cu(b)
+    for _ in range(iters):
+        U.boxes_iou_bev(ta, tb)
+elif op == "nms_cfg5":
+    b, s = synth.cfg5(256, 10, 1000)
+    tb, ts = cu(b.reshape(-1, 1000, 7)), cu(s.reshape(-1, 1000))
+    for _ in range(iters):
+        U.nms_gpu_batched(tb, ts, 0.2)
 elif op == "pib":
     p, r = synth.cfg3(256)
     tp, tr = cu(p), cu(r)
