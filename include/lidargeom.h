@@ -210,9 +210,9 @@ LG_API int lg_roipoint_pool3d_forward(const float *xyz, const float *boxes3d, co
  *                              int64 DEVICE arrays of row offsets and of output offsets (out_off[p + 1] - out_off[p] =
  *                              rows_gt(p) * rows_dt(p)); part p's matrix is out[out_off[p] ..) row-major (gt x dt).
  *                              metric 1 = bev (bev_box_overlap of columns [0,2,3,5,6]), 2 = 3d (d3_box_overlap).
- * ws must hold lg_kitti_workspace_bytes(rows of boxes, rows of query boxes) bytes.
+ * ws must hold lg_kitti_workspace_bytes(rows of boxes, rows of query boxes, num_parts (0 for the single-problem calls)) bytes.
  */
-LG_API size_t lg_kitti_workspace_bytes(int64_t num_boxes, int64_t num_query_boxes);
+LG_API size_t lg_kitti_workspace_bytes(int64_t num_boxes, int64_t num_query_boxes, int num_parts);
 LG_API int lg_rotate_iou_eval(const float *boxes, int64_t n, const float *query_boxes, int64_t k, float *out, int criterion, void *ws,
                               size_t ws_bytes, unsigned flags, void *stream);
 LG_API int lg_d3_box_overlap(const double *boxes, int64_t n, const double *qboxes, int64_t k, float *out, int criterion, void *ws,

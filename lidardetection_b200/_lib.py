@@ -72,7 +72,7 @@ def lib():
     L.lg_roipoint_pool3d_forward.restype = C.c_int
     L.lg_roipoint_pool3d_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, u32, vp]
     L.lg_kitti_workspace_bytes.restype = sz
-    L.lg_kitti_workspace_bytes.argtypes = [i64, i64]
+    L.lg_kitti_workspace_bytes.argtypes = [i64, i64, i32]
     L.lg_rotate_iou_eval.restype = C.c_int
     L.lg_rotate_iou_eval.argtypes = [vp, i64, vp, i64, vp, i32, vp, sz, u32, vp]
     L.lg_d3_box_overlap.restype = C.c_int

@@ -15,20 +15,20 @@
 // those.
 //
 // Structure: a prep kernel turns every box into a 48-byte record (rotated corners, centre, circum-radius, area) -- the
-// reference recomputes sin/cos and the corners for every PAIR.  The pair kernel works on chunks of 8192 consecutive
-// output elements per 256-thread CTA: phase 1 puts every pair to an exact-zero test (circum-circles apart by a slack
+// reference recomputes sin/cos and the corners for every PAIR.  The pair kernel gives every 256-thread CTA one 32-row x
+// 256-column tile of one part's matrix (column constants in registers, row constants broadcast from shared memory,
+// stores coalesced along the columns): phase 1 puts every pair to an exact-zero test (circum-circles apart by a slack
 // that dwarfs any rounding of the reference's predicates => the reference collects < 3 polygon points => its area is
-// exactly 0.0) and stores those results coalesced; the survivors (~0.5 % of a KITTI part) are queued in shared memory
-// and phase 2 runs the polygon path on the queue with full warps.  Several evaluation "parts" (independent N_p x K_p
-// problems, eval.py:356-395) are laid end to end in one launch.
+// exactly 0.0) and stores those results; the survivors (~0.5 % of a KITTI part, ~40 of a tile's 8192 pairs) are queued
+// in shared memory and phase 2 runs the polygon path on the queue.  Several evaluation "parts" (independent N_p x K_p
+// problems, eval.py:356-395) go into one launch: a one-CTA kernel scans the parts' tile counts, the pair kernel's CTAs
+// find their part by binary search over that prefix.
 #include "lg_common.cuh"
 
 namespace lg {
 namespace kitti {
 
 constexpr int THREADS = 256;
-constexpr int PER_THREAD = 32;  // 8192 pairs per CTA: ~40 queue entries at KITTI density, so phase 2 runs on (nearly) full warps
-constexpr int CHUNK = THREADS * PER_THREAD;
 constexpr int MAXPTS = 24;  // 8 corners + 16 crossings; the reference's buffer holds 8 (undefined beyond, see oracle)
 
 struct Rec {        // 48 bytes
@@ -265,109 +265,100 @@ struct Parts {
     const int64_t* box_off;  // [P + 1] or nullptr (single part)
     const int64_t* q_off;
     const int64_t* out_off;
+    const int64_t* tile_prefix;  // [P + 1], written by kitti_tiles_kernel (parts only)
     int num_parts;
     int64_t n, k;  // single part
-    int64_t total;
 };
 
-// element e of the concatenated outputs -> (box row, query row), both as global record indices
-__device__ __forceinline__ void locate(const Parts& P, int64_t e, int& hint, int64_t& bi, int64_t& qi) {
-    if (!P.box_off) {
-        bi = e / P.k;
-        qi = e - bi * P.k;
-        return;
-    }
-    int p = hint;
-    if (!(P.out_off[p] <= e && e < P.out_off[p + 1])) {
-        int lo = 0, hi = P.num_parts - 1;
-        while (lo < hi) {  // last part whose first element is <= e; empty parts have equal offsets and are skipped
-            const int mid = (lo + hi + 1) >> 1;
-            if (P.out_off[mid] <= e) lo = mid;
-            else hi = mid - 1;
+constexpr int TR = 32;        // rows (boxes) per tile
+constexpr int TC = THREADS;   // columns (query boxes) per tile: one per thread
+
+__host__ __device__ inline int64_t tiles_of(int64_t n, int64_t k) { return ((n + TR - 1) / TR) * ((k + TC - 1) / TC); }
+
+// exclusive prefix of the parts' tile counts (one CTA; parts are few: 51 for a KITTI val evaluation)
+__global__ void __launch_bounds__(256) kitti_tiles_kernel(const int64_t* __restrict__ box_off, const int64_t* __restrict__ q_off,
+                                                          int num_parts, int64_t* __restrict__ tile_prefix) {
+    __shared__ int64_t s_scan[256];
+    __shared__ int64_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < num_parts; p0 += 256) {
+        const int p = p0 + threadIdx.x;
+        const int64_t t = p < num_parts ? tiles_of(box_off[p + 1] - box_off[p], q_off[p + 1] - q_off[p]) : 0;
+        s_scan[threadIdx.x] = t;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            const int64_t v = threadIdx.x >= d ? s_scan[threadIdx.x - d] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
         }
-        p = lo;
-        hint = p;
+        if (p < num_parts) tile_prefix[p] = s_carry + s_scan[threadIdx.x] - t;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry += s_scan[255];
+        __syncthreads();
     }
-    const int64_t kp = P.q_off[p + 1] - P.q_off[p];
-    const int64_t r = e - P.out_off[p];
-    const int64_t i = r / kp;
-    bi = P.box_off[p] + i;
-    qi = P.q_off[p] + (r - i * kp);
+    if (threadIdx.x == 0) tile_prefix[num_parts] = s_carry;
 }
 
+// One CTA = one 32-row x 256-column tile of one part's matrix: the thread keeps its column's constants in registers, the
+// rows' constants are broadcast from shared memory, stores are coalesced along the columns.
 template <int FL, int D3>
 __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restrict__ rec_b, const Rec* __restrict__ rec_q,
                                                              const RecZ* __restrict__ z_b, const RecZ* __restrict__ z_q, Parts P,
                                                              int criterion, float* __restrict__ out) {
-    __shared__ uint16_t s_queue[CHUNK];
+    __shared__ float4 s_row[TR];  // cx, cy, 1.01 r + 1e-4 (|cx| + |cy|), area
+    __shared__ uint16_t s_queue[TR * TC];
     __shared__ int s_count;
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * CHUNK;
-    int hint = 0;
-    // walk this thread's elements base + tid, + THREADS, ... keeping (part, row, column) incrementally: one search and one
-    // 64-bit division per thread instead of one per element
-    int part = 0;
-    int64_t row0 = 0, col0 = 0, nrows = P.n, ncols = P.k, i = 0, j = 0;
-    {
-        const int64_t e = base + threadIdx.x;
-        if (e < P.total) {
-            if (P.box_off) {
-                int lo = 0, hi = P.num_parts - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (P.out_off[mid] <= e) lo = mid;
-                    else hi = mid - 1;
-                }
-                part = lo;
-                row0 = P.box_off[part], col0 = P.q_off[part];
-                nrows = P.box_off[part + 1] - row0, ncols = P.q_off[part + 1] - col0;
-                const int64_t r = e - P.out_off[part];
-                i = r / ncols, j = r - i * ncols;
-            } else {
-                i = e / ncols, j = e - i * ncols;
-            }
+    int64_t row0 = 0, col0 = 0, nrows = P.n, ncols = P.k, obase = 0, lt = blockIdx.x;
+    if (P.box_off) {
+        if ((int64_t)blockIdx.x >= P.tile_prefix[P.num_parts]) return;  // the grid is an upper bound
+        int lo = 0, hi = P.num_parts - 1;
+        while (lo < hi) {  // last part whose first tile is <= blockIdx.x; parts without tiles have equal prefixes and are skipped
+            const int mid = (lo + hi + 1) >> 1;
+            if (P.tile_prefix[mid] <= (int64_t)blockIdx.x) lo = mid;
+            else hi = mid - 1;
         }
+        row0 = P.box_off[lo], col0 = P.q_off[lo];
+        nrows = P.box_off[lo + 1] - row0, ncols = P.q_off[lo + 1] - col0;
+        obase = P.out_off[lo];
+        lt = (int64_t)blockIdx.x - P.tile_prefix[lo];
     }
-#pragma unroll 2
-    for (int u = 0; u < PER_THREAD; ++u) {
-        const int loc = u * THREADS + threadIdx.x;
-        const int64_t e = base + loc;
-        if (e >= P.total) break;
-        const int64_t bi = row0 + i, qi = col0 + j;
-        const float4 fb = reinterpret_cast<const float4*>(rec_b + bi)[2];
-        const float4 fq = reinterpret_cast<const float4*>(rec_q + qi)[2];
-        // exact-zero test: centres further apart than the circum-radii plus a slack far above the rounding of the
-        // reference's predicates (a few ulp of the coordinates) => < 3 polygon points => area exactly 0.0
-        const float dx = fb.x - fq.x, dy = fb.y - fq.y;
-        const float d2 = dx * dx + dy * dy;
-        const float R = (fb.z + fq.z) * 1.01f + 1e-4f * (fabsf(fb.x) + fabsf(fb.y) + fabsf(fq.x) + fabsf(fq.y)) + 1e-6f;
-        if (d2 > R * R && d2 < 3.0e38f) {
-            out[e] = D3 ? 0.0f : zero_bev(fq.w, fb.w, criterion);
-        } else {
-            s_queue[atomicAdd(&s_count, 1)] = (uint16_t)loc;
-        }
-        // advance by THREADS elements
-        j += THREADS;
-        while (j >= ncols) {
-            j -= ncols;
-            if (++i >= nrows) {  // next non-empty part (the last element is guarded by e >= total above)
-                if (!P.box_off || e + THREADS >= P.total) break;
-                do {
-                    ++part;
-                    row0 = P.box_off[part], col0 = P.q_off[part];
-                    nrows = P.box_off[part + 1] - row0, ncols = P.q_off[part + 1] - col0;
-                } while (nrows == 0 || ncols == 0);
-                i = 0;
+    const int64_t ctiles = (ncols + TC - 1) / TC;
+    const int64_t tr = lt / ctiles, tc = lt - tr * ctiles;
+    const int64_t r0 = tr * TR, c0 = tc * TC;
+    const int nr = (int)min((int64_t)TR, nrows - r0);
+    if (threadIdx.x == 0) s_count = 0;
+    if (threadIdx.x < nr) {
+        const float4 f = reinterpret_cast<const float4*>(rec_b + row0 + r0 + threadIdx.x)[2];
+        s_row[threadIdx.x] = make_float4(f.x, f.y, f.z * 1.01f + 1e-4f * (fabsf(f.x) + fabsf(f.y)), f.w);
+    }
+    __syncthreads();
+    const int64_t col = c0 + threadIdx.x;
+    if (col < ncols) {
+        const float4 fq = reinterpret_cast<const float4*>(rec_q + col0 + col)[2];
+        const float aq = fq.z * 1.01f + 1e-4f * (fabsf(fq.x) + fabsf(fq.y)) + 1e-6f;
+        float* o = out + obase + r0 * ncols + col;
+#pragma unroll 4
+        for (int r = 0; r < nr; ++r) {
+            const float4 fb = s_row[r];
+            // exact-zero test: centres further apart than the circum-radii plus a slack far above the rounding of the
+            // reference's predicates (a few ulp of the coordinates) => < 3 polygon points => area exactly 0.0
+            const float dx = fb.x - fq.x, dy = fb.y - fq.y;
+            const float d2 = dx * dx + dy * dy;
+            const float R = fb.z + aq;
+            if (d2 > R * R && d2 < 3.0e38f) {
+                o[(int64_t)r * ncols] = D3 ? 0.0f : zero_bev(fq.w, fb.w, criterion);
+            } else {
+                s_queue[atomicAdd(&s_count, 1)] = (uint16_t)((r << 8) | threadIdx.x);
             }
         }
     }
     __syncthreads();
     const int cnt = s_count;
     for (int t = threadIdx.x; t < cnt; t += THREADS) {
-        const int64_t e = base + (int)s_queue[t];
-        int64_t bi, qi;
-        locate(P, e, hint, bi, qi);
+        const int q = s_queue[t], r = q >> 8, c = q & 255;
+        const int64_t bi = row0 + r0 + r, qi = col0 + c0 + c;
         float cb[8], cq[8];
         const float4* pb = reinterpret_cast<const float4*>(rec_b + bi);
         const float4* pq = reinterpret_cast<const float4*>(rec_q + qi);
@@ -375,26 +366,30 @@ __global__ void __launch_bounds__(THREADS) kitti_pair_kernel(const Rec* __restri
         cb[0] = b0.x, cb[1] = b0.y, cb[2] = b0.z, cb[3] = b0.w, cb[4] = b1.x, cb[5] = b1.y, cb[6] = b1.z, cb[7] = b1.w;
         cq[0] = q0.x, cq[1] = q0.y, cq[2] = q0.z, cq[3] = q0.w, cq[4] = q1.x, cq[5] = q1.y, cq[6] = q1.z, cq[7] = q1.w;
         const double ai = inter_area<FL>(cq, cb);  // the query box is the kernel's first argument (rotate_iou.py:289-291)
-        float r;
-        if (D3) r = finish_d3(__double2float_rn(ai), z_b[bi], z_q[qi], criterion);
-        else r = finish_bev(ai, q2.w, b2.w, criterion);
-        out[e] = r;
+        float v;
+        if (D3) v = finish_d3(__double2float_rn(ai), z_b[bi], z_q[qi], criterion);
+        else v = finish_bev(ai, q2.w, b2.w, criterion);
+        out[obase + (r0 + r) * ncols + c0 + c] = v;
     }
 }
 
-inline size_t ws_bytes(int64_t nb, int64_t nq) {
+inline size_t ws_bytes(int64_t nb, int64_t nq, int parts) {
     return align_up((size_t)nb * sizeof(Rec), 256) + align_up((size_t)nq * sizeof(Rec), 256) + align_up((size_t)nb * sizeof(RecZ), 256) +
-           align_up((size_t)nq * sizeof(RecZ), 256);
+           align_up((size_t)nq * sizeof(RecZ), 256) + align_up((size_t)(parts + 1) * sizeof(int64_t), 256);
 }
 
-static int run(const float* b32, const float* q32, const double* b64, const double* q64, int64_t nb, int64_t nq, Parts P, int d3,
-               int criterion, float* out, void* ws, size_t wsb, unsigned flags, void* stream) {
-    if (!ws || wsb < ws_bytes(nb, nq)) {
-        set_error("workspace too small: need %zu bytes, got %zu", ws_bytes(nb, nq), wsb);
+static int run(const float* b32, const float* q32, const double* b64, const double* q64, int64_t nb, int64_t nq, Parts P,
+               int64_t total, int d3, int criterion, float* out, void* ws, size_t wsb, unsigned flags, void* stream) {
+    const int np = P.box_off ? P.num_parts : 0;
+    if (!ws || wsb < ws_bytes(nb, nq, np)) {
+        set_error("workspace too small: need %zu bytes, got %zu", ws_bytes(nb, nq, np), wsb);
         return LG_ERR_WORKSPACE;
     }
-    if (P.total > (int64_t)CHUNK * 2147483647LL) {
-        set_error("%lld output elements exceed the grid limit; split the call", (long long)P.total);
+    // tiles: exact for a single problem; for parts an upper bound from the totals (sum ceil(n/32) ceil(k/256) <=
+    // total/8192 + rows/32 + cols/256 + parts), the CTAs beyond the real count return at once
+    const int64_t tiles = P.box_off ? total / (TR * TC) + nb / TR + nq / TC + np + 1 : tiles_of(P.n, P.k);
+    if (tiles > 2147483647LL) {
+        set_error("%lld tiles exceed the grid limit; split the call", (long long)tiles);
         return LG_ERR_TOO_LARGE;
     }
     char* w = static_cast<char*>(ws);
@@ -405,9 +400,15 @@ static int run(const float* b32, const float* q32, const double* b64, const doub
     RecZ* zb = reinterpret_cast<RecZ*>(w);
     w += align_up((size_t)nb * sizeof(RecZ), 256);
     RecZ* zq = reinterpret_cast<RecZ*>(w);
+    w += align_up((size_t)nq * sizeof(RecZ), 256);
+    int64_t* tile_prefix = reinterpret_cast<int64_t*>(w);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool strict = flags & LG_FLAG_STRICT_FP32;
     const unsigned gb = (unsigned)((nb + 255) / 256), gq = (unsigned)((nq + 255) / 256);
+    if (P.box_off) {
+        kitti_tiles_kernel<<<1, 256, 0, st>>>(P.box_off, P.q_off, P.num_parts, tile_prefix);
+        P.tile_prefix = tile_prefix;
+    }
     if (strict) {
         kitti_prep_kernel<0><<<gb, 256, 0, st>>>(b32, b64, nb, rb, d3 ? zb : nullptr);
         kitti_prep_kernel<0><<<gq, 256, 0, st>>>(q32, q64, nq, rq, d3 ? zq : nullptr);
@@ -417,7 +418,7 @@ static int run(const float* b32, const float* q32, const double* b64, const doub
     }
     int rc = check_launch("kitti_prep_kernel");
     if (rc) return rc;
-    const unsigned grid = (unsigned)((P.total + CHUNK - 1) / CHUNK);
+    const unsigned grid = (unsigned)tiles;
     if (strict) {
         if (d3) kitti_pair_kernel<0, 1><<<grid, THREADS, 0, st>>>(rb, rq, zb, zq, P, criterion, out);
         else kitti_pair_kernel<0, 0><<<grid, THREADS, 0, st>>>(rb, rq, zb, zq, P, criterion, out);
@@ -431,9 +432,9 @@ static int run(const float* b32, const float* q32, const double* b64, const doub
 }  // namespace kitti
 }  // namespace lg
 
-extern "C" size_t lg_kitti_workspace_bytes(int64_t num_boxes, int64_t num_query_boxes) {
-    if (num_boxes < 0 || num_query_boxes < 0) return 0;
-    return lg::kitti::ws_bytes(num_boxes, num_query_boxes);
+extern "C" size_t lg_kitti_workspace_bytes(int64_t num_boxes, int64_t num_query_boxes, int num_parts) {
+    if (num_boxes < 0 || num_query_boxes < 0 || num_parts < 0) return 0;
+    return lg::kitti::ws_bytes(num_boxes, num_query_boxes, num_parts);
 }
 
 extern "C" int lg_rotate_iou_eval(const float* boxes, int64_t n, const float* query_boxes, int64_t k, float* out, int criterion,
@@ -448,8 +449,8 @@ extern "C" int lg_rotate_iou_eval(const float* boxes, int64_t n, const float* qu
         set_error("null pointer (boxes=%p query_boxes=%p out=%p)", (const void*)boxes, (const void*)query_boxes, (void*)out);
         return LG_ERR_INVALID_ARG;
     }
-    kitti::Parts P{nullptr, nullptr, nullptr, 1, n, k, n * k};
-    return kitti::run(boxes, query_boxes, nullptr, nullptr, n, k, P, 0, criterion, out, ws, ws_bytes, flags, stream);
+    kitti::Parts P{nullptr, nullptr, nullptr, nullptr, 1, n, k};
+    return kitti::run(boxes, query_boxes, nullptr, nullptr, n, k, P, n * k, 0, criterion, out, ws, ws_bytes, flags, stream);
 }
 
 extern "C" int lg_d3_box_overlap(const double* boxes, int64_t n, const double* qboxes, int64_t k, float* out, int criterion, void* ws,
@@ -464,8 +465,8 @@ extern "C" int lg_d3_box_overlap(const double* boxes, int64_t n, const double* q
         set_error("null pointer (boxes=%p qboxes=%p out=%p)", (const void*)boxes, (const void*)qboxes, (void*)out);
         return LG_ERR_INVALID_ARG;
     }
-    kitti::Parts P{nullptr, nullptr, nullptr, 1, n, k, n * k};
-    return kitti::run(nullptr, nullptr, boxes, qboxes, n, k, P, 1, criterion, out, ws, ws_bytes, flags, stream);
+    kitti::Parts P{nullptr, nullptr, nullptr, nullptr, 1, n, k};
+    return kitti::run(nullptr, nullptr, boxes, qboxes, n, k, P, n * k, 1, criterion, out, ws, ws_bytes, flags, stream);
 }
 
 extern "C" int lg_kitti_overlaps_parts(const double* gt_boxes, int64_t num_gt, const double* dt_boxes, int64_t num_dt,
@@ -487,6 +488,6 @@ extern "C" int lg_kitti_overlaps_parts(const double* gt_boxes, int64_t num_gt, c
         set_error("null pointer");
         return LG_ERR_INVALID_ARG;
     }
-    kitti::Parts P{gt_off, dt_off, out_off, num_parts, 0, 0, num_out};
-    return kitti::run(nullptr, nullptr, gt_boxes, dt_boxes, num_gt, num_dt, P, metric == 2, criterion, out, ws, ws_bytes, flags, stream);
+    kitti::Parts P{gt_off, dt_off, out_off, nullptr, num_parts, 0, 0};
+    return kitti::run(nullptr, nullptr, gt_boxes, dt_boxes, num_gt, num_dt, P, num_out, metric == 2, criterion, out, ws, ws_bytes, flags, stream);
 }

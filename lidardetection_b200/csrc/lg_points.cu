@@ -34,7 +34,7 @@ constexpr int PIB_TILE = LG_PIB_TILE;          // points per stage
 #define LG_PIB_CELLS 4096
 #endif
 #ifndef LG_PIB_MINB
-#define LG_PIB_MINB 3
+#define LG_PIB_MINB 4
 #endif
 #ifndef LG_PIB_WARP_PIPE
 #define LG_PIB_WARP_PIPE 0  // 1: a copy pipeline per warp (no CTA barrier per tile) -- measured 1.5 % slower on the B200; 0: one pipeline per CTA
@@ -45,7 +45,7 @@ constexpr int PIB_CELLS = LG_PIB_CELLS;         // 16 KB of 32-bit candidate lis
 constexpr float PIB_MIN_CELL = 0.6f;            // cells no smaller than 0.6 x the mean footprint half-extent
 constexpr int PIB_WARPS = PIB_THREADS / 32;
 constexpr int PIB_WPTS = PIB_TILE / PIB_WARPS;  // 128 points of a tile per warp
-constexpr int PIB_WLIST = 31 + PIB_WPTS + 1;    // per-warp work list (float4 items): leftover + one tile, padded to 160
+constexpr int PIB_WLIST = 64;                   // per-warp work list (float4 items): <= 31 left over + <= 32 appended per slot of the step
 
 // ---- mbarrier / bulk-copy wrappers (PTX ISA: cp.async.bulk, mbarrier) -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,11 +77,17 @@ struct PibSmem {
     static constexpr size_t stage_bytes = (size_t)PIB_STAGES * PIB_TILE_BYTES;
     static constexpr size_t cell_bytes = (size_t)PIB_CELLS * sizeof(uint32_t);
     static constexpr size_t list_bytes = (size_t)PIB_WARPS * PIB_WLIST * sizeof(float4);
-    static size_t total(int T) {
+    // the scratch of the grid build (cell ranges, touch constants, prefix) is dead once the lists are built: it shares the
+    // work lists' region
+    __host__ __device__ static size_t build_bytes(int T) {
         const int tc = T < PIB_COMPACT_MAX_BOXES ? T : PIB_COMPACT_MAX_BOXES;
-        return stage_bytes + cell_bytes + list_bytes + (size_t)T * 2 * sizeof(float4) + (size_t)tc * (sizeof(int4) + 2 * sizeof(float4)) +
-               (size_t)(tc + 8) * sizeof(int);
+        return (size_t)tc * (sizeof(int4) + 2 * sizeof(float4)) + (size_t)(tc + 8) * sizeof(int);
     }
+    __host__ __device__ static size_t region_bytes(int T) {
+        const size_t b = (build_bytes(T) + 15) / 16 * 16;
+        return b > list_bytes ? b : list_bytes;
+    }
+    static size_t total(int T) { return stage_bytes + cell_bytes + region_bytes(T) + (size_t)T * 2 * sizeof(float4); }
 };
 
 template <int FL>
@@ -93,8 +99,8 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
     float* stage = reinterpret_cast<float*>(smem4);
     uint32_t* cells = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem4) + PibSmem::stage_bytes);
     float4* lists = reinterpret_cast<float4*>(cells + PIB_CELLS);
-    float4* srec = lists + PIB_WARPS * PIB_WLIST;
-    int4* srange = reinterpret_cast<int4*>(srec + 2 * T);  // per box: ix0, iy0, cells per row, cells
+    float4* srec = reinterpret_cast<float4*>(reinterpret_cast<char*>(lists) + PibSmem::region_bytes(T));
+    int4* srange = reinterpret_cast<int4*>(lists);  // per box: ix0, iy0, cells per row, cells (build scratch, aliases the lists)
     float4* stouch = reinterpret_cast<float4*>(srange + min(T, PIB_COMPACT_MAX_BOXES));  // per box: pib_touch_consts
     int* sprefix = reinterpret_cast<int*>(stouch + 2 * min(T, PIB_COMPACT_MAX_BOXES));
 #if LG_PIB_WARP_PIPE
@@ -371,6 +377,10 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
                     wlist[wcount + __popc(hm & lt)] =
                         make_float4(xs[u], ys[u], zs[u], __uint_as_float(((uint32_t)cell[u] << 16) | (uint32_t)(obase + i0 + u)));
                 wcount += __popc(hm);
+                if (wcount >= 32) {  // keeps the list within 31 + 32 entries
+                    __syncwarp();    // orders the fill and the list writes before the round
+                    round(32);
+                }
             }
         } else {
             // general path (more than 254 boxes, or a frame with an unbounded box): every box is tested, as the reference does

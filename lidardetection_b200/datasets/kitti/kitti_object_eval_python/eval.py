@@ -81,7 +81,7 @@ def d3_box_overlap_cuda(boxes, qboxes, criterion=-1, flags=_lib.LG_FLAG_NONE):
     if n == 0 or k == 0:
         return out
     L = _lib.lib()
-    ws = torch.empty(L.lg_kitti_workspace_bytes(n, k), dtype=torch.uint8, device=b.device)
+    ws = torch.empty(L.lg_kitti_workspace_bytes(n, k, 0), dtype=torch.uint8, device=b.device)
     with torch.cuda.device(b.device):
         rc = L.lg_d3_box_overlap(_lib.ptr(b), n, _lib.ptr(q), k, _lib.ptr(out), int(criterion), _lib.ptr(ws), ws.numel(), flags,
                                  _lib.stream_ptr(b.device))
@@ -109,7 +109,7 @@ def kitti_overlaps_parts_cuda(gt_boxes, dt_boxes, gt_counts, dt_counts, metric, 
         return out, offs[2]
     L = _lib.lib()
     doffs = torch.from_numpy(offs).to(g.device, non_blocking=True)
-    ws = torch.empty(L.lg_kitti_workspace_bytes(g.shape[0], d.shape[0]), dtype=torch.uint8, device=g.device)
+    ws = torch.empty(L.lg_kitti_workspace_bytes(g.shape[0], d.shape[0], P), dtype=torch.uint8, device=g.device)
     with torch.cuda.device(g.device):
         rc = L.lg_kitti_overlaps_parts(_lib.ptr(g), g.shape[0], _lib.ptr(d), d.shape[0], _lib.ptr(doffs[0]), _lib.ptr(doffs[1]),
                                        _lib.ptr(doffs[2]), P, total, int(metric), int(criterion), _lib.ptr(out), _lib.ptr(ws),

@@ -21,7 +21,7 @@ def rotate_iou_eval_cuda(boxes, query_boxes, criterion=-1, flags=_lib.LG_FLAG_NO
     if n == 0 or k == 0:
         return out
     L = _lib.lib()
-    ws = torch.empty(L.lg_kitti_workspace_bytes(n, k), dtype=torch.uint8, device=b.device)
+    ws = torch.empty(L.lg_kitti_workspace_bytes(n, k, 0), dtype=torch.uint8, device=b.device)
     with torch.cuda.device(b.device):
         rc = L.lg_rotate_iou_eval(_lib.ptr(b), n, _lib.ptr(q), k, _lib.ptr(out), int(criterion), _lib.ptr(ws), ws.numel(), flags,
                                   _lib.stream_ptr(b.device))

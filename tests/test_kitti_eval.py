@@ -118,7 +118,7 @@ def test_c_abi_validation_without_gpu():
     L = _lib.lib()
     err = lambda: L.lg_last_error_string().decode()  # noqa: E731
     d = C.c_void_p(16)
-    assert L.lg_kitti_workspace_bytes(10, 20) >= 30 * 48 and L.lg_kitti_workspace_bytes(-1, 2) == 0
+    assert L.lg_kitti_workspace_bytes(10, 20, 0) >= 30 * 48 and L.lg_kitti_workspace_bytes(-1, 2, 0) == 0
     assert L.lg_rotate_iou_eval(d, -1, d, 3, d, -1, d, 1 << 20, 0, None) == -1 and "negative" in err()
     assert L.lg_rotate_iou_eval(None, 2, d, 3, d, -1, d, 1 << 20, 0, None) == -1 and "null" in err()
     assert L.lg_rotate_iou_eval(d, 2, d, 3, d, -1, None, 0, 0, None) == -2
