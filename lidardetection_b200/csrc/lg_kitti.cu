@@ -387,7 +387,7 @@ static int run(const float* b32, const float* q32, const double* b64, const doub
     }
     // tiles: exact for a single problem; for parts an upper bound from the totals (sum ceil(n/32) ceil(k/256) <=
     // total/8192 + rows/32 + cols/256 + parts), the CTAs beyond the real count return at once
-    const int64_t tiles = P.box_off ? total / (TR * TC) + nb / TR + nq / TC + np + 1 : tiles_of(P.n, P.k);
+    const int64_t tiles = P.box_off ? total / (TR * TC) + nb / TR + nq / TC + np + 3 : tiles_of(P.n, P.k);  // + 3: the three floors
     if (tiles > 2147483647LL) {
         set_error("%lld tiles exceed the grid limit; split the call", (long long)tiles);
         return LG_ERR_TOO_LARGE;

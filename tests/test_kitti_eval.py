@@ -207,6 +207,33 @@ def test_calculate_iou_partly_equals_per_part_calls(metric):
 
 
 @gpu
+def test_many_ragged_parts_cover_every_tile():
+    """parts of 0..70 x 0..600 boxes (tiles of 32 x 256: partial, empty and multi-tile parts) against the oracle per part"""
+    import torch
+
+    r = np.random.default_rng(3)
+    P = 120
+    gc = r.integers(0, 71, P)
+    dc = r.integers(0, 601, P)
+    gc[:6], dc[:6] = [0, 5, 1, 33, 32, 64], [7, 0, 1, 257, 256, 512]
+    gts, dts = synth.kitti_eval_frames(1, 9, gt_range=(int(gc.sum()), int(gc.sum())), fp_range=(int(dc.sum()), int(dc.sum())))
+    G, D = gts[0], dts[0][:int(dc.sum())]
+    D[:, 0:3] = G[r.integers(0, len(G), len(D)), 0:3] + r.normal(0, 1.5, (len(D), 3))  # make overlaps frequent
+    for metric in (1, 2):
+        out, off = E.kitti_overlaps_parts_cuda(torch.from_numpy(G).cuda(), torch.from_numpy(D).cuda(), gc, dc, metric)
+        out = out.cpu().numpy()
+        g0 = d0 = 0
+        for p in range(P):
+            Gp, Dp = G[g0:g0 + gc[p]], D[d0:d0 + dc[p]]
+            want = O.bev_box_overlap(Gp[:, MG.BEV_COLS], Dp[:, MG.BEV_COLS]) if metric == 1 else O.d3_box_overlap(Gp, Dp)
+            got = out[off[p]:off[p + 1]].reshape(gc[p], dc[p])
+            assert same_bits(got, want) == 0, (metric, p, gc[p], dc[p])
+            g0 += gc[p]
+            d0 += dc[p]
+        assert off[-1] == (gc * dc).sum()
+
+
+@gpu
 def test_full_size_eval_properties():
     """KITTI val size (3769 frames, 51 parts, 28 M pairs): properties that need no oracle pass over everything --
     criterion identities between the four outputs of the same pairs, symmetry of the intersection area under swapping the

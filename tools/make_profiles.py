@@ -33,14 +33,32 @@ KEYS = [
 
 
 def raw_metrics(rep, kernel):
+    """metrics of the LONGEST profiled launch whose name contains `kernel` (a call may launch a probe or a skipped twin of the
+    same kernel first); returns (metrics, demangled name, ordinal of that launch among the matches)"""
     txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     kn = hdr.index("Kernel Name")
-    for r in rows[2:]:
-        if kernel in r[kn]:
-            return [(k, r[hdr.index(k)], units[hdr.index(k)]) for k in KEYS if k in hdr], r[kn]
-    raise SystemExit(f"{kernel} not in {rep}")
+    dur = hdr.index("gpu__time_duration.sum")
+    match = [r for r in rows[2:] if kernel in r[kn]]
+    if not match:
+        raise SystemExit(f"{kernel} not in {rep}")
+    best = max(range(len(match)), key=lambda i: float(match[i][dur].replace(",", "")))
+    r = match[best]
+    return [(k, r[hdr.index(k)], units[hdr.index(k)]) for k in KEYS if k in hdr], r[kn], best
+
+
+def mangled_of(kname, kernel):
+    """iou_strip_kernel<1, 0, 1>(...) -> iou_strip_kernelILi1ELi0ELi1E (integer template arguments only)"""
+    import re
+
+    m = re.search(re.escape(kernel) + r"<([^>]*)>", kname)
+    if not m:
+        return kernel
+    args = [a.strip().replace("(int)", "") for a in m.group(1).split(",")]
+    if not all(re.fullmatch(r"-?\d+", a) for a in args):
+        return kernel
+    return kernel + "I" + "".join("Li" + (a if not a.startswith("-") else "n" + a[1:]) + "E" for a in args) + "E"
 
 
 def traffic(tag, specs):
@@ -52,7 +70,7 @@ def traffic(tag, specs):
     for spec in specs:
         wl, rest = spec.split("=", 1)
         rep, kernel = rest.split(":")[:2]
-        met, kname = raw_metrics(rep, kernel)
+        met, kname, _ = raw_metrics(rep, kernel)
         d = {k: v for k, v, _ in met}
         units = {k: u for k, _, u in met}
 
@@ -78,9 +96,10 @@ def main():
         name, rest = spec.split("=", 1)
         parts = rest.split(":")
         rep, kernel = parts[0], parts[1]
-        mangled = parts[2] if len(parts) > 2 else kernel
-        met, kname = raw_metrics(rep, kernel)
-        lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kernel, "--mangled", mangled, "--top", "30"],
+        met, kname, ordinal = raw_metrics(rep, kernel)
+        mangled = parts[2] if len(parts) > 2 else mangled_of(kname, kernel)
+        lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kernel, "--mangled", mangled, "--top", "30",
+                                "--launch", str(ordinal)],
                                capture_output=True, text=True).stdout
         out = os.path.join(ROOT, "profiles", f"{tag}_{name}.txt")
         with open(out, "w") as f:
