@@ -620,7 +620,7 @@ class PostProcWorkload(Workload):
         self.units = F
         self.boxes, self.scores = torch.from_numpy(self.boxes_np).cuda(), torch.from_numpy(self.scores_np).cuda()
         self.h_boxes, self.h_scores = torch.from_numpy(self.boxes_np).pin_memory(), torch.from_numpy(self.scores_np).pin_memory()
-        self.launches_per_step = 2  # nms_prep_kernel, nms_lazy_kernel (top-k / gather are torch's)
+        self.launches_per_step = 4  # select_topk_kernel, nms_prep_kernel, nms_lazy_kernel, select_finish_kernel
         self.h2d = (self.boxes_np.size + self.scores_np.size) * 4
         self.d2h = 0
 
@@ -661,7 +661,7 @@ class PostProcWorkload(Workload):
         t = float(np.mean(ts)) * 1e-3
         byts = float(self.boxes_np.size * 4 + self.scores_np.size * 4 + self.units * 500 * 12)
         ach = byts / t / 1e9
-        return {"bound": "hbm", "kernel": "torch.topk + gather + nms_prep_kernel + nms_lazy_kernel (whole step)", "achieved": ach, "peak": hbm_peak,
+        return {"bound": "hbm", "kernel": "select_topk_kernel + nms_prep_kernel + nms_lazy_kernel + select_finish_kernel (whole step)", "achieved": ach, "peak": hbm_peak,
                 "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
                 "algorithmic": {"bytes_per_launch": byts, "formula": "32 B x candidates + 12 B x 500 x frames", "step_ms": t * 1e3}}
 

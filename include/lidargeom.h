@@ -222,6 +222,28 @@ LG_API int lg_kitti_overlaps_parts(const double *gt_boxes, int64_t num_gt, const
                                    int64_t num_out, int metric, int criterion, float *out, void *ws, size_t ws_bytes, unsigned flags,
                                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Selection steps of the post-processing front end (pcdet/models/model_utils/model_nms_utils.py:6-25,
+ * called per frame / per class from detector3d_template.py:190-260), batched over P problems.
+ *   lg_select_topk   <- `scores >= SCORE_THRESH` mask, torch.topk(k = NMS_PRE_MAXSIZE), the box gather:
+ *       scores (P, n) f32; problem p takes its boxes from frame p / problems_per_frame:
+ *       row i of that frame = boxes + frame * box_frame_stride + i * box_row_stride (strides in floats; >= 7 floats per row)
+ *       -> top_idx (P, k) int64: candidate indices in descending score, equal scores by ascending index (0 beyond counts[p]);
+ *          counts (P) int32 = min(k, candidates passing the threshold); top_boxes (P, k, 7) f32 (0 beyond counts[p]; may be NULL).
+ *       use_thresh = 0: every candidate passes.  k <= LG_SELECT_MAX_K, n < 2^31.
+ *       ws: lg_select_workspace_bytes(P, n) bytes.
+ *   lg_select_finish <- keep[:NMS_POST_MAXSIZE], indices[keep], scores[selected] (model_nms_utils.py:21-25):
+ *       keep (P, k) / num_keep (P) as lg_nms_*_batched return them for the top_boxes above
+ *       -> selected (P, post) int64 candidate indices (-1 padded), num_out (P) = min(num_keep, post), sel_scores (P, post).
+ */
+#define LG_SELECT_MAX_K 4096
+LG_API size_t lg_select_workspace_bytes(int num_problems, int64_t n);
+LG_API int lg_select_topk(const float *scores, int num_problems, int64_t n, int k, float score_thresh, int use_thresh, const float *boxes,
+                          int64_t box_frame_stride, int64_t box_row_stride, int problems_per_frame, int64_t *top_idx, int32_t *counts,
+                          float *top_boxes, void *ws, size_t ws_bytes, unsigned flags, void *stream);
+LG_API int lg_select_finish(const int64_t *keep, const int32_t *num_keep, const int64_t *top_idx, const float *scores, int num_problems,
+                            int64_t n, int k, int post, int64_t *selected, int32_t *num_out, float *sel_scores, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

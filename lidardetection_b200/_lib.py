@@ -79,6 +79,12 @@ def lib():
     L.lg_d3_box_overlap.argtypes = [vp, i64, vp, i64, vp, i32, vp, sz, u32, vp]
     L.lg_kitti_overlaps_parts.restype = C.c_int
     L.lg_kitti_overlaps_parts.argtypes = [vp, i64, vp, i64, vp, vp, vp, i32, i64, i32, i32, vp, vp, sz, u32, vp]
+    L.lg_select_workspace_bytes.restype = sz
+    L.lg_select_workspace_bytes.argtypes = [i32, i64]
+    L.lg_select_topk.restype = C.c_int
+    L.lg_select_topk.argtypes = [vp, i32, i64, i32, f32, i32, vp, i64, i64, i32, vp, vp, vp, vp, sz, u32, vp]
+    L.lg_select_finish.restype = C.c_int
+    L.lg_select_finish.argtypes = [vp, vp, vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -90,6 +96,7 @@ EXPORTS = [
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
     "lg_roiaware_pool3d_forward", "lg_roiaware_pool3d_backward", "lg_roipoint_pool3d_forward",
     "lg_kitti_workspace_bytes", "lg_rotate_iou_eval", "lg_d3_box_overlap", "lg_kitti_overlaps_parts",
+    "lg_select_workspace_bytes", "lg_select_topk", "lg_select_finish",
 ]
 
 

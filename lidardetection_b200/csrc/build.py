@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "liblidargeom.so")
-SOURCES = ["lg_api.cu", "lg_iou.cu", "lg_nms.cu", "lg_points.cu", "lg_pool.cu", "lg_kitti.cu"]
+SOURCES = ["lg_api.cu", "lg_iou.cu", "lg_nms.cu", "lg_points.cu", "lg_pool.cu", "lg_kitti.cu", "lg_select.cu"]
 HEADERS = ["lg_common.cuh", "lg_geom.cuh", "lg_strip.cuh", "lg_pib.cuh", os.path.join("..", "..", "include", "lidargeom.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
