@@ -549,7 +549,7 @@ class KittiEvalWorkload(Workload):
         self.metric, self.unit = "KITTI-eval rotated overlap Gpairs/s (bev + 3d)", "Gpairs/s"
         self.name = (f"KITTI val evaluation overlaps: calculate_iou_partly metric 1 (bev) + metric 2 (3d), 3769 frames in {len(parts)} parts, "
                      f"{self.pairs} pairs per metric, per GPU")
-        self.launches_per_step = 6  # per metric: 2 x kitti_prep_kernel + kitti_pair_kernel
+        self.launches_per_step = 8  # per metric: kitti_tiles_kernel + 2 x kitti_prep_kernel + kitti_pair_kernel
         self.h2d = 2 * 56 * (len(self.G) + len(self.D))
         # calculate_iou_partly brings back only the non-zero entries (int64 index + float32 value), counted here once
         nnz = sum(int((o.view(torch.int32) != 0).sum()) for o in self.step())
