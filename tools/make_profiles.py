@@ -97,7 +97,7 @@ def main():
         parts = rest.split(":")
         rep, kernel = parts[0], parts[1]
         met, kname, ordinal = raw_metrics(rep, kernel)
-        mangled = parts[2] if len(parts) > 2 else mangled_of(kname, kernel)
+        mangled = parts[2] if len(parts) > 2 else "auto"  # ncu_lines derives it from the typed name in the source page
         lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, kernel, "--mangled", mangled, "--top", "30",
                                 "--launch", str(ordinal)],
                                capture_output=True, text=True).stdout

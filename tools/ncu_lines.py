@@ -47,6 +47,23 @@ def line_map(so, kernel_sub):
     raise SystemExit(f"kernel {kernel_sub} not found in {so}")
 
 
+def mangled_of(demangled, kernel):
+    """void lg::nms_lazy_kernel<(int)1, (bool)1, (int)512>(...) -> nms_lazy_kernelILi1ELb1ELi512EE: the template instance the
+    report's launch belongs to (several instances of one kernel share the substring `kernel`)"""
+    m = re.search(re.escape(kernel) + r"<([^>]*)>", demangled)
+    if not m:
+        return kernel
+    out = []
+    for arg in m.group(1).split(","):
+        t = re.fullmatch(r"\s*\((int|bool|unsigned int|long)\)(-?\d+)\s*", arg)
+        if not t:
+            return kernel
+        code = {"int": "i", "bool": "b", "unsigned int": "j", "long": "l"}[t.group(1)]
+        v = t.group(2)
+        out.append("L" + code + (v if not v.startswith("-") else "n" + v[1:]) + "E")
+    return kernel + "I" + "".join(out) + "E"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
@@ -56,7 +73,6 @@ def main():
     ap.add_argument("--launch", type=int, default=0, help="which profiled launch of that kernel")
     ap.add_argument("--mangled", default=None, help="substring of the mangled name (default: same as kernel)")
     a = ap.parse_args()
-    lm, fn = line_map(a.so, a.mangled or a.kernel)
     txt = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True,
                          text=True).stdout
     # the csv holds one block per profiled launch: "Kernel Name",...  then a header row, then rows
@@ -72,7 +88,12 @@ def main():
         elif cur is not None:
             cur["rows"].append(row)
     blocks = [b for b in blocks if a.kernel in b["name"]]
+    # ncu prints every launch twice on this page (same name, same rows): keep one of each pair
+    if len(blocks) % 2 == 0 and all(blocks[i]["name"] == blocks[i + 1]["name"] and len(blocks[i]["rows"]) == len(blocks[i + 1]["rows"])
+                                    for i in range(0, len(blocks), 2)):
+        blocks = blocks[::2]
     b = blocks[a.launch]
+    lm, fn = line_map(a.so, a.mangled if a.mangled not in (None, "auto") else mangled_of(b["name"], a.kernel))
     h = b["hdr"]
     ia, ie, it, isamp = h.index("Address"), h.index("Instructions Executed"), h.index("Thread Instructions Executed"), h.index("# Samples")
     stall_cols = [(i, c) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
