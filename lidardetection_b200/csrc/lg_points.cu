@@ -36,9 +36,6 @@ constexpr int PIB_TILE = LG_PIB_TILE;          // points per stage
 #ifndef LG_PIB_MINB
 #define LG_PIB_MINB 4
 #endif
-#ifndef LG_PIB_WARP_PIPE
-#define LG_PIB_WARP_PIPE 0  // 1: a copy pipeline per warp (no CTA barrier per tile) -- measured 1.5 % slower on the B200; 0: one pipeline per CTA
-#endif
 constexpr int PIB_STAGES = LG_PIB_STAGES;
 constexpr int PIB_TILE_BYTES = PIB_TILE * 12;  // 12 KB
 constexpr int PIB_CELLS = LG_PIB_CELLS;         // 16 KB of 32-bit candidate lists (lg_pib.cuh)
@@ -103,11 +100,7 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
     int4* srange = reinterpret_cast<int4*>(lists);  // per box: ix0, iy0, cells per row, cells (build scratch, aliases the lists)
     float4* stouch = reinterpret_cast<float4*>(srange + min(T, PIB_COMPACT_MAX_BOXES));  // per box: pib_touch_consts
     int* sprefix = reinterpret_cast<int*>(stouch + 2 * min(T, PIB_COMPACT_MAX_BOXES));
-#if LG_PIB_WARP_PIPE
-    __shared__ uint64_t bars[PIB_WARPS * PIB_STAGES];
-#else
     __shared__ uint64_t bars[PIB_STAGES];
-#endif
     __shared__ float red[8][6];
     __shared__ PibGrid sgrid;
     __shared__ int s_use_grid, s_nvalid, s_total;
@@ -121,39 +114,6 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
     const int ntiles = (int)((npts + PIB_TILE - 1) / PIB_TILE);
     const bool tma_ok = (reinterpret_cast<uintptr_t>(gp) & 15) == 0;  // bulk copies need 16-byte aligned sources
 
-#if LG_PIB_WARP_PIPE
-    // warp w owns points [w * per_warp, (w + 1) * per_warp) of the CTA's chunk, in 128-point slices through its own stages
-    const int64_t per_warp = (npts + (int64_t)PIB_WARPS * PIB_WPTS - 1) / ((int64_t)PIB_WARPS * PIB_WPTS) * PIB_WPTS;
-    auto wrange = [&](int w, int64_t& first, int64_t& count) {
-        first = min(npts, (int64_t)w * per_warp);
-        count = min(npts, first + per_warp) - first;
-    };
-    int64_t w0, wn;
-    wrange(warp, w0, wn);
-    const int wtiles = (int)((wn + PIB_WPTS - 1) / PIB_WPTS);
-    float* wstage = stage + (size_t)warp * PIB_STAGES * (PIB_WPTS * 3);
-    auto wissue = [&](int w, int t) {  // a slice whose byte count is not a multiple of 16 is loaded by the fallback
-        int64_t f, c;
-        wrange(w, f, c);
-        const unsigned bytes = (unsigned)(min((int64_t)PIB_WPTS, c - (int64_t)t * PIB_WPTS) * 12);
-        if (tma_ok && (bytes & 15) == 0) {
-            uint64_t* bar = &bars[w * PIB_STAGES + t % PIB_STAGES];
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(stage + ((size_t)w * PIB_STAGES + t % PIB_STAGES) * (PIB_WPTS * 3), gp + (f + (int64_t)t * PIB_WPTS) * 3, bytes, bar);
-        }
-    };
-    if (tid == 0) {
-        for (int s = 0; s < PIB_WARPS * PIB_STAGES; s++) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int w = 0; w < PIB_WARPS; w++) {  // the points start flowing while the grid is built
-            int64_t f, c;
-            wrange(w, f, c);
-            const int wt = (int)((c + PIB_WPTS - 1) / PIB_WPTS);
-            for (int t = 0; t < min(wt, PIB_STAGES); t++) wissue(w, t);
-        }
-    }
-#else
     auto tile_bytes = [&](int t) -> unsigned { return (unsigned)(min((int64_t)PIB_TILE, npts - (int64_t)t * PIB_TILE) * 12); };
     auto issue = [&](int t) {  // thread 0 only; a tile whose byte count is not a multiple of 16 is loaded by the fallback
         const unsigned bytes = tile_bytes(t);
@@ -170,7 +130,6 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
         for (int t = 0; t < min(ntiles, PIB_STAGES); t++) issue(t);  // the points start flowing while the grid is built
     }
 
-#endif
 
     // ---- 1. records, footprints, frame bounds
     const float* fb = boxes + (int64_t)b * T * 7;
@@ -399,27 +358,6 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
             }
         }
     };
-#if LG_PIB_WARP_PIPE
-    // every warp runs its own copy pipeline over its own contiguous share of the CTA's points: no CTA barrier after the
-    // grid is built, warps drift apart and overlap each other's lookup / test phases
-    for (int t = 0; t < wtiles; t++) {
-        const int s = t % PIB_STAGES;
-        float* sp = wstage + s * (PIB_WPTS * 3);
-        const int np = (int)min((int64_t)PIB_WPTS, wn - (int64_t)t * PIB_WPTS);
-        if (tma_ok && ((np * 12) & 15) == 0) {
-            mbar_wait(&bars[warp * PIB_STAGES + s], (unsigned)((t / PIB_STAGES) & 1));
-        } else {
-            const float* src = gp + (w0 + (int64_t)t * PIB_WPTS) * 3;
-            for (int i = lane; i < np * 3; i += 32) sp[i] = __ldg(src + i);
-            __syncwarp();
-        }
-        process(sp, np, (int)(w0 + (int64_t)t * PIB_WPTS));
-        __syncwarp();  // orders the fill and the list writes before the rounds; every lane has read its part of the stage
-        if (lane == 0 && t + PIB_STAGES < wtiles) wissue(warp, t + PIB_STAGES);
-        if (use_grid)
-            while (wcount >= 32) round(32);
-    }
-#else
     for (int t = 0; t < ntiles; t++) {
         const int s = t % PIB_STAGES;
         float* sp = stage + (size_t)s * (PIB_TILE * 3);
@@ -440,7 +378,6 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
         __syncthreads();  // everyone is done with this stage: refill it
         if (tid == 0 && t + PIB_STAGES < ntiles) issue(t + PIB_STAGES);
     }
-#endif
     if (use_grid && wcount > 0) round(wcount);
 }
 
