@@ -48,6 +48,10 @@ namespace lg {
 constexpr int REC_F4 = 7;
 constexpr int REC_FLOATS = 4 * REC_F4;
 constexpr int REC_CULL = 4, REC_TRIG = 5, REC_Z = 6;
+// per-lane scratch column of the fast polygon path: rows 0..7 hold the polygon's vertices, rows 8..11 the B box's corners
+// (staged from the registers pair_masks loaded them into, so that the data-dependent crossing / corner loops index
+// shared memory instead of re-reading the column record from global memory)
+constexpr int SLAB_ROWS_SMEM_B = 8, SLAB_ROWS = 12, SLAB_BCORNER = 8;
 
 // ---- arithmetic contract helpers --------------------------------------------------------------
 // FL = 1: reference CUDA build (nvcc 12.9, sm_100a):  a*b - c*d  ==  fma(a, b, -(c*d))
@@ -213,15 +217,16 @@ __device__ __forceinline__ uint32_t or_if_inside(uint32_t m, const uint32_t bit,
 //                           the ones s1 of the next B edge and s5 use; ptxas keeps them unfused)
 //   s3 = cross(p0,q1,q0) = fma(-Dx[i][j], f_j.y,  f_j.x * Dy[i][j])
 //   s4 = cross(q1,p1,q0) = fma(f_j.x, -Dy[i+1][j], Dx[i+1][j] * f_j.y)
-template <int FL>
+template <int FL, bool STAGE = false>
 __device__ __forceinline__ void pair_masks(const float4* __restrict__ A, const float4* __restrict__ B, uint32_t& xmask,
-                                           uint32_t& cmask) {
+                                           uint32_t& cmask, float2* __restrict__ slab = nullptr, const int sstride = 0) {
     float px[4], py[4], ex[4], ey[4], qx[4], qy[4], fx[4], fy[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const float4 a = A[k], b = B[k];
         px[k] = a.x; py[k] = a.y; ex[k] = a.z; ey[k] = a.w;
         qx[k] = b.x; qy[k] = b.y; fx[k] = b.z; fy[k] = b.w;
+        if (STAGE) slab[(SLAB_BCORNER + k) * sstride] = make_float2(b.x, b.y);
     }
     // corner margin tests first (their operands die early): kernel.cu:51-61
     uint32_t cm = 0;
@@ -289,11 +294,19 @@ __device__ __forceinline__ void pair_masks(const float4* __restrict__ A, const f
 }
 
 // crossing point of A edge i and B edge j (kernel.cu:77-91); the determinants are re-formed for this one pair
-template <int FL>
+template <int FL, bool STAGE = false>
 __device__ __forceinline__ float2 crossing_point(const float4* __restrict__ A, const float4* __restrict__ B, const int i,
-                                                 const int j) {
+                                                 const int j, const float2* __restrict__ slab = nullptr, const int sstride = 0) {
     const float4 pe = A[i];
-    const float4 q0 = B[j], q1 = B[(j + 1) & 3];
+    float4 q0, q1;
+    if (STAGE) {  // B's corners from the lane's own scratch column; q0.z (an edge component) only in the degenerate branch below
+        const float2 s0 = slab[(SLAB_BCORNER + j) * sstride], s1 = slab[(SLAB_BCORNER + ((j + 1) & 3)) * sstride];
+        q0 = make_float4(s0.x, s0.y, 0.f, 0.f);
+        q1 = make_float4(s1.x, s1.y, 0.f, 0.f);
+    } else {
+        q0 = B[j];
+        q1 = B[(j + 1) & 3];
+    }
     const float d0x = q0.x - pe.x, d0y = q0.y - pe.y, d1x = q1.x - pe.x, d1y = q1.y - pe.y;
     const float s1 = msub<FL>(d0x, pe.w, pe.z, d0y);
     const float t72 = __fmul_rn(pe.z, d1y), t73 = __fmul_rn(d1x, pe.w);
@@ -306,7 +319,7 @@ __device__ __forceinline__ float2 crossing_point(const float4* __restrict__ A, c
     } else {
         const float4 p1 = A[(i + 1) & 3];
         const float a0 = pe.y - p1.y, b0 = pe.z, c0 = msub<FL>(pe.x, p1.y, p1.x, pe.y);
-        const float a1 = q0.y - q1.y, b1 = q0.z, c1 = msub<FL>(q0.x, q1.y, q1.x, q0.y);
+        const float a1 = q0.y - q1.y, b1 = STAGE ? B[j].z : q0.z, c1 = msub<FL>(q0.x, q1.y, q1.x, q0.y);
         const float D = msub<FL>(a0, b1, a1, b0);
         X = __fdiv_rn(msub<FL>(b0, c1, b1, c0), D);
         Y = __fdiv_rn(msub<FL>(a1, c0, a0, c1), D);
@@ -320,11 +333,13 @@ __device__ __forceinline__ float2 crossing_point(const float4* __restrict__ A, c
 // converged); it is used to re-converge the warp after each data-dependent loop.
 // Returns the overlap area exactly as the reference defines it (kernel.cu:104-225), or -1 when the polygon
 // has more than 8 vertices and the pair must be handed to overlap_area_slow.
-template <int FL>
+// STAGE: B lives in global memory -> its corners are staged in rows 8..11 of the lane's scratch column (the caller's slab
+// then has SLAB_ROWS rows); false: B is in shared memory already, 8 rows suffice.
+template <int FL, bool STAGE = false>
 __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, const float4* __restrict__ B,
                                               float2* __restrict__ slab, const int sstride, const unsigned wmask) {
     uint32_t xmask, cmask;
-    pair_masks<FL>(A, B, xmask, cmask);
+    pair_masks<FL, STAGE>(A, B, xmask, cmask, slab, sstride);
     const int cnt = __popc(xmask) + __popc(cmask);
     float res = 0.f;          // cnt <= 2: the fan sum is empty or a single zero term
     if (cnt > 8) res = -1.f;  // deferred
@@ -338,7 +353,7 @@ __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, cons
         while (xmask) {
             const int e = __ffs(xmask) - 1;
             xmask &= xmask - 1;
-            const float2 v = crossing_point<FL>(A, B, e >> 2, e & 3);
+            const float2 v = crossing_point<FL, STAGE>(A, B, e >> 2, e & 3, slab, sstride);
             slab[n * sstride] = v;
             sx += v.x;
             sy += v.y;
@@ -349,8 +364,14 @@ __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, cons
         while (cmask) {
             const int e = __ffs(cmask) - 1;
             cmask &= cmask - 1;
-            const float4 c = (e & 1) ? A[e >> 1] : B[e >> 1];
-            slab[n * sstride] = make_float2(c.x, c.y);
+            float2 c;
+            if ((e & 1) || !STAGE) {
+                const float4 a = (e & 1) ? A[e >> 1] : B[e >> 1];
+                c = make_float2(a.x, a.y);
+            } else {
+                c = slab[(SLAB_BCORNER + (e >> 1)) * sstride];
+            }
+            slab[n * sstride] = c;
             sx += c.x;
             sy += c.y;
             n++;
@@ -402,7 +423,7 @@ __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, cons
 template <int FL>
 __device__ __noinline__ float overlap_area_call(const float4* __restrict__ A, const float4* __restrict__ B, float2* __restrict__ slab,
                                                 const int sstride, const unsigned wmask) {
-    return overlap_area<FL>(A, B, slab, sstride, wmask);
+    return overlap_area<FL, true>(A, B, slab, sstride, wmask);  // its callers keep B in global memory
 }
 
 // ---- the pair, 9..16 vertices (near-coincident boxes; ~0.3 % of overlapping pairs) -----------------

@@ -57,7 +57,7 @@ constexpr int SK_MAX_COLS = 1 << SK_SHIFT;
 struct StripSmem {
     static constexpr size_t a_bytes = (size_t)SK_ROWS * REC_F4 * sizeof(float4);
     static constexpr size_t dup_bytes = (size_t)SK_ROWS * 2 * sizeof(float4);
-    static constexpr size_t total = a_bytes + dup_bytes + ST_SLAB_BYTES + (size_t)(ST_THREADS / 32) * (WQ_CAP + 1 + WR_CAP) * sizeof(uint32_t);
+    static constexpr size_t total = a_bytes + dup_bytes + ST_SLAB_BYTES_STAGED + (size_t)(ST_THREADS / 32) * (WQ_CAP + 1 + WR_CAP) * sizeof(uint32_t);
 };
 
 // A tile is 32 rows x 128 columns; a warp owns 8 of its rows (rsub + 4k) x 64 columns, two adjacent columns per
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? 3 : 2)
     float4* sA = smem4;
     float4* sDup = sA + SK_ROWS * REC_F4;  // per row: (cx, cx, cy, cy), (rad, rad, -, -)
     float2* slab = reinterpret_cast<float2*>(sDup + SK_ROWS * 2);
-    uint32_t* lists = reinterpret_cast<uint32_t*>(slab + 8 * NT);
+    uint32_t* lists = reinterpret_cast<uint32_t*>(slab + SLAB_ROWS * NT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t strip = blockIdx.x;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     float4* sA = smem4;
     float4* sB = sA + FLAT_ROWS * REC_F4;
     float2* slab = reinterpret_cast<float2*>(sB + FLAT_COLS * REC_F4);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + SLAB_ROWS_SMEM_B * NT);
     uint16_t* rareq = queue + ST_QCAP;
     __shared__ int qcount, rcount;
 

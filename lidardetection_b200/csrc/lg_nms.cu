@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 3)
     float4* sA = smem4;
     float4* sB = sA + T * REC_F4;
     float2* slab = reinterpret_cast<float2*>(sB + T * REC_F4);
-    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + 8 * NT);
+    uint16_t* queue = reinterpret_cast<uint16_t*>(slab + SLAB_ROWS_SMEM_B * NT);
     uint16_t* rareq = queue + ST_QCAP;
     unsigned int* smask = reinterpret_cast<unsigned int*>(rareq + ST_RARECAP);  // 64 x (lo, hi)
     __shared__ int qcount, rcount;
@@ -285,7 +285,7 @@ struct LazyLayout {
         off_cull = o;
         o += (size_t)(nmax < LZ_CACHE ? nmax : LZ_CACHE) * sizeof(float4);
         off_slab = o;
-        o += (size_t)8 * nt * sizeof(float2);
+        o += (size_t)SLAB_ROWS * nt * sizeof(float2);
         off_queue = o;
         o += (size_t)LZ_QCAP * sizeof(uint32_t);
         off_rare = o;
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                     drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
                     __syncthreads();
                 }
-                drain_main<FL, 16, NT>(sA, grec, slab, queue, qn, rareq, &rcount, emit);
+                drain_main<FL, 16, NT, true>(sA, grec, slab, queue, qn, rareq, &rcount, emit);  // column records in global memory: staged
                 if (tid == 0) {
                     qcount = 0;
                     st_heavy += (unsigned long long)qn;

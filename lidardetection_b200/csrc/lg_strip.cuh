@@ -19,7 +19,8 @@ constexpr int ST_THREADS = 256;
 constexpr int ST_QCAP = 4096;                   // main queue entries
 constexpr int ST_RARECAP = ST_QCAP + 2048;      // rare queue entries: a full main drain always fits on top of 2048
 constexpr int ST_SLOW_LANES = 64;               // threads that run the literal path (each needs 4 slab columns)
-constexpr size_t ST_SLAB_BYTES = (size_t)8 * ST_THREADS * sizeof(float2);  // 16 KB
+constexpr size_t ST_SLAB_BYTES = (size_t)SLAB_ROWS_SMEM_B * ST_THREADS * sizeof(float2);  // 16 KB (column records in shared memory)
+constexpr size_t ST_SLAB_BYTES_STAGED = (size_t)SLAB_ROWS * ST_THREADS * sizeof(float2);  // 24 KB: + 4 staged B corners per lane
 
 // Reserve queue space for this warp's survivors of one tile and write their codes.
 // m[k] = ballot of the k-th row iteration (row = rbase + rstep * k), code = row << SHIFT | col.
@@ -51,7 +52,7 @@ __device__ __forceinline__ void push_survivors(const unsigned (&m)[NK], const in
 //   sA, sB   row / column records (shared memory, or global); code -> row = code >> SHIFT, col = code & (2^SHIFT - 1)
 //   emit(row, col, overlap, A, B) consumes one result (store an IoU, set a mask bit, ...)
 //   rareq    deferred pairs are appended at (*rcount)++; the caller guarantees *rcount + qn <= ST_RARECAP
-template <int FL, int SHIFT, int NT = ST_THREADS, typename Q, typename Emit>
+template <int FL, int SHIFT, int NT = ST_THREADS, bool STAGE = false, typename Q, typename Emit>
 __device__ __forceinline__ void drain_main(const float4* __restrict__ sA, const float4* __restrict__ sB, float2* __restrict__ slab,
                                            const Q* __restrict__ queue, const int qn, Q* __restrict__ rareq, int* rcount, Emit emit) {
     const int tid = threadIdx.x;
@@ -64,7 +65,7 @@ __device__ __forceinline__ void drain_main(const float4* __restrict__ sA, const 
             const int r = e >> SHIFT, c = e & ((1u << SHIFT) - 1u);
             const float4* A = sA + (size_t)r * REC_F4;
             const float4* B = sB + (size_t)c * REC_F4;
-            const float ov = overlap_area<FL>(A, B, slab + tid, NT, wm);
+            const float ov = overlap_area<FL, STAGE>(A, B, slab + tid, NT, wm);
             if (ov < 0.f) rareq[atomicAdd(rcount, 1)] = (Q)e;
             else emit(r, c, ov, A, B);
         }
@@ -197,7 +198,7 @@ __device__ __forceinline__ void warp_round(WarpQueue& q, const float4* __restric
         const int r = e >> SHIFT, c = e & ((1u << SHIFT) - 1u);
         const float4* A = sA + (size_t)r * REC_F4;
         const float4* B = sB + (size_t)c * REC_F4;
-        const float ov = INLINE_PATH ? overlap_area<FL>(A, B, slab_warp + lane, sstride, wm) : overlap_area_call<FL>(A, B, slab_warp + lane, sstride, wm);
+        const float ov = INLINE_PATH ? overlap_area<FL, true>(A, B, slab_warp + lane, sstride, wm) : overlap_area_call<FL>(A, B, slab_warp + lane, sstride, wm);
         if (ov < 0.f) defer = true;
         else emit(r, c, ov, A, B);
     }
