@@ -141,9 +141,33 @@ def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE):
     return keep, num
 
 
+LG_SELECT_MAX_K = 4096
+
+
+def _argsort_desc(scores):
+    """(P, N) scores -> (P, N) int64 indices in descending score (the wrapper's `scores.sort(descending=True)[1]`,
+    iou3d_nms_utils.py:92).  Up to 4096 float32 scores per problem: lg_select_topk (one CTA per problem, bitonic sort in shared
+    memory, equal scores by ascending index) when the batch has at most two problems per SM; otherwise torch.sort."""
+    P, N = scores.shape
+    if not (scores.is_cuda and scores.dtype == torch.float32 and 0 < N <= LG_SELECT_MAX_K and 0 < P <= 2 * 148):  # one CTA per problem: a
+        # batch of thousands of small problems is better served by torch's segmented sort (measured on nms_cfg5)
+        return scores.sort(1, descending=True)[1].contiguous()
+    L = _lib.lib()
+    dev = scores.device
+    sc = scores.contiguous()
+    order = torch.empty((P, N), dtype=torch.int64, device=dev)
+    cnt = torch.empty((P,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(L.lg_select_workspace_bytes(P, N), dev)
+        rc = L.lg_select_topk(_lib.ptr(sc), P, N, N, 0.0, 0, None, 0, 0, 1, _lib.ptr(order), _lib.ptr(cnt), None, _lib.ptr(ws), ws.numel(), 0,
+                              _lib.stream_ptr(dev))
+    _lib.check(rc, 'lg_select_topk')
+    return order
+
+
 def _nms_single(fn_name, boxes, scores, thresh, pre_maxsize):
     assert boxes.shape[1] == 7
-    order = scores.sort(0, descending=True)[1]
+    order = _argsort_desc(scores.reshape(1, -1))[0]
     if pre_maxsize is not None:
         order = order[:pre_maxsize]
     if pre_maxsize is not None and order.shape[0] < boxes.shape[0]:
@@ -184,7 +208,7 @@ def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE
         idx = torch.arange(b.shape[1], device=b.device).unsqueeze(0)
         scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
         counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
-    order = scores.sort(1, descending=True)[1].contiguous()
+    order = _argsort_desc(scores)
     return _nms_call(fn_name, b, order, counts, thresh, flags)
 
 
