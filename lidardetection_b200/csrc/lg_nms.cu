@@ -318,14 +318,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s;
     __shared__ unsigned long long st_heavy;
-    __shared__ unsigned xch[LZ_MAX_CLUSTER][G];  // candidate-vs-candidate suppression bits, one row per CTA of the cluster
 
     // A problem may be spread over a thread-block cluster of C CTAs (C SMs): they keep identical copies of the alive bitmap
-    // and of the pass state, split the COLUMNS of every pass (interleaved 512-column sweeps), and exchange, through
-    // distributed shared memory, (a) the G x G candidate bits before the resolve and (b) the kill words after it.
+    // and of the pass state, split the COLUMNS of every pass (interleaved 512-column sweeps), evaluate the few
+    // candidate-vs-candidate pairs redundantly, and exchange the kill words through distributed shared memory after the resolve.
     // (CL = false compiles all of that out: one CTA per problem.)
     cg::cluster_group cluster = cg::this_cluster();
     const int C = CL ? (int)cluster.num_blocks() : 1, crank = CL ? (int)cluster.block_rank() : 0;
+    const bool split = CL && C > 1;  // the problem's columns are split over several CTAs
     const int p = blockIdx.x / C;
     const int n = problem_count(counts, p, nmax);
     const int W = (n + 31) / 32;
@@ -344,6 +344,18 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     }
     int cursor = 0;  // every box below it is decided
     unsigned my_tested = 0u, my_nonzero = 0u;
+#ifdef LG_LZ_TIMING  // developer build: cycles per phase of thread 0, accumulated into stats[8 + phase] (tools/lz_timing.py)
+    long long tmark = clock64();
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define LZ_MARK(ph)                      \
+    if (tid == 0) {                      \
+        const long long now_ = clock64(); \
+        tacc[ph] += now_ - tmark;        \
+        tmark = now_;                    \
+    }
+#else
+#define LZ_MARK(ph)
+#endif
 
     auto emit = [&](int g, int j, float ov, const float4* A, const float4* B) {
         const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);  // row = the higher-scoring box (kernel.cu:304)
@@ -377,10 +389,16 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             if (lane == 0) ng_s = min(found, G);
         }
         __syncthreads();
+        LZ_MARK(0)  // candidate search
         const int ng = ng_s;
         if (ng == 0) break;
         for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
+        // cluster: the candidates are decided in this pass either way, so they leave the alive bitmap now (every CTA clears its
+        // own copy) and the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately.
+        // (One CTA per problem: they stay alive until the end of the pass and are swept like every other column.)
+        if (split && tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));
         __syncthreads();
+        LZ_MARK(1)  // candidate records
         const int g0 = group[0];
         float4 ac[G];
         int gi[G];
@@ -388,6 +406,22 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         for (int g = 0; g < G; g++) {
             ac[g] = sA[(g < ng ? g : 0) * REC_F4 + REC_CULL];
             gi[g] = g < ng ? group[g] : 0x7fffffff;  // an unused slot is "after" every box: never tested
+        }
+        // ---- candidate g against the later candidates: EVERY CTA of a cluster evaluates these (at most G (G - 1) / 2) pairs
+        // itself, so each has the complete candidate-vs-candidate bits for the resolve without an exchange through DSMEM and
+        // the cluster barrier it would need
+        if (split && warp == 0) {
+            const bool a = lane < ng;
+            const int j = a ? group[lane] : 0;
+            const float4 cj = a ? sA[lane * REC_F4 + REC_CULL] : make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned mk[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const bool t = a && lane > g;  // group[] ascends: lane > g <=> a later box
+                my_tested += (t && crank == 0) ? 1u : 0u;
+                mk[g] = __ballot_sync(0xffffffffu, t && cull_survives(ac[g], cj));
+            }
+            push_survivors<16, G>(mk, lane, 0, 1, j, &qcount, queue);
         }
         // ---- rows of the candidates against every later alive box, a chunk of columns at a time
         int jw = ((g0 + 1) >> 5) << 5;
@@ -398,6 +432,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             const int room = (LZ_QCAP - qn) / G;  // columns that cannot overflow the queue
             const bool done = jw >= n;
             if (done || room < SWEEP) {  // single drain call site: mid-row when the queue is full, and at the end of the rows
+                LZ_MARK(2)  // cull sweeps
                 if (rn + qn > LZ_RARECAP) {
                     drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
                     __syncthreads();
@@ -407,6 +442,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                     qcount = 0;
                     st_heavy += (unsigned long long)qn;
                 }
+                LZ_MARK(3)  // polygon rounds (thread 0's share; the barrier that follows is charged to the next phase)
                 if (done) break;
                 continue;
             }
@@ -432,34 +468,20 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             jw += sweeps * C * SWEEP;
         }
         __syncthreads();
+        LZ_MARK(4)  // waiting for the last polygon round
         drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
         __syncthreads();
-        // ---- resolve the speculation in score order (warp 0: lane h holds candidate h's row; at most G ballots)
-        if (CL && C > 1) {  // a candidate's column lives in ONE CTA of the cluster: share the candidate-vs-candidate bits
-            if (warp == 0) {
-                for (int g = 0; g < ng; g++) {
-                    const int j = group[g];
-                    const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
-                    const unsigned by = __ballot_sync(0xffffffffu, hit);
-                    if (lane < C) *cluster.map_shared_rank(&xch[crank][g], lane) = by;
-                }
-            }
-            cluster.sync();
-        }
+        LZ_MARK(5)  // deferred pairs
+        // ---- resolve the speculation in score order (warp 0: lane h holds candidate h's row; at most G ballots); the
+        // candidate-vs-candidate bits are local in every CTA (see above)
         if (warp == 0) {
             const int jl = lane < ng ? group[lane] : 0;
             const int64_t ol = (lane < ng && order) ? order[base + jl] : (int64_t)jl;  // loads issued before the serial part
             unsigned km = 0u;
             for (int g = 0; g < ng; g++) {
-                unsigned by;  // earlier candidates whose row suppresses g
-                if (CL && C > 1) {
-                    by = 0u;
-                    for (int r = 0; r < C; r++) by |= xch[r][g];
-                } else {
-                    const int j = group[g];
-                    const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
-                    by = __ballot_sync(0xffffffffu, hit);
-                }
+                const int j = group[g];
+                const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
+                const unsigned by = __ballot_sync(0xffffffffu, hit);  // earlier candidates whose row suppresses g
                 if ((by & km) == 0u) km |= 1u << g;
             }
             const int nk = nk_s;
@@ -470,6 +492,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             }
         }
         __syncthreads();
+        LZ_MARK(6)  // resolve (+ cluster exchange)
         const int km = keptmask_s;
         for (int w = (g0 >> 5) + tid; w < W; w += NT) {
             unsigned kill = 0u;
@@ -488,10 +511,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 alive[w] &= ~kill;
             }
         }
-        __syncthreads();
-        if (tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));  // candidates are decided either way
+        if (!split) {
+            __syncthreads();
+            if (tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));  // candidates are decided either way
+        }
         cursor = group[ng - 1] + 1;
         if (CL && C > 1) cluster.sync();  // every CTA's kill words have landed everywhere before the next candidates are chosen
+        LZ_MARK(7)  // kill words (+ cluster sync)
     }
     // all threads left the loop together
     const int nk = nk_s;
@@ -510,6 +536,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             atomicAdd(stats + 2, (unsigned long long)my_nonzero);
         }
         if (tid == 0) atomicAdd(stats + 1, st_heavy);
+#ifdef LG_LZ_TIMING
+        if (tid == 0)
+            for (int ph = 0; ph < 8; ph++) atomicAdd(stats + 8 + ph, (unsigned long long)tacc[ph]);
+#endif
     }
 }
 
