@@ -14,7 +14,8 @@
 // (order-preserving score bits << 32 | ~index) in the workspace.  If no more than k pass -- the normal case with SECOND's
 // SCORE_THRESH -- they are all selected; otherwise an MSB-first radix select over the composites (8 bits per pass, stops as
 // soon as a digit group is taken whole) finds the k-th composite and a collect pass keeps the ones at or above it.  The
-// selected composites (<= 4096) are sorted in shared memory by a bitonic network and written out with their boxes.
+// selected composites (<= 4096) are sorted by a bitonic network (registers / warp shuffles / shared memory) and written
+// out with their boxes.
 #include "lg_common.cuh"
 
 namespace lg {
@@ -116,26 +117,59 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
         }
     }
     __syncthreads();
-    // ---- bitonic sort, descending, of the first S = pow2 >= cnt entries (padding = 0 sorts last)
-    int S = 1;
-    while (S < cnt) S <<= 1;
-    for (int i = cnt + tid; i < S; i += NT) s_sel[i] = 0ull;
+    // ---- bitonic sort, descending, of all KMAX slots (padding = 0 sorts last).  Every thread owns 4 consecutive elements in
+    // registers: exchange distances 1, 2 stay inside the thread, 4..64 go through warp shuffles, only distances >= 128 cross
+    // warps through shared memory (15 of the 78 stages need a CTA barrier)
+    for (int i = cnt + tid; i < KMAX; i += NT) s_sel[i] = 0ull;
     __syncthreads();
-    for (int kk = 2; kk <= S; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (S >> 1); t += NT) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
-                const int l = i | j;
-                const unsigned long long a = s_sel[i], b = s_sel[l];
-                const bool desc = (i & kk) == 0;
-                if (desc ? (a < b) : (a > b)) {
-                    s_sel[i] = b;
-                    s_sel[l] = a;
+    {
+        unsigned long long v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = s_sel[4 * tid + e];
+        auto keep = [](unsigned long long own, unsigned long long other, bool want_max) {
+            return (own > other) == want_max ? own : other;
+        };
+        for (int kk = 2; kk <= KMAX; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                if (j >= 128) {
+                    __syncthreads();  // the previous readers of s_sel are done
+#pragma unroll
+                    for (int e = 0; e < 4; e++) s_sel[4 * tid + e] = v[e];
+                    __syncthreads();
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int x = 4 * tid + e;
+                        const unsigned long long o = s_sel[x ^ j];
+                        v[e] = keep(v[e], o, ((x & j) == 0) == ((x & kk) == 0));
+                    }
+                } else if (j >= 4) {
+                    const int d = j >> 2;  // partner thread inside the warp
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int x = 4 * tid + e;
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], d);
+                        v[e] = keep(v[e], o, ((x & j) == 0) == ((x & kk) == 0));
+                    }
+                } else {
+                    // x = 4 tid + e: bits 0, 1 of x are e's, and kk >= 4 here unless kk == 2 (then (x & kk) tests bit 1 of e)
+                    unsigned long long w[4];
+                    if (j == 2) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) w[e] = keep(v[e], v[e ^ 2], ((e & 2) == 0) == (((4 * tid + e) & kk) == 0));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) w[e] = keep(v[e], v[e ^ 1], ((e & 1) == 0) == (((4 * tid + e) & kk) == 0));
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; e++) v[e] = w[e];
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; e++) s_sel[4 * tid + e] = v[e];
     }
+    __syncthreads();
     // ---- outputs
     if (tid == 0) counts[p] = cnt;
     const float* fb = boxes ? boxes + (int64_t)(p / problems_per_frame) * box_frame_stride : nullptr;
