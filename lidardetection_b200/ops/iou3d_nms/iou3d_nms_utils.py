@@ -123,18 +123,27 @@ def boxes_iou_max(boxes_a, boxes_b, kind='iou3d', rows=True, cols=False):
     return out
 
 
-def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE):
+def _nms_buffers(fn_name, P, N, dev, flags=_lib.LG_FLAG_NONE):
+    """outputs + scratch of one batched NMS call (allocated before the first launch of a step so that the launches follow
+    each other without host work in between)"""
+    keep = torch.empty((P, N), dtype=torch.int64, device=dev)
+    num = torch.zeros((P,), dtype=torch.int32, device=dev)
+    ws = None
+    if P > 0 and N > 0:
+        with torch.cuda.device(dev):
+            ws = _workspace(_lib.lib().lg_nms_workspace_bytes_ex(P, N, 1 if 'normal' in fn_name else 0, flags), dev)
+    return keep, num, ws
+
+
+def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE, buffers=None):
     """boxes (P, N, 7) cuda f32 contiguous; order (P, N) int64 or None; counts (P,) int32 or None."""
     P, N = boxes.shape[0], boxes.shape[1]
     dev = boxes.device
-    keep = torch.empty((P, N), dtype=torch.int64, device=dev)
-    num = torch.zeros((P,), dtype=torch.int32, device=dev)
+    keep, num, ws = buffers if buffers is not None else _nms_buffers(fn_name, P, N, dev, flags)
     if P == 0 or N == 0:
         return keep, num
     L = _lib.lib()
     with torch.cuda.device(dev):
-        ws_bytes = L.lg_nms_workspace_bytes_ex(P, N, 1 if 'normal' in fn_name else 0, flags)
-        ws = _workspace(ws_bytes, dev)
         rc = getattr(L, fn_name)(_lib.ptr(boxes), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), _lib.ptr(ws),
                                  ws.numel(), _lib.ptr(keep), _lib.ptr(num), flags, _lib.stream_ptr(dev))
     _lib.check(rc, fn_name)
@@ -208,8 +217,9 @@ def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE
         idx = torch.arange(b.shape[1], device=b.device).unsqueeze(0)
         scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
         counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
+    buffers = _nms_buffers(fn_name, b.shape[0], b.shape[1], b.device, flags)
     order = _argsort_desc(scores)
-    return _nms_call(fn_name, b, order, counts, thresh, flags)
+    return _nms_call(fn_name, b, order, counts, thresh, flags, buffers)
 
 
 def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False):
