@@ -14,8 +14,8 @@
 // (order-preserving score bits << 32 | ~index) in the workspace.  If no more than k pass -- the normal case with SECOND's
 // SCORE_THRESH -- they are all selected; otherwise an MSB-first radix select over the composites (8 bits per pass, stops as
 // soon as a digit group is taken whole) finds the k-th composite and a collect pass keeps the ones at or above it.  The
-// selected composites (<= 4096) are sorted by a bitonic network (registers / warp shuffles / shared memory) and written
-// out with their boxes.
+// selected composites (<= 4096, kept in ascending candidate index by ordered block-wide compaction) are sorted by a stable
+// 4-pass LSD radix sort on the score key in shared memory and written out with their boxes.
 #include "lg_common.cuh"
 
 namespace lg {
@@ -30,15 +30,93 @@ __device__ __forceinline__ unsigned long long compose(float v, unsigned idx) {
     return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
 }
 
-// warp-aggregated append: returns this lane's slot (valid only where pred), advancing *counter by the warp's count
-__device__ __forceinline__ int warp_append(bool pred, int* counter) {
+constexpr int NW = NT / 32;
+constexpr size_t SMEM_BYTES = 2 * (size_t)KMAX * sizeof(unsigned long long) + (size_t)NW * 256 * sizeof(uint16_t);  // 80 KB
+
+// Block-wide ORDERED append: thread t's element comes before thread t + 1's.  Returns the slot of this thread's element
+// (meaningful where pred) and advances `running` (a per-thread copy of the block-uniform count) by the block's total.
+// Contains two barriers; s_warp is 32 ints of shared scratch.
+__device__ __forceinline__ int ordered_append(const bool pred, int& running, int* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0u) return 0;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    const int c = s_warp[lane];  // NW == 32: one warp count per lane
+    int before = lane < warp ? c : 0, total = c;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, d);
+        total += __shfl_xor_sync(0xffffffffu, total, d);
+    }
+    const int slot = running + before + __popc(m & ((1u << lane) - 1u));
+    running += total;
+    __syncthreads();
+    return slot;
+}
+
+// Stable LSD radix sort (4 passes of 8 bits) of KMAX composites by DESCENDING score key (the high 32 bits); equal keys keep
+// their input order, which is ascending candidate index.  Warp w ranks elements [128 w, 128 w + 128) in position order with
+// match.any (striped: lane l, slice e <-> position 128 w + 32 e + l); per-warp digit counters are scanned (digit-major) into
+// scatter offsets.  Result in bufA.
+__device__ __forceinline__ void radix_sort_desc(unsigned long long* bufA, unsigned long long* bufB, uint16_t* cnt, int* s_warp) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned long long *src = bufA, *dst = bufB;
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 32 + 8 * pass;
+        for (int i = tid; i < NW * 256 / 2; i += NT) reinterpret_cast<uint32_t*>(cnt)[i] = 0u;
+        __syncthreads();
+        unsigned long long v[4];
+        int r[4], dg[4];
+        uint16_t* wc = cnt + warp * 256;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            v[e] = src[128 * warp + 32 * e + lane];
+            const int d = 255 - (int)((v[e] >> shift) & 255ull);  // larger key -> lower bin
+            dg[e] = d;
+            const unsigned m = __match_any_sync(0xffffffffu, d);
+            const int base = wc[d];
+            __syncwarp();
+            if (lane == __ffs(m) - 1) wc[d] = (uint16_t)(base + __popc(m));
+            __syncwarp();
+            r[e] = base + __popc(m & lt);
+        }
+        __syncthreads();
+        {   // exclusive scan of cnt in (digit, warp) order: thread t owns digit t >> 2, warps 8 (t & 3) .. + 7
+            const int d = tid >> 2, w0 = 8 * (tid & 3);
+            int c[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                c[k] = cnt[(w0 + k) * 256 + d];
+                sum += c[k];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, incl, dd);
+                if (lane >= dd) incl += o;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            const int wt = s_warp[lane];
+            int wbefore = lane < warp ? wt : 0;
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) wbefore += __shfl_xor_sync(0xffffffffu, wbefore, dd);
+            int run = wbefore + incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                cnt[(w0 + k) * 256 + d] = (uint16_t)run;
+                run += c[k];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; e++) dst[wc[dg[e]] + r[e]] = v[e];
+        __syncthreads();
+        unsigned long long* t = src;
+        src = dst;
+        dst = t;
+    }
 }
 
 __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict__ scores, const int64_t n, const int k, const float thresh,
@@ -47,26 +125,27 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
                                                           const int problems_per_frame, unsigned long long* __restrict__ ws,
                                                           int64_t* __restrict__ top_idx, int32_t* __restrict__ counts,
                                                           float* __restrict__ top_boxes) {
-    __shared__ unsigned long long s_sel[KMAX];
+    extern __shared__ unsigned long long smem_sel[];
+    unsigned long long* s_sel = smem_sel;          // KMAX composites
+    unsigned long long* s_alt = smem_sel + KMAX;   // the radix sort's second buffer
+    uint16_t* s_cnt = reinterpret_cast<uint16_t*>(smem_sel + 2 * KMAX);
     __shared__ int s_hist[256];
-    __shared__ int s_cnt, s_digit, s_want, s_stop;
+    __shared__ int s_warp[NW];
+    __shared__ int s_digit, s_want, s_stop;
     const int p = blockIdx.x, tid = threadIdx.x;
     const float* s = scores + (int64_t)p * n;
     unsigned long long* cand = ws + (int64_t)p * n;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    // ---- pass A: candidates that pass the threshold -> composites (any order)
+    // ---- pass A: candidates that pass the threshold -> composites, in ascending candidate index
+    int V = 0;
     for (int64_t i0 = 0; i0 < n; i0 += NT) {
         const int64_t i = i0 + tid;
         const float v = i < n ? __ldg(s + i) : 0.f;
         const bool ok = i < n && (use_thresh ? (v >= thresh) : true);
-        const int slot = warp_append(ok, &s_cnt);
+        const int slot = ordered_append(ok, V, s_warp);
         if (ok) cand[slot] = compose(v, (unsigned)i);
     }
     __syncthreads();
-    const int V = s_cnt;
     const int cnt = V < k ? V : k;
-    __syncthreads();
     if (V <= k) {
         for (int i = tid; i < V; i += NT) s_sel[i] = cand[i];
     } else {
@@ -105,71 +184,20 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             __syncthreads();
             if (stop) break;
         }
-        // composites are distinct, so exactly k of them are >= bound
-        if (tid == 0) s_cnt = 0;
-        __syncthreads();
+        // composites are distinct, so exactly k of them are >= bound; collected in ascending candidate index
+        int taken = 0;
         for (int i0 = 0; i0 < V; i0 += NT) {
             const int i = i0 + tid;
             const unsigned long long c = i < V ? cand[i] : 0ull;
             const bool ok = i < V && c >= bound;
-            const int slot = warp_append(ok, &s_cnt);
+            const int slot = ordered_append(ok, taken, s_warp);
             if (ok && slot < KMAX) s_sel[slot] = c;
         }
     }
-    __syncthreads();
-    // ---- bitonic sort, descending, of all KMAX slots (padding = 0 sorts last).  Every thread owns 4 consecutive elements in
-    // registers: exchange distances 1, 2 stay inside the thread, 4..64 go through warp shuffles, only distances >= 128 cross
-    // warps through shared memory (15 of the 78 stages need a CTA barrier)
+    // ---- sort: all KMAX slots (padding = 0 sorts last), descending score, ties in input order = ascending index
     for (int i = cnt + tid; i < KMAX; i += NT) s_sel[i] = 0ull;
     __syncthreads();
-    {
-        unsigned long long v[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) v[e] = s_sel[4 * tid + e];
-        auto keep = [](unsigned long long own, unsigned long long other, bool want_max) {
-            return (own > other) == want_max ? own : other;
-        };
-        for (int kk = 2; kk <= KMAX; kk <<= 1) {
-            for (int j = kk >> 1; j > 0; j >>= 1) {
-                if (j >= 128) {
-                    __syncthreads();  // the previous readers of s_sel are done
-#pragma unroll
-                    for (int e = 0; e < 4; e++) s_sel[4 * tid + e] = v[e];
-                    __syncthreads();
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int x = 4 * tid + e;
-                        const unsigned long long o = s_sel[x ^ j];
-                        v[e] = keep(v[e], o, ((x & j) == 0) == ((x & kk) == 0));
-                    }
-                } else if (j >= 4) {
-                    const int d = j >> 2;  // partner thread inside the warp
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int x = 4 * tid + e;
-                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], d);
-                        v[e] = keep(v[e], o, ((x & j) == 0) == ((x & kk) == 0));
-                    }
-                } else {
-                    // x = 4 tid + e: bits 0, 1 of x are e's, and kk >= 4 here unless kk == 2 (then (x & kk) tests bit 1 of e)
-                    unsigned long long w[4];
-                    if (j == 2) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) w[e] = keep(v[e], v[e ^ 2], ((e & 2) == 0) == (((4 * tid + e) & kk) == 0));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) w[e] = keep(v[e], v[e ^ 1], ((e & 1) == 0) == (((4 * tid + e) & kk) == 0));
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; e++) v[e] = w[e];
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < 4; e++) s_sel[4 * tid + e] = v[e];
-    }
-    __syncthreads();
+    radix_sort_desc(s_sel, s_alt, s_cnt, s_warp);
     // ---- outputs
     if (tid == 0) counts[p] = cnt;
     const float* fb = boxes ? boxes + (int64_t)(p / problems_per_frame) * box_frame_stride : nullptr;
@@ -242,7 +270,9 @@ extern "C" int lg_select_topk(const float* scores, int num_problems, int64_t n, 
         return LG_ERR_WORKSPACE;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    sel::select_topk_kernel<<<(unsigned)num_problems, sel::NT, 0, st>>>(scores, n, k, score_thresh, use_thresh, boxes, box_frame_stride,
+    int rc = set_smem(sel::select_topk_kernel, sel::SMEM_BYTES);
+    if (rc) return rc;
+    sel::select_topk_kernel<<<(unsigned)num_problems, sel::NT, sel::SMEM_BYTES, st>>>(scores, n, k, score_thresh, use_thresh, boxes, box_frame_stride,
                                                                         box_row_stride, problems_per_frame,
                                                                         static_cast<unsigned long long*>(ws), top_idx, counts, top_boxes);
     return check_launch("select_topk_kernel");

@@ -155,7 +155,7 @@ LG_SELECT_MAX_K = 4096
 
 def _argsort_desc(scores):
     """(P, N) scores -> (P, N) int64 indices in descending score (the wrapper's `scores.sort(descending=True)[1]`,
-    iou3d_nms_utils.py:92).  Up to 4096 float32 scores per problem: lg_select_topk (one CTA per problem, bitonic sort in shared
+    iou3d_nms_utils.py:92).  Up to 4096 float32 scores per problem: lg_select_topk (one CTA per problem, stable radix sort in shared
     memory, equal scores by ascending index) when the batch has at most two problems per SM; otherwise torch.sort."""
     P, N = scores.shape
     if not (scores.is_cuda and scores.dtype == torch.float32 and 0 < N <= LG_SELECT_MAX_K and 0 < P <= 2 * 148):  # one CTA per problem: a
