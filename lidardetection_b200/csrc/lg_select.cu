@@ -58,7 +58,8 @@ __device__ __forceinline__ int ordered_append(const bool pred, int& running, int
 // their input order, which is ascending candidate index.  Warp w ranks elements [128 w, 128 w + 128) in position order with
 // match.any (striped: lane l, slice e <-> position 128 w + 32 e + l); per-warp digit counters are scanned (digit-major) into
 // scatter offsets.  Result in bufA.
-__device__ __forceinline__ void radix_sort_desc(unsigned long long* bufA, unsigned long long* bufB, uint16_t* cnt, int* s_warp) {
+// E = elements per thread (1, 2 or 4): the first 1024 E slots are sorted (warp w ranks [32 E w, 32 E (w + 1))).
+__device__ __forceinline__ void radix_sort_desc(unsigned long long* bufA, unsigned long long* bufB, uint16_t* cnt, int* s_warp, const int E) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
     unsigned long long *src = bufA, *dst = bufB;
@@ -71,15 +72,17 @@ __device__ __forceinline__ void radix_sort_desc(unsigned long long* bufA, unsign
         uint16_t* wc = cnt + warp * 256;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            v[e] = src[128 * warp + 32 * e + lane];
-            const int d = 255 - (int)((v[e] >> shift) & 255ull);  // larger key -> lower bin
-            dg[e] = d;
-            const unsigned m = __match_any_sync(0xffffffffu, d);
-            const int base = wc[d];
-            __syncwarp();
-            if (lane == __ffs(m) - 1) wc[d] = (uint16_t)(base + __popc(m));
-            __syncwarp();
-            r[e] = base + __popc(m & lt);
+            if (e < E) {  // block-uniform
+                v[e] = src[32 * E * warp + 32 * e + lane];
+                const int d = 255 - (int)((v[e] >> shift) & 255ull);  // larger key -> lower bin
+                dg[e] = d;
+                const unsigned m = __match_any_sync(0xffffffffu, d);
+                const int base = wc[d];
+                __syncwarp();
+                if (lane == __ffs(m) - 1) wc[d] = (uint16_t)(base + __popc(m));
+                __syncwarp();
+                r[e] = base + __popc(m & lt);
+            }
         }
         __syncthreads();
         {   // exclusive scan of cnt in (digit, warp) order: thread t owns digit t >> 2, warps 8 (t & 3) .. + 7
@@ -111,7 +114,8 @@ __device__ __forceinline__ void radix_sort_desc(unsigned long long* bufA, unsign
         }
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 4; e++) dst[wc[dg[e]] + r[e]] = v[e];
+        for (int e = 0; e < 4; e++)
+            if (e < E) dst[wc[dg[e]] + r[e]] = v[e];
         __syncthreads();
         unsigned long long* t = src;
         src = dst;
@@ -194,10 +198,11 @@ __global__ void __launch_bounds__(NT) select_topk_kernel(const float* __restrict
             if (ok && slot < KMAX) s_sel[slot] = c;
         }
     }
-    // ---- sort: all KMAX slots (padding = 0 sorts last), descending score, ties in input order = ascending index
-    for (int i = cnt + tid; i < KMAX; i += NT) s_sel[i] = 0ull;
+    // ---- sort the first 1024 E >= cnt slots (padding = 0 sorts last): descending score, ties in input order = ascending index
+    const int E = cnt <= NT ? 1 : (cnt <= 2 * NT ? 2 : 4);
+    for (int i = cnt + tid; i < NT * E; i += NT) s_sel[i] = 0ull;
     __syncthreads();
-    radix_sort_desc(s_sel, s_alt, s_cnt, s_warp);
+    radix_sort_desc(s_sel, s_alt, s_cnt, s_warp, E);
     // ---- outputs
     if (tid == 0) counts[p] = cnt;
     const float* fb = boxes ? boxes + (int64_t)(p / problems_per_frame) * box_frame_stride : nullptr;
