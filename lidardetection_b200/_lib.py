@@ -106,6 +106,22 @@ def check(rc, what):
         raise LidarGeomError(f"{what} failed with status {rc}: {msg}")
 
 
+def require_usable_cuda(what):
+    """The *_cpu entry points of the reference API are served by the GPU (no CPU fallback by contract).  The reference calls
+    them from dataset code that may run in forked DataLoader workers (database_sampler.py:212-216, box_utils.py:85); CUDA
+    cannot be initialised in a process forked from one that already holds a context, so say so instead of crashing inside
+    the driver ("DataLoader workers")."""
+    import torch
+
+    if torch.cuda._is_in_bad_fork():
+        raise LidarGeomError(
+            f"{what}: this process was forked from a parent that had already initialised CUDA, so it cannot use the GPU.  {what} runs on "
+            "the GPU here (there is no CPU fallback).  Start the workers with the 'spawn' or 'forkserver' method -- "
+            "DataLoader(..., multiprocessing_context='spawn') -- or call it with num_workers=0; see INTEGRATION.md.")
+    if not torch.cuda.is_available():
+        raise LidarGeomError(f"{what}: no CUDA device is visible; {what} runs on the GPU here (there is no CPU fallback)")
+
+
 def ptr(t):
     """device/host pointer of a torch tensor (None -> NULL)"""
     return None if t is None else C.c_void_p(t.data_ptr())

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "liblidargeom.so")
 SOURCES = ["lg_api.cu", "lg_iou.cu", "lg_nms.cu", "lg_points.cu", "lg_pool.cu", "lg_kitti.cu", "lg_select.cu"]
-HEADERS = ["lg_common.cuh", "lg_geom.cuh", "lg_strip.cuh", "lg_pib.cuh", os.path.join("..", "..", "include", "lidargeom.h")]
+HEADERS = ["lg_common.cuh", "lg_geom.cuh", "lg_trig.cuh", "lg_strip.cuh", "lg_pib.cuh", os.path.join("..", "..", "include", "lidargeom.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -30,8 +30,21 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
     extra = os.environ.get("LG_EXTRA_NVCC_FLAGS", "").split()  # developer experiments only (e.g. -DLG_LZ_G=4)
-    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
-    subprocess.check_call(cmd)
+    # one nvcc per translation unit, side by side (the units are independent: no relocatable device code), then one link
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in FLAGS if f != "--shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        subprocess.check_call([NVCC] + cflags + ["-c", "-o", obj, os.path.join(HERE, src)])
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([NVCC] + FLAGS + ["-o", OUT] + objs)
     return OUT
 
 

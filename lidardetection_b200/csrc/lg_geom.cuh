@@ -27,12 +27,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-// full-precision libdevice sinf/cosf (no -use_fast_math); the CPU-only test tier re-points these at the
-// oracle's restatement of libdevice when it compiles this header for the host (tests/host_emu/)
-#ifndef LG_SINF
-#define LG_SINF(x) sinf(x)
-#define LG_COSF(x) cosf(x)
-#endif
+// sinf / cosf per arithmetic flavor (lg_trig.cuh): FL = 1 full-precision libdevice (no -use_fast_math; the CPU-only test tier
+// re-points LG_SINF / LG_COSF at the oracle's restatement of libdevice when it compiles this header for the host,
+// tests/host_emu/), FL = 0 glibc's double-precision algorithm restated for the device
+#include "lg_trig.cuh"
 #ifndef LG_ATAN2F
 #define LG_ATAN2F(y, x) atan2f((y), (x))
 #endif
@@ -85,7 +83,7 @@ __device__ __forceinline__ void make_record(const float* __restrict__ box, float
     const float cx = box[0], cy = box[1], z = box[2], dx = box[3], dy = box[4], dz = box[5], th = box[6];
     const float hx = __fmul_rn(dx, 0.5f), hy = __fmul_rn(dy, 0.5f);
     const float x1 = __fsub_rn(cx, hx), x2 = __fadd_rn(cx, hx), y1 = __fsub_rn(cy, hy), y2 = __fadd_rn(cy, hy);
-    const float co = LG_COSF(th), si = LG_SINF(th);
+    const float co = trig_cos<FL>(th), si = trig_sin<FL>(th);
     // rotate_around_center works on (corner - centre), which is NOT exactly +-h after rounding
     const float ex1 = __fsub_rn(x1, cx), ex2 = __fsub_rn(x2, cx), ey1 = __fsub_rn(y1, cy), ey2 = __fsub_rn(y2, cy);
     float X[4], Y[4];
@@ -101,7 +99,7 @@ __device__ __forceinline__ void make_record(const float* __restrict__ box, float
             Y[k] = __fadd_rn(__fadd_rn(__fmul_rn(ddx[k], si), __fmul_rn(ddy[k], co)), cy);
         }
     }
-    const float cn = LG_COSF(-th), sn = LG_SINF(-th);
+    const float cn = trig_cos<FL>(-th), sn = trig_sin<FL>(-th);
     const float tx = __fadd_rn(hx, 1e-2f), ty = __fadd_rn(hy, 1e-2f);
     const float area = __fmul_rn(dx, dy);
     // Conservative exact-zero cull.  A pair yields a polygon vertex only if an edge of

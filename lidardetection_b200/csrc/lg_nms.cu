@@ -344,6 +344,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     }
     int cursor = 0;  // every box below it is decided
     unsigned my_tested = 0u, my_nonzero = 0u;
+    // a peer's shared memory may only be touched once that peer has started and initialised its bitmap
+    if (CL && C > 1) cluster.sync();
 #ifdef LG_LZ_TIMING  // developer build: cycles per phase of thread 0, accumulated into stats[8 + phase] (tools/lz_timing.py)
     long long tmark = clock64();
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -391,7 +393,13 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         __syncthreads();
         LZ_MARK(0)  // candidate search
         const int ng = ng_s;
-        if (ng == 0) break;
+        // cluster: this CTA has chosen its candidates (every CTA picks the same ones from identical bitmaps); peers wait for
+        // this arrival before their kill words of this pass may touch our bitmap (barrier_wait below)
+        if (CL && C > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        if (ng == 0) {
+            if (CL && C > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            break;
+        }
         for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
         // cluster: the candidates are decided in this pass either way, so they leave the alive bitmap now (every CTA clears its
         // own copy) and the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately.
@@ -494,6 +502,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         __syncthreads();
         LZ_MARK(6)  // resolve (+ cluster exchange)
         const int km = keptmask_s;
+        if (CL && C > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // every peer has its candidates of this pass
         for (int w = (g0 >> 5) + tid; w < W; w += NT) {
             unsigned kill = 0u;
 #pragma unroll

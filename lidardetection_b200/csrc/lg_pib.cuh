@@ -22,9 +22,10 @@
 namespace lg {
 
 // record: r0 = (cx, cy, cz, dz/2)   r1 = (cosa, sina, tx, ty)
+template <int FL>
 __device__ __forceinline__ void make_pib_record(const float* __restrict__ box, const float margin, float4& r0, float4& r1) {
     const float cx = box[0], cy = box[1], cz = box[2], dx = box[3], dy = box[4], dz = box[5], rz = box[6];
-    const float cosa = LG_COSF(-rz), sina = LG_SINF(-rz);
+    const float cosa = trig_cos<FL>(-rz), sina = trig_sin<FL>(-rz);
     const float tx = __double2float_ru((double)dx / 2.0 + (double)margin);
     const float ty = __double2float_ru((double)dy / 2.0 + (double)margin);
     // (double)|z-cz| > (double)dz/2.0  <=>  |z-cz| > RD(dz/2); dz/2 is exact in float except for

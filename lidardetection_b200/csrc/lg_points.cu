@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
     bool bounded = true;
     for (int k = tid; k < T; k += NT) {
         float4 r0, r1;
-        make_pib_record(fb + k * 7, 1e-5f, r0, r1);
+        make_pib_record<FL>(fb + k * 7, 1e-5f, r0, r1);
         srec[2 * k] = r0;
         srec[2 * k + 1] = r1;
         float ex, ey;
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(PIB_THREADS)
     const int nbx = (int)min((int64_t)PIBM_BOXES, n - box0);
     if (tid < nbx) {
         float4 r0, r1;
-        make_pib_record(boxes + (box0 + tid) * 7, margin, r0, r1);
+        make_pib_record<FL>(boxes + (box0 + tid) * 7, margin, r0, r1);
         srec[2 * tid] = r0;
         srec[2 * tid + 1] = r1;
     }

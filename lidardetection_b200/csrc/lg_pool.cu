@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1)
     const float* box = rois + (size_t)blockIdx.x * 7;
     int32_t* lists = pts_idx + (size_t)blockIdx.x * V * max_pts;
     float4 r0, r1;
-    make_pib_record(box, 1e-5f, r0, r1);
+    make_pib_record<1>(box, 1e-5f, r0, r1);
     const float dx = box[3], dy = box[4], dz = box[5];
     const int cap = max_pts - 1;  // slot 0 is the counter
     if (smem_cnt)
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(RP_THREADS, 2)
     const float* P = xyz + (size_t)blockIdx.y * n * 3;
     const float* F = feat + (size_t)blockIdx.y * n * c;
     float4 r0, r1;
-    make_pib_record(boxes + bj * 7, 1e-5f, r0, r1);
+    make_pib_record<1>(boxes + bj * 7, 1e-5f, r0, r1);
     const int64_t k0 = ((int64_t)crank * RP_WARPS + warp) * seg;
     const int k1 = (int)min(k0 + seg, (int64_t)n);
     int cnt = 0;

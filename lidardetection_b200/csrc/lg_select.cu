@@ -25,7 +25,9 @@ constexpr int NT = 1024;
 constexpr int KMAX = 4096;
 
 __device__ __forceinline__ unsigned long long compose(float v, unsigned idx) {
-    const unsigned b = __float_as_uint(v);
+    unsigned b = __float_as_uint(v);
+    if (b == 0x80000000u) b = 0u;          // -0.0 == +0.0, as every comparison-based sort (torch.sort / topk) sees them
+    if (v != v) b = 0x7FFFFFFFu;           // any NaN, whatever its sign bit, ranks above +inf (torch's order)
     const unsigned key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // larger float -> larger unsigned
     return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
 }

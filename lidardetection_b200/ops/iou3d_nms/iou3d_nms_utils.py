@@ -53,6 +53,7 @@ def boxes_bev_iou_cpu(boxes_a, boxes_b):
     boxes_b, is_numpy = common_utils.check_numpy_to_torch(boxes_b)
     assert not (boxes_a.is_cuda or boxes_b.is_cuda), 'Only support CPU tensors'
     assert boxes_a.shape[1] == 7 and boxes_b.shape[1] == 7
+    _lib.require_usable_cuda('boxes_bev_iou_cpu')
     dev = torch.device('cuda', torch.cuda.current_device())
     ans = _iou_call('lg_boxes_iou_bev', boxes_a.to(dev), boxes_b.to(dev), flags=_lib.LG_FLAG_STRICT_FP32)
     ans_iou = ans.cpu().to(boxes_a.dtype)
@@ -153,14 +154,26 @@ def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE, bu
 LG_SELECT_MAX_K = 4096
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 def _argsort_desc(scores):
     """(P, N) scores -> (P, N) int64 indices in descending score (the wrapper's `scores.sort(descending=True)[1]`,
     iou3d_nms_utils.py:92).  Up to 4096 float32 scores per problem: lg_select_topk (one CTA per problem, stable radix sort in shared
-    memory, equal scores by ascending index) when the batch has at most two problems per SM; otherwise torch.sort."""
+    memory) when the batch has at most two problems per SM; otherwise torch's stable segmented sort.  ONE ordering rule on both
+    branches: equal scores by ascending index, -0.0 == +0.0, NaN first -- so nms_gpu(frame) and nms_gpu_batched(frames) agree
+    whatever the batch size."""
     P, N = scores.shape
-    if not (scores.is_cuda and scores.dtype == torch.float32 and 0 < N <= LG_SELECT_MAX_K and 0 < P <= 2 * 148):  # one CTA per problem: a
-        # batch of thousands of small problems is better served by torch's segmented sort (measured on nms_cfg5)
-        return scores.sort(1, descending=True)[1].contiguous()
+    if not (scores.is_cuda and scores.dtype == torch.float32 and 0 < N <= LG_SELECT_MAX_K and 0 < P <= 2 * _sm_count(scores.device)):
+        # one CTA per problem: a batch of thousands of small problems is better served by torch's segmented sort (measured on nms_cfg5)
+        return scores.sort(1, descending=True, stable=True)[1].contiguous()
     L = _lib.lib()
     dev = scores.device
     sc = scores.contiguous()

@@ -25,6 +25,7 @@ def points_in_boxes_cpu(points, boxes):
     assert points.shape[1] == 3
     points, is_numpy = common_utils.check_numpy_to_torch(points)
     boxes, is_numpy = common_utils.check_numpy_to_torch(boxes)
+    _lib.require_usable_cuda('points_in_boxes_cpu')
     dev = torch.device('cuda', torch.cuda.current_device())
     out = points_in_boxes_mask_gpu(points.float().to(dev), boxes.float().to(dev), margin=1e-2,
                                    flags=_lib.LG_FLAG_STRICT_FP32)
@@ -126,7 +127,7 @@ class RoIAwarePool3dFunction(Function):
 
 def roiaware_pool3d_forward(rois, pts, pts_feature, out_size, max_pts_each_voxel=128, pool_method='max'):
     """The extension call of the reference (roiaware_pool3d_cuda.forward, roiaware_pool3d.cpp:25-62) with the three outputs
-    returned instead of pre-allocated: pooled (N, ox, oy, oz, C) f32, argmax (same shape, int32; None for 'avg', which never
+    returned instead of pre-allocated: pooled (N, ox, oy, oz, C) f32, argmax (same shape, int32; zeros for 'avg', which never
     reads it), pts_idx_of_voxels (N, ox, oy, oz, max_pts) int32."""
     assert rois.is_cuda and pts.is_cuda and pts_feature.is_cuda
     out_x, out_y, out_z = (out_size,) * 3 if isinstance(out_size, int) else out_size
@@ -134,7 +135,8 @@ def roiaware_pool3d_forward(rois, pts, pts_feature, out_size, max_pts_each_voxel
     n, m, c = r.shape[0], p.shape[0], f.shape[-1]
     method = {'max': 0, 'avg': 1}[pool_method]
     pooled = torch.empty((n, out_x, out_y, out_z, c), dtype=torch.float32, device=f.device)
-    argmax = torch.empty((n, out_x, out_y, out_z, c), dtype=torch.int32, device=f.device) if method == 0 else None
+    # allocated for both methods, as the reference does (roiaware_pool3d_utils.py:85); avg pooling leaves it zero-filled
+    argmax = torch.empty((n, out_x, out_y, out_z, c), dtype=torch.int32, device=f.device)
     pts_idx = torch.empty((n, out_x, out_y, out_z, max_pts_each_voxel), dtype=torch.int32, device=f.device)
     L = _lib.lib()
     with torch.cuda.device(f.device):

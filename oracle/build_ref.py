@@ -45,10 +45,34 @@ EXTS = {
 }
 
 
+# the reference's own Python wrappers of the two extensions, byte-compiled (py_compile) into oracle/_ref/py/*.pyc so that the
+# route-B test (tests/test_route_b.py) can run the UNMODIFIED reference Python on the GPU box, where /root/reference does
+# not exist; compiled outputs only, no source is copied
+PY_MODULES = {
+    "iou3d_nms_utils": "pcdet/ops/iou3d_nms/iou3d_nms_utils.py",
+    "roiaware_pool3d_utils": "pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py",
+}
+
+
+def build_py():
+    import py_compile
+
+    out = os.path.join(OUT, "py")
+    os.makedirs(out, exist_ok=True)
+    for name, rel in PY_MODULES.items():
+        py_compile.compile(os.path.join(REF_ROOT, rel), cfile=os.path.join(out, name + ".pyc"), dfile=rel, doraise=True)
+    print(f"[build_ref] byte-compiled {sorted(PY_MODULES)} into {out}")
+
+
+def py_built():
+    return all(os.path.exists(os.path.join(OUT, "py", n + ".pyc")) for n in PY_MODULES)
+
+
 def build(verbose=False):
     if not os.path.isdir(REF_ROOT):
         print(f"[build_ref] {REF_ROOT} not present; keeping whatever is prebuilt in {OUT}")
         return False
+    build_py()
     os.environ["TORCH_CUDA_ARCH_LIST"] = "10.0a"
     from torch.utils.cpp_extension import load
 

@@ -41,3 +41,44 @@ def roipoint_pool3d_cuda():
 
 def available():
     return iou3d_nms_cuda() is not None and roiaware_pool3d_cuda() is not None
+
+
+def reference_python(module, ext, ext_name, package):
+    """The reference's OWN Python wrapper module (`iou3d_nms_utils` / `roiaware_pool3d_utils`, byte-compiled unmodified by
+    oracle/build_ref.py into oracle/_ref/py/) imported inside a synthetic package `package`, with `ext` standing where the
+    module does `from . import <ext_name>` and a 4-line stub for `...utils.common_utils` (the real one drags in the whole
+    detector framework).  Returns None when the bytecode is not there."""
+    import sys
+    import types
+
+    path = os.path.join(_HERE, "_ref", "py", module + ".pyc")
+    if not os.path.exists(path):
+        return None
+    sub = {"iou3d_nms_utils": "iou3d_nms", "roiaware_pool3d_utils": "roiaware_pool3d"}[module]
+    for name in (package, package + ".ops", package + ".utils", f"{package}.ops.{sub}"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    cu = types.ModuleType(package + ".utils.common_utils")
+
+    def check_numpy_to_torch(x):  # pcdet/utils/common_utils.py:46-49
+        import numpy as np
+        import torch
+
+        if isinstance(x, np.ndarray):
+            return torch.from_numpy(x).float(), True
+        return x, False
+
+    cu.check_numpy_to_torch = check_numpy_to_torch
+    sys.modules[package + ".utils.common_utils"] = cu
+    sys.modules[package + ".utils"].common_utils = cu
+    sys.modules[f"{package}.ops.{sub}.{ext_name}"] = ext
+    setattr(sys.modules[f"{package}.ops.{sub}"], ext_name, ext)
+    full = f"{package}.ops.{sub}.{module}"
+    loader = importlib.machinery.SourcelessFileLoader(full, path)
+    spec = importlib.util.spec_from_loader(full, loader)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[full] = mod
+    loader.exec_module(mod)
+    return mod

@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, "libemu_geom.so")
 SRCS = [os.path.join(HERE, "emu_geom.cpp")]
 DEPS = SRCS + [os.path.join(HERE, "lg_host_emu.h"), os.path.join(ROOT, "lidardetection_b200", "csrc", "lg_geom.cuh"),
-               os.path.join(ROOT, "lidardetection_b200", "csrc", "lg_pib.cuh")]
+               os.path.join(ROOT, "lidardetection_b200", "csrc", "lg_pib.cuh"),
+               os.path.join(ROOT, "lidardetection_b200", "csrc", "lg_trig.cuh")]
 
 
 def build(force=False):

@@ -96,7 +96,7 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
     float lo_x = INFINITY, hi_x = -INFINITY, lo_y = INFINITY, hi_y = -INFINITY, sum_ext = 0.f, nv = 0.f;
     bool bounded = true;
     for (int k = 0; k < T; k++) {
-        make_pib_record(boxes + k * 7, 1e-5f, rec[2 * k], rec[2 * k + 1]);
+        make_pib_record<1>(boxes + k * 7, 1e-5f, rec[2 * k], rec[2 * k + 1]);
         float ex, ey;
         if (pib_footprint(rec[2 * k], rec[2 * k + 1], ex, ey, bounded)) {
             lo_x = fminf(lo_x, rec[2 * k].x - ex); hi_x = fmaxf(hi_x, rec[2 * k].x + ex);
@@ -154,4 +154,36 @@ extern "C" long long emu_points_in_boxes(const float* boxes, int T, const float*
         out[p] = r;
     }
     return tests;
+}
+
+// ---- the device restatement of glibc's sinf / cosf (lg_trig.cuh), for the sweep against the host's libm ----
+extern "C" void emu_glibc_sincosf(const float* x, long long n, float* out, int want_cos) {
+    for (long long i = 0; i < n; i++) out[i] = glibc_sincosf(x[i], want_cos);
+}
+// sweep over float bit patterns first, first + stride, ... (count of them); returns the number of results whose bits differ
+// from the host libm's sinf / cosf (NaN results compare equal to each other)
+extern "C" long long emu_glibc_sweep(unsigned first, unsigned stride, long long count, unsigned* first_bad) {
+    long long bad = 0;
+    unsigned u = first;
+    for (long long i = 0; i < count; i++, u += stride) {
+        const float f = __uint_as_float(u);
+        const float s0 = sinf(f), s1 = glibc_sincosf(f, 0), c0 = cosf(f), c1 = glibc_sincosf(f, 1);
+        const bool bs = __float_as_uint(s0) != __float_as_uint(s1) && !(s0 != s0 && s1 != s1);
+        const bool bc = __float_as_uint(c0) != __float_as_uint(c1) && !(c0 != c0 && c1 != c1);
+        if ((bs || bc) && bad++ == 0 && first_bad) *first_bad = u;
+    }
+    return bad;
+}
+
+// all-pairs 0/1 mask of points_in_boxes_cpu (pib_mask_kernel), flavor 0 = the reference CPU build
+extern "C" void emu_points_mask(const float* boxes, int T, const float* pts, long long M, int32_t* out, int flavor) {
+    for (int k = 0; k < T; k++) {
+        float4 r0, r1;
+        if (flavor) make_pib_record<1>(boxes + k * 7, 1e-5f, r0, r1);
+        else make_pib_record<0>(boxes + k * 7, 1e-5f, r0, r1);
+        for (long long p = 0; p < M; p++) {
+            const float x = pts[3 * p], y = pts[3 * p + 1], z = pts[3 * p + 2];
+            out[(long long)k * M + p] = (flavor ? pt_in_box<1>(x, y, z, r0, r1) : pt_in_box<0>(x, y, z, r0, r1)) ? 1 : 0;
+        }
+    }
 }

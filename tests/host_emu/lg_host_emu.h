@@ -30,6 +30,12 @@ static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fdividef(float a, float b) { return a / b; }  // approximate on the device: ordering keys only
 static inline float __frcp_rn(float a) { return 1.0f / a; }
+// double-precision intrinsics of lg_trig.cuh (the restatement of glibc's sinf / cosf)
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline int __double2int_rz(double a) { return (int)a; }
+static inline double __ll2double_rn(long long a) { return (double)a; }
+static inline float __double2float_rn(double a) { return (float)a; }
 static inline unsigned __float2uint_rn(float x) { return (unsigned)llrintf(x); }
 static inline int __float2int_rd(float x) { return (int)floorf(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -87,10 +87,11 @@ def test_iou_family_vs_oracle(seed, centre, pri, n, m):
     n3 = assert_iou_close(U.boxes_iou3d_gpu(ta, tb).cpu().numpy(), O.boxes_iou3d(a, b, O.FLAVOR_CUDA), "iou3d")
     # the arithmetic contract is mirrored exactly; only vertex-order ties may move last bits
     assert max(nb, no, n3) <= max(1, n * m // 2000)
-    # strict (CPU-build) arithmetic vs the CPU flavor: differs only through libdevice vs glibc trig
+    # strict (CPU-build) arithmetic vs the CPU flavor: un-contracted FP32 and glibc's sinf / cosf restated on the device
+    # (lg_trig.cuh) -- the same bits, except where a vertex order hangs on the last bit of atan2f (libdevice here, glibc there)
     strict = U._iou_call("lg_boxes_iou_bev", ta, tb, flags=_lib.LG_FLAG_STRICT_FP32).cpu().numpy()
-    d = np.abs(strict - O.boxes_iou_bev(a, b, O.FLAVOR_CPU))
-    assert d.max() <= 5e-5  # reference CPU vs reference GPU disagree at this level themselves
+    ns = assert_iou_close(strict, O.boxes_iou_bev(a, b, O.FLAVOR_CPU), "strict iou_bev vs CPU flavor")
+    assert ns <= max(1, n * m // 2000)
 
 
 @pytest.mark.parametrize("name", IOU_SETS)
@@ -172,11 +173,53 @@ def test_nms_lazy_equals_full_mask_equals_oracle(n, thresh, seed):
         got = k_lazy[f, : int(n_lazy[f])].cpu().numpy()
         inv = np.empty(n, np.int64)
         inv[order] = np.arange(n)
-        if f < 2:
+        if f < 2 or not R.available():
             assert np.array_equal(got, want), explain_nms_mismatch(boxes[f][order], inv[got], inv[want], thresh, False)
-        elif not np.array_equal(got, want):
-            # near-duplicates sit on vertex-order ties (libdevice vs glibc atan2f): report, do not require
-            print("near-duplicate frame differs from the CPU oracle:", explain_nms_mismatch(boxes[f][order], inv[got], inv[want], thresh, False))
+        else:
+            # near-duplicates sit on vertex-order ties, where the oracle's glibc atan2f is not the authority: the reference
+            # kernel itself (libdevice atan2f), run live on this GPU, is (iou3d_nms.cpp:90-136)
+            bs = tb[f][torch.from_numpy(order).to(dev())].contiguous()
+            keep = torch.LongTensor(n)
+            nk = R.iou3d_nms_cuda().nms_gpu(bs, keep, thresh)
+            want_live = order[keep[:nk].numpy()]
+            assert np.array_equal(got, want_live), explain_nms_mismatch(boxes[f][order], inv[got], inv[want_live], thresh, False)
+
+
+def test_cfg5_multihead_full_size_small_problem_variant():
+    """BASELINE configs[4] at full size: NuScenes CBGS multi-head NMS, 256 frames x 10 classes = 2560 problems of 1000 boxes,
+    thresh 0.2 (cbgs_second_multihead.yaml:196-206, model_nms_utils.py:28-65).  2560 >= 2 x SMs problems of <= 1536 boxes
+    launch nms_lazy_kernel<., false, 256> (two 256-thread CTAs per SM) behind torch's segmented sort -- the variant
+    bench.py --workload nms_cfg5 times; sub-batches of 160 problems take the 512-thread / lg_select_topk variant."""
+    b, s = synth.cfg5(256, 10, 1000, seed=synth.SEEDS["cfg5"])
+    boxes, scores = b.reshape(-1, 1000, 7), s.reshape(-1, 1000)
+    P = boxes.shape[0]
+    assert P == 2560
+    tb, ts = cu(boxes), cu(scores)
+    keep, num = U.nms_gpu_batched(tb, ts, 0.2)
+    assert keep.shape == (P, 1000) and num.shape == (P,)
+    num_h, keep_h = num.cpu().numpy(), keep.cpu().numpy()
+    # (1) the oracle on a stride of problems
+    for p in range(0, P, 97):
+        order = ts[p].sort(0, descending=True, stable=True)[1].cpu().numpy()
+        want = O.nms(boxes[p], scores[p], 0.2, flavor=O.FLAVOR_CUDA, order=order)
+        got = keep_h[p, : num_h[p]]
+        inv = np.empty(1000, np.int64)
+        inv[order] = np.arange(1000)
+        assert np.array_equal(got, want), (p, explain_nms_mismatch(boxes[p][order], inv[got], inv[want], 0.2, False))
+        assert (keep_h[p, num_h[p]:] == -1).all()
+    # (2) the 512-thread variant (a batch below 2 x SMs problems) and the full-mask formulation on sub-batches
+    for p0 in (0, 1200, 2400):
+        k1, n1 = U.nms_gpu_batched(tb[p0:p0 + 160], ts[p0:p0 + 160], 0.2)
+        assert torch.equal(n1, num[p0:p0 + 160]) and torch.equal(k1, keep[p0:p0 + 160])
+    k2, n2 = U.nms_gpu_batched(tb[:320], ts[:320], 0.2, full_mask=True)
+    assert torch.equal(n2, num[:320]) and torch.equal(k2, keep[:320])
+    # (3) ragged counts through the same variant
+    counts = torch.from_numpy(np.random.default_rng(1).integers(0, 1001, P).astype(np.int32))
+    kc, nc = U.nms_gpu_batched(tb, ts, 0.2, counts)
+    for p in range(0, P, 211):
+        c = int(counts[p])
+        want = U.nms_gpu(tb[p, :c], ts[p, :c], 0.2)[0]
+        assert int(nc[p]) == want.numel() and torch.equal(kc[p, : want.numel()], want)
 
 
 @pytest.mark.parametrize("n", [20000, 52000])
@@ -295,12 +338,12 @@ def test_cpu_named_functions_run_on_the_gpu_with_cpu_semantics():
         assert np.array_equal(m, g["pib_ref_mask"][f])  # bit-exact vs the reference's own CPU output
     t = PU.points_in_boxes_cpu(torch.from_numpy(g["pib_pts"][0]), torch.from_numpy(g["pib_boxes"][0]))
     assert isinstance(t, torch.Tensor) and not t.is_cuda
-    for name in ("kat_sq", "car35", "cfg3iou"):
+    for name in IOU_SETS:  # all nine sets of the reference's compiled boxes_iou_bev_cpu (iou3d_cpu.cpp:232-252), 1e-5 absolute
         a, b, ref = g[f"iou_{name}_a"], g[f"iou_{name}_b"], g[f"iou_{name}_ref"]
         got = U.boxes_bev_iou_cpu(a, b)
         assert isinstance(got, np.ndarray) and got.shape == ref.shape
-        assert np.abs(got - ref).max() <= IOU_ATOL
-        assert np.array_equal(got == 0, ref == 0)
+        nbad = assert_iou_close(got, ref, f"boxes_bev_iou_cpu {name}")
+        assert nbad <= max(1, ref.size // 2000), f"{name}: {nbad} of {ref.size} entries not bit-identical to the reference CPU build"
 
 
 # ------------------------------------------------------------------------------------------ tier A, live

@@ -22,6 +22,9 @@ def emu():
     L.emu_slow_count.restype = C.c_longlong
     L.emu_points_in_boxes.restype = C.c_longlong
     L.emu_points_in_boxes.argtypes = [fp, C.c_int, fp, C.c_longlong, ip, C.c_int, C.POINTER(C.c_int)]
+    L.emu_glibc_sweep.restype = C.c_longlong
+    L.emu_glibc_sweep.argtypes = [C.c_uint, C.c_uint, C.c_longlong, C.POINTER(C.c_uint)]
+    L.emu_points_mask.argtypes = [fp, C.c_int, fp, C.c_longlong, ip, C.c_int]
     return L
 
 
@@ -54,6 +57,37 @@ def test_device_pair_code_matches_oracle_bit_for_bit(emu, name):
         got = pairs(emu, a, b, mode + 4)  # +4: with the exact-zero cull in front, as the kernels run it
         want = ora(a, b, O.FLAVOR_CUDA)
         assert np.array_equal(bits(got), bits(want)), f"{name} mode {mode}: {(bits(got) != bits(want)).sum()} of {got.size} differ"
+
+
+def test_device_restatement_of_glibc_sinf_cosf_matches_the_host_libm(emu):
+    """FL = 0 trigonometry (lg_trig.cuh) against the libm the reference's CPU build calls: every 16th float bit pattern
+    (2^28 inputs, each through sinf and cosf; tools/check_glibc_trig.py is the exhaustive sweep), plus every float in the
+    range of box headings."""
+    fb = C.c_uint(0)
+    assert emu.emu_glibc_sweep(7, 16, 1 << 28, C.byref(fb)) == 0, hex(fb.value)
+    lo, hi = np.float32(0.78).view(np.uint32), np.float32(6.5).view(np.uint32)  # [0.78, 6.5]: pi/4 .. beyond 2 pi, every float
+    for sign in (0, 1 << 31):
+        assert emu.emu_glibc_sweep(int(lo) | sign, 1, int(hi - lo), C.byref(fb)) == 0, hex(fb.value)
+
+
+@pytest.mark.parametrize("name", sorted(SETS))
+def test_strict_flavor_matches_the_reference_cpu_build_bit_for_bit(emu, name):
+    """LG_FLAG_STRICT_FP32 (boxes_bev_iou_cpu): un-contracted arithmetic + glibc trigonometry == the oracle's CPU flavor, which
+    is pinned bit-for-bit to the reference's compiled boxes_iou_bev_cpu (tests/test_oracle_pin.py)"""
+    a, b = SETS[name]()
+    got = pairs(emu, a, b, 1 + 4, flavor=0)
+    want = O.boxes_iou_bev(a, b, O.FLAVOR_CPU)
+    assert np.array_equal(bits(got), bits(want)), f"{name}: {(bits(got) != bits(want)).sum()} of {got.size} differ"
+
+
+def test_strict_points_mask_matches_the_reference_cpu_build(emu):
+    pts, rois = synth.cfg3(n_frames=1, n_points=4096, n_rois=60)
+    r = np.random.default_rng(3)
+    p = np.concatenate([pts[0], boundary_points(r, rois[0], 4096)]).astype(np.float32)
+    out = np.empty((60, len(p)), np.int32)
+    emu.emu_points_mask(np.ascontiguousarray(rois[0]).ctypes.data_as(fp), 60, p.ctypes.data_as(fp), len(p), out.ctypes.data_as(ip), 0)
+    want = O.points_in_boxes_mask(p, rois[0], margin=1e-5, flavor=O.FLAVOR_CPU)
+    assert np.array_equal(out, want)
 
 
 def test_cull_never_drops_a_nonzero_pair(emu):
