@@ -173,7 +173,7 @@ def _argsort_desc(scores):
     P, N = scores.shape
     if not (scores.is_cuda and scores.dtype == torch.float32 and 0 < N <= LG_SELECT_MAX_K and 0 < P <= 2 * _sm_count(scores.device)):
         # one CTA per problem: a batch of thousands of small problems is better served by torch's segmented sort (measured on nms_cfg5)
-        return scores.sort(1, descending=True, stable=True)[1].contiguous()
+        return scores.sort(dim=1, descending=True, stable=True)[1].contiguous()
     L = _lib.lib()
     dev = scores.device
     sc = scores.contiguous()
