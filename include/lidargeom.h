@@ -134,8 +134,17 @@ LG_API int lg_nms_rotated_batched(const float *boxes, const int64_t *order, cons
 LG_API int lg_nms_normal_batched(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
                           float thresh, void *ws, size_t ws_bytes, int64_t *keep, int32_t *num_keep, unsigned flags,
                           void *stream);
+/* The general form: `normal` 0 rotated / 1 axis-aligned; keep is (P, keep_ld) and only the first max_keep <= keep_ld entries
+ * of a row are written (kept indices, then -1), num_keep[p] <= max_keep.  max_keep is the caller's NMS_POST_MAXSIZE
+ * (model_nms_utils.py:20 `selected[:NMS_POST_MAXSIZE]`): the first max_keep kept boxes are exactly the reference's truncated
+ * list, and the kernels stop choosing candidates once it is full.  The two entry points above are this one with
+ * max_keep = keep_ld = nmax. */
+LG_API int lg_nms_batched_ex(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
+                             float thresh, int normal, int max_keep, int64_t keep_ld, void *ws, size_t ws_bytes, int64_t *keep,
+                             int32_t *num_keep, unsigned flags, void *stream);
 /* The same pipeline one phase at a time, for profiling (bench.py times the mask kernel alone for its
- * roofline line): phases is a bit-or of LG_NMS_PHASE_*; ws carries the records and the mask between calls. */
+ * roofline line): phases is a bit-or of LG_NMS_PHASE_*; ws carries the records and the mask between calls.  The lazy rotated
+ * NMS is ONE kernel (records included): it runs when LG_NMS_PHASE_SWEEP is set and ignores the other two bits. */
 #define LG_NMS_PHASE_RECORDS 1u
 #define LG_NMS_PHASE_MASK 2u
 #define LG_NMS_PHASE_SWEEP 4u

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblidargeom.so")
+LIB_PATH = os.environ.get("LG_LIB_PATH") or os.path.join(_HERE, "liblidargeom.so")  # LG_LIB_PATH: developer builds (tools/lz_timing.py)
 
 LG_FLAG_NONE = 0
 LG_FLAG_STRICT_FP32 = 1
@@ -53,6 +53,8 @@ def lib():
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp]
+    L.lg_nms_batched_ex.restype = C.c_int
+    L.lg_nms_batched_ex.argtypes = [vp, vp, vp, i32, i32, f32, i32, i32, i64, vp, sz, vp, vp, u32, vp]
     L.lg_nms_batched_phases.restype = C.c_int
     L.lg_nms_batched_phases.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp, i32, u32]
     for name in ("lg_nms_rotated", "lg_nms_normal"):
@@ -92,7 +94,7 @@ def lib():
 EXPORTS = [
     "lg_version", "lg_last_error_string", "lg_check_device",
     "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d", "lg_iou_reduce_workspace_bytes", "lg_boxes_iou_reduce",
-    "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
+    "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_ex", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
     "lg_roiaware_pool3d_forward", "lg_roiaware_pool3d_backward", "lg_roipoint_pool3d_forward",
     "lg_kitti_workspace_bytes", "lg_rotate_iou_eval", "lg_d3_box_overlap", "lg_kitti_overlaps_parts",

@@ -26,16 +26,17 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, extra_flags=()):
+    """out / extra_flags: developer builds next to the product library (e.g. -DLG_LZ_TIMING into liblidargeom_timing.so)"""
+    if out is None and not force and not stale():
         return OUT
     extra = os.environ.get("LG_EXTRA_NVCC_FLAGS", "").split()  # developer experiments only (e.g. -DLG_LZ_G=4)
     # one nvcc per translation unit, side by side (the units are independent: no relocatable device code), then one link
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build" if out is None else "build_" + os.path.splitext(os.path.basename(out))[0])
     os.makedirs(objdir, exist_ok=True)
-    cflags = [f for f in FLAGS if f != "--shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    cflags = [f for f in FLAGS if f != "--shared"] + extra + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
@@ -44,8 +45,8 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    subprocess.check_call([NVCC] + FLAGS + ["-o", OUT] + objs)
-    return OUT
+    subprocess.check_call([NVCC] + FLAGS + ["-o", out or OUT] + objs)
+    return out or OUT
 
 
 if __name__ == "__main__":

@@ -17,6 +17,8 @@
 // All P problems of a batch go through three launches in total, with no host synchronisation.
 #include <cooperative_groups.h>
 
+#include <atomic>
+
 #include "lg_common.cuh"
 #include "lg_strip.cuh"
 
@@ -185,18 +187,19 @@ __device__ __forceinline__ unsigned long long shfl64(unsigned long long v, int s
 // one warp per problem (iou3d_nms.cpp:116-132 restated for the device)
 __global__ void __launch_bounds__(32)
     nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int64_t* __restrict__ order,
-                     const int32_t* __restrict__ counts, const int nmax, const int cbk, int64_t* __restrict__ keep,
-                     int32_t* __restrict__ num_keep) {
+                     const int32_t* __restrict__ counts, const int nmax, const int cbk, int64_t* __restrict__ keep, const int keep_ld,
+                     const int max_keep, int32_t* __restrict__ num_keep) {
     extern __shared__ unsigned long long remv[];
     const int p = blockIdx.x, lane = threadIdx.x;
     const int n = problem_count(counts, p, nmax);
     const int nb = (n + 63) / 64;
     const int64_t base = (int64_t)p * nmax;
     const unsigned long long* M = mask + base * cbk;
+    int64_t* const krow = keep + (int64_t)p * keep_ld;
     for (int w = lane; w < nb; w += 32) remv[w] = 0ull;
     __syncwarp();
     int nk = 0;
-    for (int b = 0; b < nb; b++) {
+    for (int b = 0; b < nb && nk < max_keep; b++) {  // NMS_POST_MAXSIZE reached: the rest cannot be kept
         const int r0 = b * 64 + lane, r1 = r0 + 32;
         const unsigned long long d0 = (r0 < n) ? M[(int64_t)r0 * cbk + b] : 0ull;
         const unsigned long long d1 = (r1 < n) ? M[(int64_t)r1 * cbk + b] : 0ull;
@@ -224,10 +227,11 @@ __global__ void __launch_bounds__(32)
         {
             const unsigned long long below0 = kept & ((1ull << lane) - 1ull);
             const unsigned long long below1 = kept & ((1ull << (lane + 32)) - 1ull);
-            if ((kept >> lane) & 1ull) keep[base + nk + __popcll(below0)] = order ? order[base + r0] : (int64_t)r0;
-            if ((kept >> (lane + 32)) & 1ull) keep[base + nk + __popcll(below1)] = order ? order[base + r1] : (int64_t)r1;
+            const int q0 = nk + __popcll(below0), q1 = nk + __popcll(below1);
+            if (((kept >> lane) & 1ull) && q0 < max_keep) krow[q0] = order ? order[base + r0] : (int64_t)r0;
+            if (((kept >> (lane + 32)) & 1ull) && q1 < max_keep) krow[q1] = order ? order[base + r1] : (int64_t)r1;
         }
-        nk += __popcll(kept);
+        nk = min(nk + __popcll(kept), max_keep);
         // fold the kept rows into remv for the later column blocks (independent loads, 4 in flight)
         for (int w = b + 1 + lane; w < nb; w += 32) {
             unsigned long long acc = remv[w];
@@ -250,11 +254,11 @@ __global__ void __launch_bounds__(32)
         __syncwarp();
     }
     if (lane == 0) num_keep[p] = nk;
-    for (int i = nk + lane; i < nmax; i += 32) keep[base + i] = -1;
+    for (int i = nk + lane; i < max_keep; i += 32) krow[i] = -1;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Lazy rotated NMS: one CTA per problem, no N x N/64 mask.
+// Lazy rotated NMS: one CTA (or one thread-block cluster) per problem, no N x N/64 mask, no separate record kernel.
 //
 // The reference's sweep (iou3d_nms.cpp:121-132) reads row i of the mask only when box i is KEPT, so only
 // kept rows have to exist.  Per pass the CTA takes the next LZ_G boxes that are still alive (speculating
@@ -267,60 +271,87 @@ __global__ void __launch_bounds__(32)
 //             the others are kept and their rows are OR-ed out of the alive bitmap.
 // Every IoU that decides anything is iou_bev(kept box, later box) exactly as in the mask formulation, so the
 // keep list is identical; the work drops from N^2/2 pairs to about (#kept + failed speculations) x N.
+//
+// A problem is a chain of dependent passes, each of them a handful of latency-bound phases (one polygon round is a
+// ~1500-instruction dependency chain per lane), so the kernel is as fast as it has few passes: 32 candidates per pass
+// fill the polygon rounds (with 8, a pass queued ~120 pairs for 512 threads) and quarter the number of passes; a failed
+// speculation costs a row of pair tests on otherwise idle lanes, not latency.
 constexpr int LZ_THREADS = 512;  // one problem is latency-bound: 16 warps hide the polygon path's dependency chains
-constexpr int LZ_G = 8;          // speculative candidates per pass
-constexpr int LZ_QCAP = 8192;    // u32 codes: candidate << 16 | box
-constexpr int LZ_RARECAP = LZ_QCAP + 1024;
+constexpr int LZ_G = 32;         // speculative candidates per pass (one lane each in the resolve)
+constexpr int LZ_GH = 16;        // candidates per warp in a sweep: two warp groups share every column word
 constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
-constexpr int LZ_SWEEP = LZ_THREADS;  // columns per sweep of the 16 warps
 constexpr int LZ_MAX_CLUSTER = 8;     // portable cluster size limit
 constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared memory per CTA on sm_100a, minus the static part
 
+struct LazyLayout;
+static inline int lazy_gcap(int nmax, int nt);  // largest of 32 / 16 / 8 candidates per pass whose layout fits, 0 if none does
+
 struct LazyLayout {
-    int words;         // alive words
-    size_t off_cull, off_slab, off_queue, off_rare, off_alive, off_sup, total;
-    __host__ __device__ explicit LazyLayout(int nmax, int nt = LZ_THREADS) {
+    int words, sstride;  // alive words; pitch of a suppression row (odd: the resolve reads a column of the rows conflict-free)
+    int qcap, rarecap;   // u32 codes: candidate << 16 | box.  qcap = one sweep step of the CTA at 100 % survivors + all candidate pairs
+    int gcap;            // candidates per pass: LZ_G, fewer when the suppression rows of a very large problem would not fit
+    size_t off_cand, off_cull, off_slab, off_queue, off_rare, off_alive, off_sup, total;
+    __host__ __device__ explicit LazyLayout(int nmax, int nt = LZ_THREADS, int gcap_ = LZ_G) {
         words = (nmax + 31) / 32;
+        sstride = words | 1;
+        qcap = 16 * nt + 512;
+        rarecap = qcap + 1024;
+        gcap = gcap_;
         size_t o = (size_t)LZ_G * REC_F4 * sizeof(float4);  // candidate records first
+        off_cand = o;
+        o += (size_t)LZ_G * sizeof(float4);
         off_cull = o;
         o += (size_t)(nmax < LZ_CACHE ? nmax : LZ_CACHE) * sizeof(float4);
         off_slab = o;
         o += (size_t)SLAB_ROWS * nt * sizeof(float2);
         off_queue = o;
-        o += (size_t)LZ_QCAP * sizeof(uint32_t);
+        o += (size_t)qcap * sizeof(uint32_t);
         off_rare = o;
-        o += (size_t)LZ_RARECAP * sizeof(uint32_t);
+        o += (size_t)rarecap * sizeof(uint32_t);
         off_alive = o;
         o += (size_t)words * sizeof(uint32_t);
         off_sup = o;
-        o += (size_t)LZ_G * words * sizeof(uint32_t);
+        o += (size_t)gcap * sstride * sizeof(uint32_t);
         total = o;
     }
 };
 
+static inline int lazy_gcap(int nmax, int nt) {
+    for (int g = LZ_G; g >= 8; g >>= 1)
+        if (LazyLayout(nmax, nt, g).total <= LZ_SMEM_LIMIT) return g;
+    return 0;
+}
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // NT = 512 threads for one latency-bound problem per SM; NT = 256 (two CTAs per SM) when the batch has several small
-// problems per SM, so that one problem's serial phases (candidate search, resolve, barriers) overlap another's rounds
+// problems per SM, so that one problem's serial phases (candidate search, resolve, barriers) overlap another's rounds.
+// rec: workspace, written by the kernel's own prologue (the 112-byte records of lg_geom.cuh, in score order) and read
+// back through L2 -- never through the read-only path, which is not coherent with writes of the same launch.
 template <int FL, bool CL, int NT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
-    nms_lazy_kernel(const float4* __restrict__ rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
-                    const int nmax, const float thresh, int64_t* __restrict__ keep, int32_t* __restrict__ num_keep,
-                    unsigned long long* __restrict__ stats) {
-    constexpr int G = LZ_G, SWEEP = NT;  // columns per sweep of the CTA's warps
+    nms_lazy_kernel(const float* __restrict__ boxes, float4* rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
+                    const int nmax, const float thresh, int64_t* __restrict__ keep, const int keep_ld, const int max_keep,
+                    int32_t* __restrict__ num_keep, unsigned long long* __restrict__ stats, const int gcap) {
+    constexpr int G = LZ_G, GH = LZ_GH, NW = NT / 32, WG = NW / 2, STEP = WG * 32;  // columns per sweep step of the CTA's warps
     extern __shared__ float4 smem4[];
-    const LazyLayout L(nmax, NT);
+    const LazyLayout L(nmax, NT, gcap);
     char* sm = reinterpret_cast<char*>(smem4);
     float4* sA = smem4;
+    float4* scand = reinterpret_cast<float4*>(sm + L.off_cand);
     float4* scull = reinterpret_cast<float4*>(sm + L.off_cull);
     float2* slab = reinterpret_cast<float2*>(sm + L.off_slab);
     uint32_t* queue = reinterpret_cast<uint32_t*>(sm + L.off_queue);
     uint32_t* rareq = reinterpret_cast<uint32_t*>(sm + L.off_rare);
     uint32_t* alive = reinterpret_cast<uint32_t*>(sm + L.off_alive);
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
-    __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s;
+    const int SW = L.sstride, QCAP = L.qcap, RARECAP = L.rarecap;
+    __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s;
     __shared__ unsigned long long st_heavy;
 
     // A problem may be spread over a thread-block cluster of C CTAs (C SMs): they keep identical copies of the alive bitmap
-    // and of the pass state, split the COLUMNS of every pass (interleaved 512-column sweeps), evaluate the few
+    // and of the pass state, split the COLUMNS of every pass (interleaved sweep steps), evaluate the few
     // candidate-vs-candidate pairs redundantly, and exchange the kill words through distributed shared memory after the resolve.
     // (CL = false compiles all of that out: one CTA per problem.)
     cg::cluster_group cluster = cg::this_cluster();
@@ -331,24 +362,38 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     const int W = (n + 31) / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base = (int64_t)p * nmax;
-    const float4* grec = rec + base * REC_F4;
+    float4* grec = rec + base * REC_F4;
 
+    // ---- prologue: the problem's records, in score order (every CTA of a cluster builds an interleaved share)
+    for (int i = crank * NT + tid; i < n; i += C * NT) {
+        int64_t src = i;
+        if (order) {
+            src = __ldg(order + base + i);
+            if (src < 0 || src >= nmax) src = i;  // defensive: never read out of the problem's rows
+        }
+        make_record<FL>(boxes + (base + src) * 7, grec + (int64_t)i * REC_F4);
+    }
     for (int w = tid; w < W; w += NT) alive[w] = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu;
-    for (int w = tid; w < G * W; w += NT) sup[w] = 0u;
-    for (int j = tid; j < min(n, LZ_CACHE); j += NT) scull[j] = __ldg(grec + (int64_t)j * REC_F4 + REC_CULL);
+    for (int w = tid; w < gcap * SW; w += NT) sup[w] = 0u;
     if (tid == 0) {
         qcount = 0;
         rcount = 0;
         nk_s = 0;
+        qvalid_s = QCAP;
+        sfail_s = 0x7fffffff;
         st_heavy = 0ull;
     }
+    // records visible to the whole problem (cluster barrier: release / acquire at cluster scope); it also tells every CTA that
+    // its peers have started and initialised their bitmaps, which must hold before any of them is touched remotely
+    if (split) cluster.sync();
+    else __syncthreads();
+    for (int j = tid; j < min(n, LZ_CACHE); j += NT) scull[j] = __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL);
     int cursor = 0;  // every box below it is decided
-    unsigned my_tested = 0u, my_nonzero = 0u;
-    // a peer's shared memory may only be touched once that peer has started and initialised its bitmap
-    if (CL && C > 1) cluster.sync();
+    unsigned my_tested = 0u, my_nonzero = 0u;  // my_tested: warp-uniform, lane 0 reports it
 #ifdef LG_LZ_TIMING  // developer build: cycles per phase of thread 0, accumulated into stats[8 + phase] (tools/lz_timing.py)
     long long tmark = clock64();
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int npass = 0;
 #define LZ_MARK(ph)                      \
     if (tid == 0) {                      \
         const long long now_ = clock64(); \
@@ -362,7 +407,37 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     auto emit = [&](int g, int j, float ov, const float4* A, const float4* B) {
         const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);  // row = the higher-scoring box (kernel.cu:304)
         my_nonzero += ov > 0.f ? 1u : 0u;
-        if (iou > thresh) atomicOr(&sup[g * W + (j >> 5)], 1u << (j & 31));
+        if (iou > thresh) atomicOr(&sup[g * SW + (j >> 5)], 1u << (j & 31));
+    };
+    // optimistic push: the sweeps of a pass run without a barrier and reserve queue space as they go; a reservation that does
+    // not fit writes nothing and records where the queue stopped being complete (every later reservation fails as well, so the
+    // entries below qvalid_s are exactly those of the successful ones) and the earliest step that lost pairs.
+    auto push = [&](const unsigned (&mk)[GH], const int rbase, const int col, const int step) {
+        unsigned any = 0u;
+#pragma unroll
+        for (int k = 0; k < GH; k++) any |= mk[k];
+        if (any == 0u) return;
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < GH; k++) total += __popc(mk[k]);
+        int qb = 0;
+        if (lane == 0) {
+            qb = atomicAdd(&qcount, total);
+            if (qb + total > QCAP) {
+                atomicMin(&qvalid_s, qb);
+                atomicMin(&sfail_s, step);
+            }
+        }
+        qb = __shfl_sync(0xffffffffu, qb, 0);
+        if (qb + total > QCAP) return;
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < GH; k++) {
+            if (mk[k]) {
+                if ((mk[k] >> lane) & 1u) queue[qb + __popc(mk[k] & lt)] = (uint32_t)(((rbase + k) << 16) | col);
+                qb += __popc(mk[k]);
+            }
+        }
     };
 
     while (true) {
@@ -370,193 +445,229 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         // ---- the next G alive boxes at or after the cursor (warp 0)
         if (warp == 0) {
             int found = 0;
-            for (int w0 = cursor >> 5; w0 < W && found < G; w0 += 32) {
-                const int w = w0 + lane;
-                unsigned word = w < W ? alive[w] : 0u;
-                if (w == (cursor >> 5)) word &= 0xFFFFFFFFu << (cursor & 31);
-                int incl = __popc(word);
+            if (nk_s < max_keep) {  // NMS_POST_MAXSIZE reached (model_nms_utils.py:20): nothing further can be kept
+                for (int w0 = cursor >> 5; w0 < W && found < gcap; w0 += 32) {
+                    const int w = w0 + lane;
+                    unsigned word = w < W ? alive[w] : 0u;
+                    if (w == (cursor >> 5)) word &= 0xFFFFFFFFu << (cursor & 31);
+                    int incl = __popc(word);
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    int slot = found + incl - __popc(word);
+                    while (word && slot < gcap) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        group[slot++] = w * 32 + b;
+                    }
+                    found += __shfl_sync(0xffffffffu, incl, 31);
                 }
-                int slot = found + incl - __popc(word);
-                while (word && slot < G) {
-                    const int b = __ffs(word) - 1;
-                    word &= word - 1;
-                    group[slot++] = w * 32 + b;
-                }
-                found += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (lane == 0) ng_s = min(found, G);
+            if (lane == 0) ng_s = min(found, gcap);
         }
         __syncthreads();
         LZ_MARK(0)  // candidate search
         const int ng = ng_s;
         // cluster: this CTA has chosen its candidates (every CTA picks the same ones from identical bitmaps); peers wait for
-        // this arrival before their kill words of this pass may touch our bitmap (barrier_wait below)
-        if (CL && C > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        // this arrival before their kill words of this pass may touch our bitmap (cluster_wait below)
+        if (split) cluster_arrive();
         if (ng == 0) {
-            if (CL && C > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            if (split) cluster_wait();
             break;
         }
-        for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
-        // cluster: the candidates are decided in this pass either way, so they leave the alive bitmap now (every CTA clears its
-        // own copy) and the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately.
-        // (One CTA per problem: they stay alive until the end of the pass and are swept like every other column.)
-        if (split && tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));
+        for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldcg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
+        if (tid < ng) {
+            const int j = group[tid];
+            scand[tid] = j < LZ_CACHE ? scull[j] : __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL);
+            // the candidates are decided in this pass either way: they leave the alive bitmap now (every CTA of a cluster clears
+            // its own copy), so the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately
+            atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
+        }
         __syncthreads();
         LZ_MARK(1)  // candidate records
-        const int g0 = group[0];
-        float4 ac[G];
-        int gi[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-            ac[g] = sA[(g < ng ? g : 0) * REC_F4 + REC_CULL];
-            gi[g] = g < ng ? group[g] : 0x7fffffff;  // an unused slot is "after" every box: never tested
-        }
-        // ---- candidate g against the later candidates: EVERY CTA of a cluster evaluates these (at most G (G - 1) / 2) pairs
-        // itself, so each has the complete candidate-vs-candidate bits for the resolve without an exchange through DSMEM and
-        // the cluster barrier it would need
-        if (split && warp == 0) {
-            const bool a = lane < ng;
-            const int j = a ? group[lane] : 0;
-            const float4 cj = a ? sA[lane * REC_F4 + REC_CULL] : make_float4(0.f, 0.f, 0.f, 0.f);
-            unsigned mk[G];
-#pragma unroll
-            for (int g = 0; g < G; g++) {
-                const bool t = a && lane > g;  // group[] ascends: lane > g <=> a later box
-                my_tested += (t && crank == 0) ? 1u : 0u;
-                mk[g] = __ballot_sync(0xffffffffu, t && cull_survives(ac[g], cj));
-            }
-            push_survivors<16, G>(mk, lane, 0, 1, j, &qcount, queue);
-        }
-        // ---- rows of the candidates against every later alive box, a chunk of columns at a time
-        int jw = ((g0 + 1) >> 5) << 5;
+        const int g0 = group[0], glast = group[ng - 1];
+        // ---- rows of the candidates against every later alive box.  Warp group `half` tests its GH candidates against the
+        // 32 columns of one alive word per step; the steps of a pass are interleaved over the CTAs of a cluster.
+        const int half = warp / WG, wcol = warp % WG;
+        const int kmax = min(GH, ng - GH * half);  // candidates of this warp group in this pass (<= 0: none)
+        const int nsteps = (n - (((glast + 1) >> 5) << 5) + C * STEP - 1) / (C * STEP);  // per CTA; all boxes up to glast are decided or candidates
+        const int jw0 = ((glast + 1) >> 5) << 5;
+        int s0 = 0;          // first step not yet swept
+        bool safe = false;   // after an overflow: one step at a time, which an empty queue always holds
         while (true) {
-            __syncthreads();
-            const int qn = qcount, rn = rcount;
-            __syncthreads();
-            const int room = (LZ_QCAP - qn) / G;  // columns that cannot overflow the queue
-            const bool done = jw >= n;
-            if (done || room < SWEEP) {  // single drain call site: mid-row when the queue is full, and at the end of the rows
-                LZ_MARK(2)  // cull sweeps
-                if (rn + qn > LZ_RARECAP) {
-                    drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
-                    __syncthreads();
-                }
-                drain_main<FL, 16, NT, true>(sA, grec, slab, queue, qn, rareq, &rcount, emit);  // column records in global memory: staged
-                if (tid == 0) {
-                    qcount = 0;
-                    st_heavy += (unsigned long long)qn;
-                }
-                LZ_MARK(3)  // polygon rounds (thread 0's share; the barrier that follows is charged to the next phase)
-                if (done) break;
-                continue;
-            }
-            const int sweeps = min(room / SWEEP, (n - jw + C * SWEEP - 1) / (C * SWEEP));
-            for (int s = 0; s < sweeps; s++) {
-                const int jb = jw + (s * C + crank) * SWEEP + warp * 32;  // this warp's 32-aligned word of this CTA's columns
-                if (jb >= n) break;
-                const unsigned word = alive[jb >> 5];
-                if (word == 0u) continue;  // warp-uniform
-                const int j = jb + lane;
-                const bool a = (word >> lane) & 1u;
-                const float4 cj = a ? (j < LZ_CACHE ? scull[j] : __ldg(grec + (int64_t)j * REC_F4 + REC_CULL)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                unsigned mk[G];
+            const int s1 = safe ? min(s0 + 1, nsteps) : nsteps;
+            // ---- candidate g against the later candidates (part of step 0): EVERY CTA of a cluster evaluates these (at most
+            // G (G - 1) / 2) pairs itself, so each has the complete candidate-vs-candidate bits for the resolve without an exchange
+            // through DSMEM and the cluster barrier it would need
+            if (s0 == 0 && warp < G / GH && warp * GH < ng) {
+                const bool a = lane < ng;
+                const int j = a ? group[lane] : 0;
+                const float4 cj = a ? scand[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned mk[GH];
 #pragma unroll
-                for (int g = 0; g < G; g++) {
-                    const bool t = a && j > gi[g];
-                    my_tested += t ? 1u : 0u;
-                    mk[g] = __ballot_sync(0xffffffffu, t && cull_survives(ac[g], cj));
+                for (int k = 0; k < GH; k++) {
+                    const int g = warp * GH + k;
+                    mk[k] = __ballot_sync(0xffffffffu, a && lane > g && cull_survives(scand[g < ng ? g : 0], cj));  // group[] ascends: lane > g <=> a later box
                 }
-                // code = candidate << 16 | box: push_survivors' (row << SHIFT | col) with row = g, col = j
-                push_survivors<16, G>(mk, lane, 0, 1, j, &qcount, queue);
+                push(mk, warp * GH, j, 0);
+                if (warp == 0 && crank == 0 && !safe) my_tested += (unsigned)(ng * (ng - 1) / 2);
             }
-            jw += sweeps * C * SWEEP;
+            if (kmax > 0) {
+                for (int s = s0; s < s1; s++) {
+                    const int jb = jw0 + (s * C + crank) * STEP + wcol * 32;  // this warp's 32-aligned word of this CTA's columns
+                    if (jb >= n) break;
+                    const unsigned word = alive[jb >> 5];
+                    if (word == 0u) continue;  // warp-uniform
+                    const int j = jb + lane;
+                    const bool a = (word >> lane) & 1u;
+                    const float4 cj = a ? (j < LZ_CACHE ? scull[j] : __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    unsigned mk[GH];
+#pragma unroll
+                    for (int k = 0; k < GH; k++) {
+                        mk[k] = 0u;
+                        if (k < kmax) mk[k] = __ballot_sync(0xffffffffu, a && cull_survives(scand[GH * half + k], cj));  // warp-uniform guard
+                    }
+                    my_tested += (unsigned)(__popc(word) * kmax);
+                    push(mk, GH * half, j, s);
+                }
+            }
+            __syncthreads();
+            const int qn = min(qcount, qvalid_s), rn = rcount, sfail = sfail_s;
+            __syncthreads();
+            LZ_MARK(2)  // cull sweeps
+            if (rn + qn > RARECAP) {
+                drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
+                __syncthreads();
+            }
+            drain_main<FL, 16, NT, true>(sA, grec, slab, queue, qn, rareq, &rcount, emit);  // column records in global memory: staged
+            if (tid == 0) {
+                qcount = 0;
+                qvalid_s = QCAP;
+                sfail_s = 0x7fffffff;
+                st_heavy += (unsigned long long)qn;
+            }
+            LZ_MARK(3)  // polygon rounds (thread 0's share; the barrier that follows is charged to the next phase)
+            if (sfail == 0x7fffffff) {
+                if (s1 >= nsteps) break;
+                s0 = s1;      // safe mode, step by step
+            } else {
+                s0 = sfail;   // pairs were lost from this step on (steps >= sfail that did fit are simply evaluated again:
+                safe = true;  // setting a suppression bit twice changes nothing)
+            }
+            __syncthreads();  // the queue is empty again before the next sweep pushes
         }
         __syncthreads();
         LZ_MARK(4)  // waiting for the last polygon round
         drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
         __syncthreads();
         LZ_MARK(5)  // deferred pairs
-        // ---- resolve the speculation in score order (warp 0: lane h holds candidate h's row; at most G ballots); the
-        // candidate-vs-candidate bits are local in every CTA (see above)
+        // ---- resolve the speculation in score order (warp 0, lane g = candidate g); the candidate-vs-candidate bits are local
+        // in every CTA (see above)
         if (warp == 0) {
             const int jl = lane < ng ? group[lane] : 0;
-            const int64_t ol = (lane < ng && order) ? order[base + jl] : (int64_t)jl;  // loads issued before the serial part
+            const int64_t ol = (lane < ng && order) ? __ldg(order + base + jl) : (int64_t)jl;  // loads issued before the serial part
+            // colm: the earlier candidates h whose row suppresses this lane's candidate (a column of the rows: SW is odd and
+            // the candidates sit in a few neighbouring words, so the loads are broadcasts or conflict-free)
+            unsigned colm = 0u;
+            const int wl = jl >> 5, bl = jl & 31;
+            for (int h = 0; h < ng; h++) colm |= ((sup[h * SW + wl] >> bl) & 1u) << h;
+            colm &= (1u << lane) - 1u;
             unsigned km = 0u;
-            for (int g = 0; g < ng; g++) {
-                const int j = group[g];
-                const bool hit = lane < g && ((sup[lane * W + (j >> 5)] >> (j & 31)) & 1u);
-                const unsigned by = __ballot_sync(0xffffffffu, hit);  // earlier candidates whose row suppresses g
-                if ((by & km) == 0u) km |= 1u << g;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const unsigned cg_ = __shfl_sync(0xffffffffu, colm, g);  // independent of the chain: issued ahead of it
+                if (g < ng && (cg_ & km) == 0u) km |= 1u << g;
             }
             const int nk = nk_s;
-            if (crank == 0 && ((km >> lane) & 1u)) keep[base + nk + __popc(km & ((1u << lane) - 1u))] = ol;
+            const int pos = nk + __popc(km & ((1u << lane) - 1u));
+            if (crank == 0 && ((km >> lane) & 1u) && pos < max_keep) keep[(int64_t)p * keep_ld + pos] = ol;
             if (lane == 0) {
                 keptmask_s = (int)km;
-                nk_s = nk + __popc(km);
+                nk_s = min(nk + __popc(km), max_keep);
             }
         }
         __syncthreads();
-        LZ_MARK(6)  // resolve (+ cluster exchange)
-        const int km = keptmask_s;
-        if (CL && C > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // every peer has its candidates of this pass
-        for (int w = (g0 >> 5) + tid; w < W; w += NT) {
+        LZ_MARK(6)  // resolve
+        const unsigned km = (unsigned)keptmask_s;
+        if (split) cluster_wait();  // every peer has chosen its candidates of this pass: its bitmap may be touched now
+        // kill words: four threads per word, eight rows each
+        for (int wb = (g0 >> 5); wb < W; wb += NT / 4) {
+            const int w = wb + (tid >> 2), part = tid & 3;
             unsigned kill = 0u;
+            if (w < W) {
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (g < ng) {
-                    if ((km >> g) & 1) kill |= sup[g * W + w];
-                    sup[g * W + w] = 0u;
+                for (int k = 0; k < G / 4; k++) {
+                    const int g = part * (G / 4) + k;
+                    if (g < ng) {
+                        if ((km >> g) & 1u) kill |= sup[g * SW + w];
+                        sup[g * SW + w] = 0u;
+                    }
                 }
             }
-            if (CL && C > 1) {
-                if (kill) {  // peers update the same words: atomics everywhere
+            kill |= __shfl_xor_sync(0xffffffffu, kill, 1);
+            kill |= __shfl_xor_sync(0xffffffffu, kill, 2);
+            if (w < W && part == 0 && kill) {
+                if (split) {  // peers update the same words: atomics everywhere
                     for (int r = 0; r < C; r++) atomicAnd(cluster.map_shared_rank(&alive[w], r), ~kill);
+                } else {
+                    alive[w] &= ~kill;
                 }
-            } else {
-                alive[w] &= ~kill;
             }
         }
-        if (!split) {
-            __syncthreads();
-            if (tid < ng) atomicAnd(&alive[group[tid] >> 5], ~(1u << (group[tid] & 31)));  // candidates are decided either way
-        }
-        cursor = group[ng - 1] + 1;
-        if (CL && C > 1) cluster.sync();  // every CTA's kill words have landed everywhere before the next candidates are chosen
+        cursor = glast + 1;
+#ifdef LG_LZ_TIMING
+        npass++;
+#endif
+        if (split) cluster.sync();  // every CTA's kill words have landed everywhere before the next candidates are chosen
         LZ_MARK(7)  // kill words (+ cluster sync)
     }
     // all threads left the loop together
     const int nk = nk_s;
     if (crank == 0) {
         if (tid == 0) num_keep[p] = nk;
-        for (int i = nk + tid; i < nmax; i += NT) keep[base + i] = -1;
+        for (int i = nk + tid; i < max_keep; i += NT) keep[(int64_t)p * keep_ld + i] = -1;
     }
     if (stats) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            my_tested += __shfl_xor_sync(0xffffffffu, my_tested, d);
-            my_nonzero += __shfl_xor_sync(0xffffffffu, my_nonzero, d);
-        }
+        for (int d = 16; d > 0; d >>= 1) my_nonzero += __shfl_xor_sync(0xffffffffu, my_nonzero, d);
         if (lane == 0) {
             atomicAdd(stats, (unsigned long long)my_tested);
             atomicAdd(stats + 2, (unsigned long long)my_nonzero);
         }
         if (tid == 0) atomicAdd(stats + 1, st_heavy);
 #ifdef LG_LZ_TIMING
-        if (tid == 0)
+        if (tid == 0) {
             for (int ph = 0; ph < 8; ph++) atomicAdd(stats + 8 + ph, (unsigned long long)tacc[ph]);
+            atomicAdd(stats + 16, (unsigned long long)npass);
+            atomicMax(stats + 17, (unsigned long long)npass);
+            unsigned long long tsum = 0ull;
+            for (int ph = 0; ph < 8; ph++) tsum += (unsigned long long)tacc[ph];
+            atomicMax(stats + 18, tsum);
+        }
 #endif
     }
 }
 
 enum { PHASE_RECORDS = 1, PHASE_MASK = 2, PHASE_SWEEP = 4, PHASE_ALL = 7 };
 
+// per-device facts, looked up once (the C ABI keeps no state that matters: these are caches of immutable properties)
+static int device_sm_count(int dev) {
+    static std::atomic<int> cache[64];
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        v = 148;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 static int nms_entry(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax, float thresh, void* ws,
-                     size_t ws_bytes, int64_t* keep, int32_t* num_keep, unsigned flags, void* stream, bool normal,
-                     unsigned phases = PHASE_ALL) {
+                     size_t ws_bytes, int64_t* keep, int keep_ld, int max_keep, int32_t* num_keep, unsigned flags, void* stream,
+                     bool normal, unsigned phases = PHASE_ALL) {
     if (P < 0 || nmax < 0) {
         set_error("negative size num_problems=%d nmax=%d", P, nmax);
         return LG_ERR_INVALID_ARG;
@@ -566,12 +677,13 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
         set_error("null pointer (boxes=%p keep=%p num_keep=%p)", (const void*)boxes, (void*)keep, (void*)num_keep);
         return LG_ERR_INVALID_ARG;
     }
+    if (max_keep > nmax) max_keep = nmax;
+    if (nmax > 0 && (max_keep < 0 || keep_ld < max_keep)) {
+        set_error("max_keep=%d keep_ld=%d: need 0 <= max_keep <= keep_ld", max_keep, keep_ld);
+        return LG_ERR_INVALID_ARG;
+    }
     if (nmax > LG_NMS_MAX_BOXES) {
         set_error("nmax=%d exceeds LG_NMS_MAX_BOXES=%d", nmax, LG_NMS_MAX_BOXES);
-        return LG_ERR_TOO_LARGE;
-    }
-    if (P > 65535) {
-        set_error("num_problems=%d exceeds 65535; split the batch", P);
         return LG_ERR_TOO_LARGE;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -595,39 +707,38 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
     unsigned long long* stats = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes);
     unsigned long long* mask = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + rec_bytes + NMS_STATS_BYTES);
     const bool strict = (flags & LG_FLAG_STRICT_FP32) != 0;
-    // the lazy kernel keeps the alive bitmap and 8 suppression rows of a problem in shared memory: beyond ~50,000 boxes
-    // they no longer fit next to the queues, and the mask + sweep formulation takes over (same keep list)
-    const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0 || LazyLayout(nmax).total > LZ_SMEM_LIMIT;
+    // the lazy kernel keeps the alive bitmap and the suppression rows of its candidates in shared memory: 32 candidates per pass
+    // up to ~8,000 boxes, 16 / 8 beyond; past ~50,000 boxes nothing fits next to the queues and the mask + sweep formulation
+    // takes over (same keep list)
+    const int gcap512 = lazy_gcap(nmax, LZ_THREADS);
+    const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0 || gcap512 == 0;
     int rc;
-    if (!normal) {
-        if (phases & PHASE_RECORDS) {
-            dim3 pg((nmax + 255) / 256, P);
-            if (strict) nms_prep_kernel<0><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
-            else nms_prep_kernel<1><<<pg, 256, 0, st>>>(boxes, order, counts, nmax, rec);
-            if ((rc = check_launch("nms_prep_kernel"))) return rc;
+    if (!normal && !full) {
+        // lazy path: records, candidate rows and the greedy resolve in ONE launch; only the rows of kept boxes are ever evaluated
+        if (!(phases & PHASE_SWEEP)) return LG_OK;
+        cudaError_t e = cudaMemsetAsync(stats, 0, NMS_STATS_BYTES, st);
+        if (e != cudaSuccess) {
+            set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return (int)e;
         }
-        if (!full) {
-            // lazy path: only the rows of kept boxes are ever evaluated
-            if (!(phases & PHASE_SWEEP)) return LG_OK;
-            cudaError_t e = cudaMemsetAsync(stats, 0, NMS_STATS_BYTES, st);
-            if (e != cudaSuccess) {
-                set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
-                return (int)e;
-            }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int sms = device_sm_count(dev);
+        // the batch goes out in slices of at most 65,535 problems (grid.x of a clustered launch is problems x cluster size)
+        for (int p0 = 0; p0 < P; p0 += 32768) {
+            const int pn = min(P - p0, 32768);
             // cluster size: as many SMs per problem as leaves every CTA of the batch resident at once (the kernel is bound by
-            // one SM's instruction throughput per problem), and never fewer than 1024 columns per CTA
-            int dev = 0, sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            // one SM's latency per problem), and never fewer than two sweep steps per CTA
             int csize = 1;
-            while (csize < LZ_MAX_CLUSTER && (int64_t)P * csize * 2 <= sms && nmax >= csize * 2 * LZ_SWEEP) csize *= 2;
+            while (csize < LZ_MAX_CLUSTER && (int64_t)pn * csize * 2 <= sms && nmax >= csize * 2 * (LZ_THREADS / 2)) csize *= 2;
             if (flags & LG_FLAG_NMS_NO_CLUSTER) csize = 1;
             // many small problems: 256-thread CTAs, two per SM
-            const bool small = csize == 1 && nmax <= 1536 && (int64_t)P >= 2 * sms;
+            const bool small = csize == 1 && nmax <= 1536 && (int64_t)pn >= 2 * sms;
             const int nt = small ? 256 : LZ_THREADS;
-            const LazyLayout L(nmax, nt);
+            const int gcap = small ? lazy_gcap(nmax, 256) : gcap512;
+            const LazyLayout L(nmax, nt, gcap);
             cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3((unsigned)(P * csize));
+            lc.gridDim = dim3((unsigned)(pn * csize));
             lc.blockDim = dim3((unsigned)nt);
             lc.dynamicSmemBytes = L.total;
             lc.stream = st;
@@ -639,9 +750,15 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
             lc.attrs = at;
             lc.numAttrs = csize > 1 ? 1 : 0;  // a plain launch when every problem gets one CTA
             cudaError_t le;
+            const float* bx = boxes + (size_t)p0 * nmax * 7;
+            float4* rc4 = rec + (size_t)p0 * nmax * REC_F4;
+            const int64_t* od = order ? order + (size_t)p0 * nmax : nullptr;
+            const int32_t* cn = counts ? counts + p0 : nullptr;
+            int64_t* kp = keep + (size_t)p0 * keep_ld;
+            int32_t* nk = num_keep + p0;
             auto launch = [&](auto kern) -> cudaError_t {
                 if ((rc = set_smem(kern, L.total))) return cudaSuccess;
-                return cudaLaunchKernelEx(&lc, kern, (const float4*)rec, order, counts, nmax, thresh, keep, num_keep, stats);
+                return cudaLaunchKernelEx(&lc, kern, bx, rc4, od, cn, nmax, thresh, kp, keep_ld, max_keep, nk, stats, gcap);
             };
             rc = 0;
             if (strict) le = csize > 1 ? launch(nms_lazy_kernel<0, true, 512>) : (small ? launch(nms_lazy_kernel<0, false, 256>) : launch(nms_lazy_kernel<0, false, 512>));
@@ -651,28 +768,48 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
                 set_error("nms_lazy_kernel (cluster of %d): %s", csize, cudaGetErrorString(le));
                 return (int)le;
             }
-            return check_launch("nms_lazy_kernel");
+            if ((rc = check_launch("nms_lazy_kernel"))) return rc;
         }
-        if (!(phases & PHASE_MASK)) goto sweep;
-        dim3 mg(tri, P);
-        if (strict) {
-            if ((rc = set_smem(nms_mask_kernel<0>, NmsSmem::total))) return rc;
-            nms_mask_kernel<0><<<mg, NMS_THREADS, NmsSmem::total, st>>>(rec, counts, nmax, cbk, thresh, mask);
-        } else {
-            if ((rc = set_smem(nms_mask_kernel<1>, NmsSmem::total))) return rc;
-            nms_mask_kernel<1><<<mg, NMS_THREADS, NmsSmem::total, st>>>(rec, counts, nmax, cbk, thresh, mask);
-        }
-        if ((rc = check_launch("nms_mask_kernel"))) return rc;
-    } else if (phases & PHASE_MASK) {
-        dim3 mg(tri, P);
-        if (strict) nms_normal_mask_kernel<0><<<mg, NMS_TILE, 0, st>>>(boxes, order, counts, nmax, cbk, thresh, mask);
-        else nms_normal_mask_kernel<1><<<mg, NMS_TILE, 0, st>>>(boxes, order, counts, nmax, cbk, thresh, mask);
-        if ((rc = check_launch("nms_normal_mask_kernel"))) return rc;
+        return LG_OK;
     }
-sweep:
-    if (!(phases & PHASE_SWEEP)) return LG_OK;
-    nms_sweep_kernel<<<P, 32, (size_t)cbk * sizeof(unsigned long long), st>>>(mask, order, counts, nmax, cbk, keep, num_keep);
-    return check_launch("nms_sweep_kernel");
+    // mask + sweep formulation, in slices of at most 65,535 problems (grid.y)
+    for (int p0 = 0; p0 < P; p0 += 65535) {
+        const int pn = min(P - p0, 65535);
+        const float* bx = boxes + (size_t)p0 * nmax * 7;
+        float4* rc4 = rec + (size_t)p0 * nmax * REC_F4;
+        const int64_t* od = order ? order + (size_t)p0 * nmax : nullptr;
+        const int32_t* cn = counts ? counts + p0 : nullptr;
+        unsigned long long* mk = mask + (size_t)p0 * nmax * cbk;
+        dim3 mg(tri, pn);
+        if (!normal) {
+            if (phases & PHASE_RECORDS) {
+                dim3 pg((nmax + 255) / 256, pn);
+                if (strict) nms_prep_kernel<0><<<pg, 256, 0, st>>>(bx, od, cn, nmax, rc4);
+                else nms_prep_kernel<1><<<pg, 256, 0, st>>>(bx, od, cn, nmax, rc4);
+                if ((rc = check_launch("nms_prep_kernel"))) return rc;
+            }
+            if (phases & PHASE_MASK) {
+                if (strict) {
+                    if ((rc = set_smem(nms_mask_kernel<0>, NmsSmem::total))) return rc;
+                    nms_mask_kernel<0><<<mg, NMS_THREADS, NmsSmem::total, st>>>(rc4, cn, nmax, cbk, thresh, mk);
+                } else {
+                    if ((rc = set_smem(nms_mask_kernel<1>, NmsSmem::total))) return rc;
+                    nms_mask_kernel<1><<<mg, NMS_THREADS, NmsSmem::total, st>>>(rc4, cn, nmax, cbk, thresh, mk);
+                }
+                if ((rc = check_launch("nms_mask_kernel"))) return rc;
+            }
+        } else if (phases & PHASE_MASK) {
+            if (strict) nms_normal_mask_kernel<0><<<mg, NMS_TILE, 0, st>>>(bx, od, cn, nmax, cbk, thresh, mk);
+            else nms_normal_mask_kernel<1><<<mg, NMS_TILE, 0, st>>>(bx, od, cn, nmax, cbk, thresh, mk);
+            if ((rc = check_launch("nms_normal_mask_kernel"))) return rc;
+        }
+        if (phases & PHASE_SWEEP) {
+            nms_sweep_kernel<<<pn, 32, (size_t)cbk * sizeof(unsigned long long), st>>>(mk, od, cn, nmax, cbk, keep + (size_t)p0 * keep_ld, keep_ld,
+                                                                                        max_keep, num_keep + p0);
+            if ((rc = check_launch("nms_sweep_kernel"))) return rc;
+        }
+    }
+    return LG_OK;
 }
 
 }  // namespace lg
@@ -681,7 +818,7 @@ extern "C" size_t lg_nms_workspace_bytes_ex(int P, int nmax, int normal, unsigne
     if (P <= 0 || nmax <= 0) return 0;
     const size_t cbk = ((size_t)nmax + 63) / 64;
     size_t b = lg::align_up((size_t)P * nmax * lg::REC_F4 * sizeof(float4), 256) + lg::NMS_STATS_BYTES + 16;
-    if (normal || (flags & LG_FLAG_NMS_FULL_MASK) || lg::LazyLayout(nmax).total > lg::LZ_SMEM_LIMIT)
+    if (normal || (flags & LG_FLAG_NMS_FULL_MASK) || lg::lazy_gcap(nmax, lg::LZ_THREADS) == 0)
         b += (size_t)P * nmax * cbk * sizeof(unsigned long long);
     return b;
 }
@@ -696,28 +833,38 @@ extern "C" size_t lg_nms_stats_offset(int P, int nmax) {
 extern "C" int lg_nms_rotated_batched(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax,
                                       float thresh, void* ws, size_t ws_bytes, int64_t* keep, int32_t* num_keep,
                                       unsigned flags, void* stream) {
-    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, num_keep, flags, stream, false);
+    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, nmax, nmax, num_keep, flags, stream, false);
 }
 
 extern "C" int lg_nms_normal_batched(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax,
                                      float thresh, void* ws, size_t ws_bytes, int64_t* keep, int32_t* num_keep,
                                      unsigned flags, void* stream) {
-    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, num_keep, flags, stream, true);
+    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, nmax, nmax, num_keep, flags, stream, true);
+}
+
+extern "C" int lg_nms_batched_ex(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax, float thresh,
+                                 int normal, int max_keep, int64_t keep_ld, void* ws, size_t ws_bytes, int64_t* keep, int32_t* num_keep,
+                                 unsigned flags, void* stream) {
+    if (keep_ld < 0 || keep_ld > 0x7fffffffLL) {
+        lg::set_error("keep_ld=%lld out of range", (long long)keep_ld);
+        return LG_ERR_INVALID_ARG;
+    }
+    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, (int)keep_ld, max_keep, num_keep, flags, stream, normal != 0);
 }
 
 extern "C" int lg_nms_batched_phases(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax,
                                      float thresh, void* ws, size_t ws_bytes, int64_t* keep, int32_t* num_keep,
                                      unsigned flags, void* stream, int normal, unsigned phases) {
-    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, num_keep, flags, stream, normal != 0,
+    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, nmax, nmax, num_keep, flags, stream, normal != 0,
                          phases & lg::PHASE_ALL);
 }
 
 extern "C" int lg_nms_rotated(const float* boxes, const int64_t* order, int n, float thresh, void* ws, size_t ws_bytes,
                               int64_t* keep, int32_t* num_keep, unsigned flags, void* stream) {
-    return lg::nms_entry(boxes, order, nullptr, 1, n, thresh, ws, ws_bytes, keep, num_keep, flags, stream, false);
+    return lg::nms_entry(boxes, order, nullptr, 1, n, thresh, ws, ws_bytes, keep, n, n, num_keep, flags, stream, false);
 }
 
 extern "C" int lg_nms_normal(const float* boxes, const int64_t* order, int n, float thresh, void* ws, size_t ws_bytes,
                              int64_t* keep, int32_t* num_keep, unsigned flags, void* stream) {
-    return lg::nms_entry(boxes, order, nullptr, 1, n, thresh, ws, ws_bytes, keep, num_keep, flags, stream, true);
+    return lg::nms_entry(boxes, order, nullptr, 1, n, thresh, ws, ws_bytes, keep, n, n, num_keep, flags, stream, true);
 }

@@ -90,7 +90,9 @@ def _select_native(scores, box_preds, ppf, nms_config, score_thresh, k, post):
                               _lib.ptr(ws), ws.numel(), 0, st)
     _lib.check(rc, 'lg_select_topk')
     fn = {'nms_gpu': 'lg_nms_rotated_batched', 'nms_normal_gpu': 'lg_nms_normal_batched'}[_cfg(nms_config, 'NMS_TYPE')]
-    keep, num = iou3d_nms_utils._nms_call(fn, top_boxes, None, counts, float(_cfg(nms_config, 'NMS_THRESH')))
+    # NMS_POST_MAXSIZE stops the NMS itself (model_nms_utils.py:20): keep keeps its (P, k) pitch, only its first `post` columns are written
+    keep, num = iou3d_nms_utils._nms_call(fn, top_boxes, None, counts, float(_cfg(nms_config, 'NMS_THRESH')),
+                                          buffers=iou3d_nms_utils._nms_buffers(fn, P, k, dev), max_keep=post)
     selected = torch.empty((P, post), dtype=torch.int64, device=dev)
     num_out = torch.empty((P,), dtype=torch.int32, device=dev)
     sel_scores = torch.empty((P, post), dtype=torch.float32, device=dev)

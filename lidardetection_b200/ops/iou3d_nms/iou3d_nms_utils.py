@@ -124,10 +124,10 @@ def boxes_iou_max(boxes_a, boxes_b, kind='iou3d', rows=True, cols=False):
     return out
 
 
-def _nms_buffers(fn_name, P, N, dev, flags=_lib.LG_FLAG_NONE):
+def _nms_buffers(fn_name, P, N, dev, flags=_lib.LG_FLAG_NONE, max_keep=None):
     """outputs + scratch of one batched NMS call (allocated before the first launch of a step so that the launches follow
     each other without host work in between)"""
-    keep = torch.empty((P, N), dtype=torch.int64, device=dev)
+    keep = torch.empty((P, N if max_keep is None else min(int(max_keep), N)), dtype=torch.int64, device=dev)
     num = torch.zeros((P,), dtype=torch.int32, device=dev)
     ws = None
     if P > 0 and N > 0:
@@ -136,17 +136,20 @@ def _nms_buffers(fn_name, P, N, dev, flags=_lib.LG_FLAG_NONE):
     return keep, num, ws
 
 
-def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE, buffers=None):
-    """boxes (P, N, 7) cuda f32 contiguous; order (P, N) int64 or None; counts (P,) int32 or None."""
+def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE, buffers=None, max_keep=None):
+    """boxes (P, N, 7) cuda f32 contiguous; order (P, N) int64 or None; counts (P,) int32 or None.
+    max_keep: NMS_POST_MAXSIZE -- keep comes back as (P, min(max_keep, N)) and the kernels stop once a row is full."""
     P, N = boxes.shape[0], boxes.shape[1]
     dev = boxes.device
-    keep, num, ws = buffers if buffers is not None else _nms_buffers(fn_name, P, N, dev, flags)
-    if P == 0 or N == 0:
+    keep, num, ws = buffers if buffers is not None else _nms_buffers(fn_name, P, N, dev, flags, max_keep)
+    if P == 0 or N == 0 or keep.shape[1] == 0:
         return keep, num
     L = _lib.lib()
+    mk = keep.shape[1] if max_keep is None else min(int(max_keep), keep.shape[1])  # a wider keep keeps its pitch; columns >= mk stay unwritten
     with torch.cuda.device(dev):
-        rc = getattr(L, fn_name)(_lib.ptr(boxes), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), _lib.ptr(ws),
-                                 ws.numel(), _lib.ptr(keep), _lib.ptr(num), flags, _lib.stream_ptr(dev))
+        rc = L.lg_nms_batched_ex(_lib.ptr(boxes), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), 1 if 'normal' in fn_name else 0,
+                                 mk, keep.stride(0), _lib.ptr(ws), ws.numel(), _lib.ptr(keep), _lib.ptr(num), flags,
+                                 _lib.stream_ptr(dev))
     _lib.check(rc, fn_name)
     return keep, num
 
@@ -222,7 +225,7 @@ def nms_normal_gpu(boxes, scores, thresh, **kwargs):
     return _nms_single('lg_nms_normal_batched', boxes, scores, thresh, None)
 
 
-def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE):
+def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE, max_keep=None):
     assert boxes.dim() == 3 and boxes.shape[2] == 7 and scores.shape == boxes.shape[:2]
     b = boxes.contiguous().float()
     if counts is not None:
@@ -230,22 +233,24 @@ def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE
         idx = torch.arange(b.shape[1], device=b.device).unsqueeze(0)
         scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
         counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
-    buffers = _nms_buffers(fn_name, b.shape[0], b.shape[1], b.device, flags)
+    buffers = _nms_buffers(fn_name, b.shape[0], b.shape[1], b.device, flags, max_keep)
     order = _argsort_desc(scores)
-    return _nms_call(fn_name, b, order, counts, thresh, flags, buffers)
+    return _nms_call(fn_name, b, order, counts, thresh, flags, buffers, max_keep)
 
 
-def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False):
-    """P independent rotated-NMS problems in two launches (records, lazy NMS) and no host sync.
+def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False, max_keep=None):
+    """P independent rotated-NMS problems in two launches (score sort, lazy NMS incl. its records) and no host sync.
     :param boxes: (P, N, 7), :param scores: (P, N), :param counts: optional (P,) valid boxes per problem
     :param full_mask: materialise the reference's N x N/64 suppression mask and sweep it (three launches)
         instead of evaluating kept rows only; the keep lists are identical
+    :param max_keep: NMS_POST_MAXSIZE (model_nms_utils.py:20): only the first max_keep kept boxes are wanted; keep is then
+        (P, min(max_keep, N)) and the kernel stops once a problem's row is full
     :return: keep (P, N) int64 indices into each problem's boxes, padded with -1; num_keep (P,) int32
     """
     flags = _lib.LG_FLAG_NMS_FULL_MASK if full_mask else _lib.LG_FLAG_NONE
-    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts, flags)
+    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts, flags, max_keep)
 
 
-def nms_normal_gpu_batched(boxes, scores, thresh, counts=None):
+def nms_normal_gpu_batched(boxes, scores, thresh, counts=None, max_keep=None):
     """Batched axis-aligned NMS; see nms_gpu_batched."""
-    return _nms_batched('lg_nms_normal_batched', boxes, scores, thresh, counts)
+    return _nms_batched('lg_nms_normal_batched', boxes, scores, thresh, counts, max_keep=max_keep)

@@ -1,14 +1,22 @@
 #!/usr/bin/env python
-"""Developer tool: per-phase cycle breakdown of nms_lazy_kernel (build with LG_EXTRA_NVCC_FLAGS=-DLG_LZ_TIMING).
+"""Developer tool: per-phase cycle breakdown of nms_lazy_kernel.  Run it here first (it builds
+lidardetection_b200/liblidargeom_timing.so with -DLG_LZ_TIMING; the .so travels with the gpurun snapshot), then on the GPU box:
+    python tools/lz_timing.py --build ; gpurun -- 'LG_LIB_PATH=lidardetection_b200/liblidargeom_timing.so python tools/lz_timing.py'
 Phases are timed by thread 0 of every CTA between the kernel's barriers and summed over CTAs."""
 import ctypes as C
 import os
 import sys
 
-import torch
-
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if "--build" in sys.argv:
+    from lidardetection_b200.csrc import build as lbuild
+
+    print(lbuild.build(out=os.path.join(ROOT, "lidardetection_b200", "liblidargeom_timing.so"), extra_flags=["-DLG_LZ_TIMING"]))
+    sys.exit(0)
+
+import torch  # noqa: E402
+
 from lidardetection_b200 import _lib, synth  # noqa: E402
 
 P, N = 64, 4096
@@ -25,9 +33,9 @@ for _ in range(2):
 torch.cuda.synchronize()
 off = L.lg_nms_stats_offset(P, N)
 st = ws[off:off + 256].view(torch.int64).cpu().tolist()
-names = ["candidate search", "candidate records", "cull sweeps", "polygon rounds (thread 0)", "wait for last round", "deferred pairs", "resolve + exchange", "kill + cluster sync"]
+names = ["candidate search", "candidate records", "cull sweeps", "polygon rounds (thread 0)", "wait for last round", "deferred pairs", "resolve", "kill + cluster sync"]
 tot = sum(st[8:16])
 print("pairs cull-tested", st[0], "polygon", st[1], "nonzero", st[2], "kept/frame", float(num.float().mean()))
 for n, v in zip(names, st[8:16]):
     print(f"{n:28s} {v / max(tot, 1) * 100:5.1f} %   {v / 1.965e3 / (2 * P):8.1f} us per CTA")
-print("sum per CTA", tot / 1.965e3 / (2 * P), "us")
+print("sum per CTA", tot / 1.965e3 / (2 * P), "us;  passes per CTA: mean", st[16] / (2 * P), "max", st[17], ";  slowest CTA", st[18] / 1.965e3, "us")
