@@ -79,8 +79,17 @@ __device__ __forceinline__ float msub_p(float a, float b, float m) {
 
 // ---- per-box record ----------------------------------------------------------------------------
 template <int FL>
+__device__ __forceinline__ void make_record_v(const float cx, const float cy, const float z, const float dx, const float dy, const float dz,
+                                              const float th, float4* __restrict__ rec);
+
+template <int FL>
 __device__ __forceinline__ void make_record(const float* __restrict__ box, float4* __restrict__ rec) {
-    const float cx = box[0], cy = box[1], z = box[2], dx = box[3], dy = box[4], dz = box[5], th = box[6];
+    make_record_v<FL>(box[0], box[1], box[2], box[3], box[4], box[5], box[6], rec);
+}
+
+template <int FL>
+__device__ __forceinline__ void make_record_v(const float cx, const float cy, const float z, const float dx, const float dy, const float dz,
+                                              const float th, float4* __restrict__ rec) {
     const float hx = __fmul_rn(dx, 0.5f), hy = __fmul_rn(dy, 0.5f);
     const float x1 = __fsub_rn(cx, hx), x2 = __fadd_rn(cx, hx), y1 = __fsub_rn(cy, hy), y2 = __fadd_rn(cy, hy);
     const float co = trig_cos<FL>(th), si = trig_sin<FL>(th);
@@ -99,7 +108,9 @@ __device__ __forceinline__ void make_record(const float* __restrict__ box, float
             Y[k] = __fadd_rn(__fadd_rn(__fmul_rn(ddx[k], si), __fmul_rn(ddy[k], co)), cy);
         }
     }
-    const float cn = trig_cos<FL>(-th), sn = trig_sin<FL>(-th);
+    // cosf(-th), sinf(-th) of check_in_box2d (kernel.cu:55-56): both implementations are exactly even / odd -- checked over
+    // every float by tests/test_host_emu.py::test_trig_of_the_negated_heading -- so the second pair of calls is a sign flip
+    const float cn = co, sn = -si;
     const float tx = __fadd_rn(hx, 1e-2f), ty = __fadd_rn(hy, 1e-2f);
     const float area = __fmul_rn(dx, dy);
     // Conservative exact-zero cull.  A pair yields a polygon vertex only if an edge of

@@ -261,36 +261,40 @@ __global__ void __launch_bounds__(32)
 // Lazy rotated NMS: one CTA (or one thread-block cluster) per problem, no N x N/64 mask, no separate record kernel.
 //
 // The reference's sweep (iou3d_nms.cpp:121-132) reads row i of the mask only when box i is KEPT, so only
-// kept rows have to exist.  Per pass the CTA takes the next LZ_G boxes that are still alive (speculating
-// that they will all be kept), and evaluates their rows against every later alive box at once:
+// kept rows have to exist.  A problem is worked off in passes; every pass decides a set of CANDIDATES taken from the
+// first alive (undecided) boxes in score order, and evaluates their rows against every later alive box at once:
+//   select -> the alive boxes at and after the cursor are listed densely; the first 4 G of them are the WINDOW.
+//             independent mode (the default): a window box is a candidate iff the exact-zero circle test separates it from
+//               EVERY earlier window box -- whatever those turn out to be, none of them can suppress it, and everything before
+//               the window is decided, so a candidate is KEPT, unconditionally; up to G candidates per pass, no speculation.
+//               The others wait: most are suppressed by a candidate in this very pass, the rest head the next window.
+//             speculative mode (high thresholds, where overlapping boxes mostly survive): the first G alive boxes are the
+//               candidates, all assumed kept; the resolve below sorts it out.  A problem starts in this mode when
+//               thresh > 0.3 and leaves it for good as soon as a pass loses more than a quarter of its candidates.
 //   cull   -> (candidate, box) codes of the pairs the circle test cannot prove disjoint, in a smem queue;
-//   drain  -> the polygon path on full warps; iou(candidate, box) > thresh sets a bit in the candidate's
-//             suppression row (smem);
-//   resolve-> candidates are walked in score order: one that an earlier KEPT candidate of the same pass
-//             suppresses is dropped together with its row (the speculation failed, its row is discarded);
-//             the others are kept and their rows are OR-ed out of the alive bitmap.
+//   drain  -> the polygon path on full warps; iou(candidate, box) > thresh marks the box: in the pass's kill bitmap
+//             (independent mode) or in the candidate's suppression row (speculative mode);
+//   resolve-> speculative mode only: candidates are walked in score order, one that an earlier KEPT candidate of the same
+//             pass suppresses is dropped together with its row; the rows of the others are OR-ed into the kill words;
+//   kill   -> the marked boxes leave the alive bitmap.
 // Every IoU that decides anything is iou_bev(kept box, later box) exactly as in the mask formulation, so the
-// keep list is identical; the work drops from N^2/2 pairs to about (#kept + failed speculations) x N.
+// keep list is identical; the work drops from N^2/2 pairs to about #kept x #alive.
 //
 // A problem is a chain of dependent passes, each of them a handful of latency-bound phases (one polygon round is a
-// ~1500-instruction dependency chain per lane), so the kernel is as fast as it has few passes: 32 candidates per pass
-// fill the polygon rounds (with 8, a pass queued ~120 pairs for 512 threads) and quarter the number of passes; a failed
-// speculation costs a row of pair tests on otherwise idle lanes, not latency.
+// ~1500-instruction dependency chain per lane), so the kernel is as fast as it has few passes and few rounds per pass.
 constexpr int LZ_THREADS = 512;  // one problem is latency-bound: 16 warps hide the polygon path's dependency chains
-constexpr int LZ_G = 32;         // speculative candidates per pass (one lane each in the resolve)
-constexpr int LZ_GH = 16;        // candidates per warp in a sweep: two warp groups share every column word
+constexpr int LZ_G = 32;         // candidates per pass (one lane each in the resolve)
+constexpr int LZ_GH = 16;        // candidates per warp in a sweep: two warp groups share every 32 columns
+constexpr int LZ_WIN = 4 * LZ_G; // window: the first alive boxes among which the candidates are chosen
 constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
 constexpr int LZ_MAX_CLUSTER = 8;     // portable cluster size limit
 constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared memory per CTA on sm_100a, minus the static part
-
-struct LazyLayout;
-static inline int lazy_gcap(int nmax, int nt);  // largest of 32 / 16 / 8 candidates per pass whose layout fits, 0 if none does
 
 struct LazyLayout {
     int words, sstride;  // alive words; pitch of a suppression row (odd: the resolve reads a column of the rows conflict-free)
     int qcap, rarecap;   // u32 codes: candidate << 16 | box.  qcap = one sweep step of the CTA at 100 % survivors + all candidate pairs
     int gcap;            // candidates per pass: LZ_G, fewer when the suppression rows of a very large problem would not fit
-    size_t off_cand, off_cull, off_slab, off_queue, off_rare, off_alive, off_sup, total;
+    size_t off_cand, off_cull, off_slab, off_queue, off_rare, off_alive, off_kill, off_kept, off_prefix, off_win, off_conf, off_dlist, off_sup, total;
     __host__ __device__ explicit LazyLayout(int nmax, int nt = LZ_THREADS, int gcap_ = LZ_G) {
         words = (nmax + 31) / 32;
         sstride = words | 1;
@@ -310,13 +314,25 @@ struct LazyLayout {
         o += (size_t)rarecap * sizeof(uint32_t);
         off_alive = o;
         o += (size_t)words * sizeof(uint32_t);
+        off_kill = o;
+        o += (size_t)words * sizeof(uint32_t);
+        off_kept = o;
+        o += (size_t)words * sizeof(uint32_t);
+        off_prefix = o;
+        o += (size_t)words * sizeof(int);
+        off_win = o;
+        o += (size_t)LZ_WIN * sizeof(int);
+        off_conf = o;
+        o += (size_t)LZ_WIN * sizeof(int);
+        off_dlist = o;
+        o += ((size_t)nmax * sizeof(uint16_t) + 15) / 16 * 16;
         off_sup = o;
         o += (size_t)gcap * sstride * sizeof(uint32_t);
         total = o;
     }
 };
 
-static inline int lazy_gcap(int nmax, int nt) {
+static inline int lazy_gcap(int nmax, int nt) {  // largest of 32 / 16 / 8 candidates per pass whose layout fits, 0 if none does
     for (int g = LZ_G; g >= 8; g >>= 1)
         if (LazyLayout(nmax, nt, g).total <= LZ_SMEM_LIMIT) return g;
     return 0;
@@ -326,7 +342,7 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // NT = 512 threads for one latency-bound problem per SM; NT = 256 (two CTAs per SM) when the batch has several small
-// problems per SM, so that one problem's serial phases (candidate search, resolve, barriers) overlap another's rounds.
+// problems per SM, so that one problem's serial phases (selection, resolve, barriers) overlap another's rounds.
 // rec: workspace, written by the kernel's own prologue (the 112-byte records of lg_geom.cuh, in score order) and read
 // back through L2 -- never through the read-only path, which is not coherent with writes of the same launch.
 template <int FL, bool CL, int NT>
@@ -345,14 +361,20 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     uint32_t* queue = reinterpret_cast<uint32_t*>(sm + L.off_queue);
     uint32_t* rareq = reinterpret_cast<uint32_t*>(sm + L.off_rare);
     uint32_t* alive = reinterpret_cast<uint32_t*>(sm + L.off_alive);
+    uint32_t* killw = reinterpret_cast<uint32_t*>(sm + L.off_kill);
+    uint32_t* keptw = reinterpret_cast<uint32_t*>(sm + L.off_kept);  // kept boxes: independent candidates are kept out of score order
+    int* wprefix = reinterpret_cast<int*>(sm + L.off_prefix);
+    int* window = reinterpret_cast<int*>(sm + L.off_win);
+    int* wconf = reinterpret_cast<int*>(sm + L.off_conf);
+    uint16_t* dlist = reinterpret_cast<uint16_t*>(sm + L.off_dlist);
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     const int SW = L.sstride, QCAP = L.qcap, RARECAP = L.rarecap;
-    __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s;
+    __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s, nwin_s, nalive_s, cursor_s, spec_s;
     __shared__ unsigned long long st_heavy;
 
     // A problem may be spread over a thread-block cluster of C CTAs (C SMs): they keep identical copies of the alive bitmap
     // and of the pass state, split the COLUMNS of every pass (interleaved sweep steps), evaluate the few
-    // candidate-vs-candidate pairs redundantly, and exchange the kill words through distributed shared memory after the resolve.
+    // candidate-vs-candidate pairs redundantly, and exchange the kill words through distributed shared memory.
     // (CL = false compiles all of that out: one CTA per problem.)
     cg::cluster_group cluster = cg::this_cluster();
     const int C = CL ? (int)cluster.num_blocks() : 1, crank = CL ? (int)cluster.block_rank() : 0;
@@ -364,35 +386,9 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     const int64_t base = (int64_t)p * nmax;
     float4* grec = rec + base * REC_F4;
 
-    // ---- prologue: the problem's records, in score order (every CTA of a cluster builds an interleaved share)
-    for (int i = crank * NT + tid; i < n; i += C * NT) {
-        int64_t src = i;
-        if (order) {
-            src = __ldg(order + base + i);
-            if (src < 0 || src >= nmax) src = i;  // defensive: never read out of the problem's rows
-        }
-        make_record<FL>(boxes + (base + src) * 7, grec + (int64_t)i * REC_F4);
-    }
-    for (int w = tid; w < W; w += NT) alive[w] = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu;
-    for (int w = tid; w < gcap * SW; w += NT) sup[w] = 0u;
-    if (tid == 0) {
-        qcount = 0;
-        rcount = 0;
-        nk_s = 0;
-        qvalid_s = QCAP;
-        sfail_s = 0x7fffffff;
-        st_heavy = 0ull;
-    }
-    // records visible to the whole problem (cluster barrier: release / acquire at cluster scope); it also tells every CTA that
-    // its peers have started and initialised their bitmaps, which must hold before any of them is touched remotely
-    if (split) cluster.sync();
-    else __syncthreads();
-    for (int j = tid; j < min(n, LZ_CACHE); j += NT) scull[j] = __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL);
-    int cursor = 0;  // every box below it is decided
-    unsigned my_tested = 0u, my_nonzero = 0u;  // my_tested: warp-uniform, lane 0 reports it
 #ifdef LG_LZ_TIMING  // developer build: cycles per phase of thread 0, accumulated into stats[8 + phase] (tools/lz_timing.py)
     long long tmark = clock64();
-    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int npass = 0;
 #define LZ_MARK(ph)                      \
     if (tid == 0) {                      \
@@ -403,12 +399,42 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
 #else
 #define LZ_MARK(ph)
 #endif
+    // ---- prologue: the problem's records, in score order (every CTA of a cluster builds an interleaved share)
+    for (int i = crank * NT + tid; i < n; i += C * NT) {
+        int64_t src = i;
+        if (order) {
+            src = __ldg(order + base + i);
+            if (src < 0 || src >= nmax) src = i;  // defensive: never read out of the problem's rows
+        }
+        make_record<FL>(boxes + (base + src) * 7, grec + (int64_t)i * REC_F4);
+    }
+    for (int w = tid; w < W; w += NT) {
+        alive[w] = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xFFFFFFFFu;
+        killw[w] = 0u;
+        keptw[w] = 0u;
+    }
+    for (int w = tid; w < gcap * SW; w += NT) sup[w] = 0u;
+    if (tid == 0) {
+        qcount = 0;
+        rcount = 0;
+        nk_s = 0;
+        qvalid_s = QCAP;
+        sfail_s = 0x7fffffff;
+        cursor_s = 0;
+        spec_s = thresh > 0.3f ? 1 : 0;
+        st_heavy = 0ull;
+    }
+    // records visible to the whole problem (cluster barrier: release / acquire at cluster scope); it also tells every CTA that
+    // its peers have started and initialised their bitmaps, which must hold before any of them is touched remotely
+    LZ_MARK(9)  // prologue: records
+    if (split) cluster.sync();
+    else __syncthreads();
+    LZ_MARK(10)  // prologue: barrier
+    for (int j = tid; j < min(n, LZ_CACHE); j += NT) scull[j] = __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL);
+    unsigned my_tested = 0u, my_nonzero = 0u;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    auto quad = [&](const int j) -> float4 { return j < LZ_CACHE ? scull[j] : __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL); };
 
-    auto emit = [&](int g, int j, float ov, const float4* A, const float4* B) {
-        const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);  // row = the higher-scoring box (kernel.cu:304)
-        my_nonzero += ov > 0.f ? 1u : 0u;
-        if (iou > thresh) atomicOr(&sup[g * SW + (j >> 5)], 1u << (j & 31));
-    };
     // optimistic push: the sweeps of a pass run without a barrier and reserve queue space as they go; a reservation that does
     // not fit writes nothing and records where the queue stopped being complete (every later reservation fails as well, so the
     // entries below qvalid_s are exactly those of the successful ones) and the earliest step that lost pairs.
@@ -428,9 +454,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 atomicMin(&sfail_s, step);
             }
         }
-        qb = __shfl_sync(0xffffffffu, qb, 0);
+        qb = __shfl_sync(FULL, qb, 0);
         if (qb + total > QCAP) return;
-        const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
         for (int k = 0; k < GH; k++) {
             if (mk[k]) {
@@ -442,66 +467,146 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
 
     while (true) {
         __syncthreads();
-        // ---- the next G alive boxes at or after the cursor (warp 0)
+        const int cursor = cursor_s;  // every box below it is decided
+        const bool spec = spec_s != 0;
+        const int wincap = spec ? gcap : min(LZ_WIN, 4 * gcap);
+        // ---- (warp 0) alive boxes at and after the cursor: per-word offsets of the dense list, and the window
         if (warp == 0) {
-            int found = 0;
-            if (nk_s < max_keep) {  // NMS_POST_MAXSIZE reached (model_nms_utils.py:20): nothing further can be kept
-                for (int w0 = cursor >> 5; w0 < W && found < gcap; w0 += 32) {
+            int total = 0;
+            // NMS_POST_MAXSIZE (model_nms_utils.py:20): the first max_keep kept boxes in score order are final once that many
+            // are kept BELOW the cursor (independent candidates are kept out of order; everything below the cursor is decided)
+            bool full = max_keep <= 0;
+            if (!full && nk_s >= max_keep) {
+                int kb = 0;
+                for (int w = lane; w <= (cursor >> 5) && w < W; w += 32) {
+                    unsigned word = keptw[w];
+                    if (w == (cursor >> 5)) word &= ~(FULL << (cursor & 31));
+                    kb += __popc(word);
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) kb += __shfl_xor_sync(FULL, kb, d);
+                full = kb >= max_keep;
+            }
+            if (!full) {
+                for (int w0 = cursor >> 5; w0 < W; w0 += 32) {
                     const int w = w0 + lane;
                     unsigned word = w < W ? alive[w] : 0u;
-                    if (w == (cursor >> 5)) word &= 0xFFFFFFFFu << (cursor & 31);
-                    int incl = __popc(word);
+                    if (w == (cursor >> 5)) word &= FULL << (cursor & 31);
+                    const int c = __popc(word);
+                    int incl = c;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        const int v = __shfl_up_sync(FULL, incl, d);
                         if (lane >= d) incl += v;
                     }
-                    int slot = found + incl - __popc(word);
-                    while (word && slot < gcap) {
+                    int slot = total + incl - c;
+                    if (w < W) wprefix[w] = slot;
+                    while (word && slot < wincap) {  // the window: every lane lists the boxes of its own word (few, once the bitmap thins out)
                         const int b = __ffs(word) - 1;
                         word &= word - 1;
-                        group[slot++] = w * 32 + b;
+                        window[slot++] = w * 32 + b;
                     }
-                    found += __shfl_sync(0xffffffffu, incl, 31);
+                    total += __shfl_sync(FULL, incl, 31);
                 }
             }
-            if (lane == 0) ng_s = min(found, gcap);
+            if (lane == 0) {
+                nalive_s = total;
+                nwin_s = min(total, wincap);
+                qcount = 0;  // the queue of the previous pass is drained
+                qvalid_s = QCAP;
+                sfail_s = 0x7fffffff;
+            }
         }
         __syncthreads();
-        LZ_MARK(0)  // candidate search
-        const int ng = ng_s;
-        // cluster: this CTA has chosen its candidates (every CTA picks the same ones from identical bitmaps); peers wait for
-        // this arrival before their kill words of this pass may touch our bitmap (cluster_wait below)
-        if (split) cluster_arrive();
-        if (ng == 0) {
-            if (split) cluster_wait();
-            break;
+        LZ_MARK(0)  // alive scan
+        const int nal = nalive_s, nwin = nwin_s;
+        if (nal == 0) break;  // every CTA of a cluster derives the same pass from identical bitmaps: all leave together
+        // ---- (all) the dense list of alive boxes, four threads per word; and, in independent mode, which window boxes the
+        // circle test cannot separate from an earlier window box
+        for (int wb = cursor >> 5; wb < W; wb += NT / 4) {
+            const int w = wb + (tid >> 2), part = tid & 3;
+            if (w < W) {
+                unsigned word = alive[w];
+                if (w == (cursor >> 5)) word &= FULL << (cursor & 31);
+                unsigned bits = (word >> (8 * part)) & 0xffu;
+                int off = wprefix[w] + __popc(word & ((1u << (8 * part)) - 1u));
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    dlist[off++] = (uint16_t)(w * 32 + 8 * part + b);
+                }
+            }
         }
+        if (!spec) {
+            const int chunk = (wincap + 3) >> 2;
+            for (int b0 = 0; b0 < nwin; b0 += NT / 4) {
+                const int b = b0 + (tid >> 2), part = tid & 3;
+                bool cf = false;
+                if (b < nwin) {
+                    const float4 qb = quad(window[b]);
+                    const int a1 = min(part * chunk + chunk, b);
+                    for (int a = part * chunk; a < a1; a++) cf |= cull_survives(quad(window[a]), qb);
+                    my_tested += (unsigned)max(a1 - part * chunk, 0);
+                }
+                const unsigned m = __ballot_sync(FULL, cf);
+                if (b < nwin && part == 0) wconf[b] = (int)((m >> (lane & ~3)) & 0xfu);
+            }
+        }
+        __syncthreads();
+        LZ_MARK(1)  // dense list + window conflicts
+        // ---- (warp 0) the candidates
+        if (warp == 0) {
+            int cnt = 0, firstskip = -1;
+            for (int c0 = 0; c0 < nwin; c0 += 32) {
+                const int b = c0 + lane;
+                const bool inw = b < nwin;
+                const bool f = inw && (spec || wconf[b] == 0);
+                const unsigned m = __ballot_sync(FULL, f);
+                const int slot = cnt + __popc(m & lt);
+                const bool sel = f && slot < gcap;
+                if (sel) group[slot] = window[b];
+                const unsigned un = __ballot_sync(FULL, inw && !sel);
+                if (firstskip < 0 && un) firstskip = c0 + __ffs(un) - 1;
+                cnt += __popc(m);
+            }
+            if (lane == 0) {
+                ng_s = min(cnt, gcap);  // >= 1: the first window box has no earlier one
+                // next cursor: the first window box that is not a candidate, else the first alive box after the window
+                cursor_s = firstskip >= 0 ? window[firstskip] : (nwin < nal ? (int)dlist[nwin] : n);
+            }
+        }
+        __syncthreads();
+        const int ng = ng_s;
         for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldcg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
         if (tid < ng) {
             const int j = group[tid];
-            scand[tid] = j < LZ_CACHE ? scull[j] : __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL);
-            // the candidates are decided in this pass either way: they leave the alive bitmap now (every CTA of a cluster clears
-            // its own copy), so the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately
+            scand[tid] = quad(j);
+            // the candidates are decided in this pass: they leave the alive bitmap now (every CTA of a cluster clears its own
+            // copy), so the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately
             atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
         }
         __syncthreads();
-        LZ_MARK(1)  // candidate records
-        const int g0 = group[0], glast = group[ng - 1];
-        // ---- rows of the candidates against every later alive box.  Warp group `half` tests its GH candidates against the
-        // 32 columns of one alive word per step; the steps of a pass are interleaved over the CTAs of a cluster.
+        LZ_MARK(2)  // candidates + their records
+        const int g0 = group[0];
+        auto emit = [&](int g, int j, float ov, const float4* A, const float4* B) {
+            const float iou = iou_from_overlap(ov, A[REC_CULL].w, B[REC_CULL].w);  // row = the higher-scoring box (kernel.cu:304)
+            my_nonzero += ov > 0.f ? 1u : 0u;
+            if (iou > thresh) atomicOr(spec ? &sup[g * SW + (j >> 5)] : &killw[j >> 5], 1u << (j & 31));
+        };
+        // ---- rows of the candidates against every later alive box.  Warp group `half` tests its GH candidates against 32
+        // entries of the dense list per step; the steps of a pass are interleaved over the CTAs of a cluster.
         const int half = warp / WG, wcol = warp % WG;
         const int kmax = min(GH, ng - GH * half);  // candidates of this warp group in this pass (<= 0: none)
-        const int nsteps = (n - (((glast + 1) >> 5) << 5) + C * STEP - 1) / (C * STEP);  // per CTA; all boxes up to glast are decided or candidates
-        const int jw0 = ((glast + 1) >> 5) << 5;
+        const int ghi = kmax > 0 ? group[GH * half + kmax - 1] : 0;  // the last of them
+        const int nsteps = (nal + C * STEP - 1) / (C * STEP);  // per CTA
         int s0 = 0;          // first step not yet swept
         bool safe = false;   // after an overflow: one step at a time, which an empty queue always holds
         while (true) {
             const int s1 = safe ? min(s0 + 1, nsteps) : nsteps;
-            // ---- candidate g against the later candidates (part of step 0): EVERY CTA of a cluster evaluates these (at most
-            // G (G - 1) / 2) pairs itself, so each has the complete candidate-vs-candidate bits for the resolve without an exchange
-            // through DSMEM and the cluster barrier it would need
-            if (s0 == 0 && warp < G / GH && warp * GH < ng) {
+            // candidate g against the later candidates (part of step 0; speculative mode only -- independent candidates are
+            // separated by the circle test): EVERY CTA of a cluster evaluates these (at most G (G - 1) / 2) pairs itself, so
+            // each has the complete candidate-vs-candidate bits for the resolve without an exchange through DSMEM
+            if (spec && s0 == 0 && warp < G / GH && warp * GH < ng) {
                 const bool a = lane < ng;
                 const int j = a ? group[lane] : 0;
                 const float4 cj = a ? scand[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -509,129 +614,189 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
 #pragma unroll
                 for (int k = 0; k < GH; k++) {
                     const int g = warp * GH + k;
-                    mk[k] = __ballot_sync(0xffffffffu, a && lane > g && cull_survives(scand[g < ng ? g : 0], cj));  // group[] ascends: lane > g <=> a later box
+                    mk[k] = __ballot_sync(FULL, a && lane > g && cull_survives(scand[g < ng ? g : 0], cj));  // group[] ascends: lane > g <=> a later box
                 }
                 push(mk, warp * GH, j, 0);
-                if (warp == 0 && crank == 0 && !safe) my_tested += (unsigned)(ng * (ng - 1) / 2);
+                if (lane == 0 && warp == 0 && crank == 0 && !safe) my_tested += (unsigned)(ng * (ng - 1) / 2);
             }
             if (kmax > 0) {
                 for (int s = s0; s < s1; s++) {
-                    const int jb = jw0 + (s * C + crank) * STEP + wcol * 32;  // this warp's 32-aligned word of this CTA's columns
-                    if (jb >= n) break;
-                    const unsigned word = alive[jb >> 5];
-                    if (word == 0u) continue;  // warp-uniform
-                    const int j = jb + lane;
-                    const bool a = (word >> lane) & 1u;
-                    const float4 cj = a ? (j < LZ_CACHE ? scull[j] : __ldcg(grec + (int64_t)j * REC_F4 + REC_CULL)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int pos = (s * C + crank) * STEP + wcol * 32 + lane;
+                    const int j = pos < nal ? (int)dlist[pos] : 0;
+                    const bool a = pos < nal && ((alive[j >> 5] >> (j & 31)) & 1u);  // the candidates have left the bitmap
+                    if (!__any_sync(FULL, a)) continue;
+                    const float4 cj = a ? quad(j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     unsigned mk[GH];
+                    if (__all_sync(FULL, !a || j > ghi)) {  // the usual case: every column lies after all of this group's candidates
 #pragma unroll
-                    for (int k = 0; k < GH; k++) {
-                        mk[k] = 0u;
-                        if (k < kmax) mk[k] = __ballot_sync(0xffffffffu, a && cull_survives(scand[GH * half + k], cj));  // warp-uniform guard
+                        for (int k = 0; k < GH; k++) {
+                            mk[k] = 0u;
+                            if (k < kmax) mk[k] = __ballot_sync(FULL, a && cull_survives(scand[GH * half + k], cj));  // warp-uniform guard
+                        }
+                        my_tested += a ? (unsigned)kmax : 0u;
+                    } else {  // window boxes that are not candidates sit between the candidates: only the earlier candidates test them
+#pragma unroll
+                        for (int k = 0; k < GH; k++) {
+                            mk[k] = 0u;
+                            if (k < kmax) {
+                                const bool t = a && j > group[GH * half + k];
+                                my_tested += t ? 1u : 0u;
+                                mk[k] = __ballot_sync(FULL, t && cull_survives(scand[GH * half + k], cj));
+                            }
+                        }
                     }
-                    my_tested += (unsigned)(__popc(word) * kmax);
                     push(mk, GH * half, j, s);
                 }
             }
             __syncthreads();
             const int qn = min(qcount, qvalid_s), rn = rcount, sfail = sfail_s;
-            __syncthreads();
-            LZ_MARK(2)  // cull sweeps
+            LZ_MARK(3)  // cull sweeps
             if (rn + qn > RARECAP) {
                 drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);
                 __syncthreads();
             }
             drain_main<FL, 16, NT, true>(sA, grec, slab, queue, qn, rareq, &rcount, emit);  // column records in global memory: staged
+            if (tid == 0) st_heavy += (unsigned long long)qn;
+            LZ_MARK(4)  // polygon rounds (thread 0's share; the barrier that follows is charged to the next phase)
+            if (sfail == 0x7fffffff && s1 >= nsteps) break;
+            // overflow (adversarial inputs: nearly every pair survives the cull): go on step by step from the first step that lost
+            // pairs; steps >= sfail that did fit are simply evaluated again -- marking a box twice changes nothing
+            __syncthreads();  // everybody has read the counters and left the queue
             if (tid == 0) {
                 qcount = 0;
                 qvalid_s = QCAP;
                 sfail_s = 0x7fffffff;
-                st_heavy += (unsigned long long)qn;
             }
-            LZ_MARK(3)  // polygon rounds (thread 0's share; the barrier that follows is charged to the next phase)
-            if (sfail == 0x7fffffff) {
-                if (s1 >= nsteps) break;
-                s0 = s1;      // safe mode, step by step
-            } else {
-                s0 = sfail;   // pairs were lost from this step on (steps >= sfail that did fit are simply evaluated again:
-                safe = true;  // setting a suppression bit twice changes nothing)
-            }
-            __syncthreads();  // the queue is empty again before the next sweep pushes
+            s0 = sfail == 0x7fffffff ? s1 : sfail;
+            safe = true;
+            __syncthreads();
         }
         __syncthreads();
-        LZ_MARK(4)  // waiting for the last polygon round
-        drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the suppression rows must be complete before the resolve
+        // cluster: this CTA has read its bitmap for the last time in this pass (the dense list and the sweeps' alive test are
+        // behind it); peers wait for this arrival before their kill words of this pass may touch it (cluster_wait below)
+        if (split) cluster_arrive();
+        LZ_MARK(5)  // waiting for the last polygon round
+        drain_rare<FL, 16, NT>(sA, grec, slab, rareq, &rcount, emit);  // the marks must be complete before the resolve / the kills
         __syncthreads();
-        LZ_MARK(5)  // deferred pairs
-        // ---- resolve the speculation in score order (warp 0, lane g = candidate g); the candidate-vs-candidate bits are local
-        // in every CTA (see above)
+        LZ_MARK(6)  // deferred pairs
+        // ---- (warp 0, lane g = candidate g) keep list; in speculative mode first resolve the speculation in score order
         if (warp == 0) {
             const int jl = lane < ng ? group[lane] : 0;
-            const int64_t ol = (lane < ng && order) ? __ldg(order + base + jl) : (int64_t)jl;  // loads issued before the serial part
-            // colm: the earlier candidates h whose row suppresses this lane's candidate (a column of the rows: SW is odd and
-            // the candidates sit in a few neighbouring words, so the loads are broadcasts or conflict-free)
-            unsigned colm = 0u;
-            const int wl = jl >> 5, bl = jl & 31;
-            for (int h = 0; h < ng; h++) colm |= ((sup[h * SW + wl] >> bl) & 1u) << h;
-            colm &= (1u << lane) - 1u;
-            unsigned km = 0u;
+            unsigned km = ng >= 32 ? FULL : ((1u << ng) - 1u);
+            if (spec) {
+                // colm: the earlier candidates h whose row suppresses this lane's candidate (a column of the rows: SW is odd and
+                // the candidates sit in a few neighbouring words, so the loads are broadcasts or conflict-free)
+                unsigned colm = 0u;
+                const int wl = jl >> 5, bl = jl & 31;
+                for (int h = 0; h < ng; h++) colm |= ((sup[h * SW + wl] >> bl) & 1u) << h;
+                colm &= lt;
+                km = 0u;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                const unsigned cg_ = __shfl_sync(0xffffffffu, colm, g);  // independent of the chain: issued ahead of it
-                if (g < ng && (cg_ & km) == 0u) km |= 1u << g;
+                for (int g = 0; g < G; g++) {
+                    const unsigned cg_ = __shfl_sync(FULL, colm, g);  // independent of the chain: issued ahead of it
+                    if (g < ng && (cg_ & km) == 0u) km |= 1u << g;
+                }
             }
-            const int nk = nk_s;
-            const int pos = nk + __popc(km & ((1u << lane) - 1u));
-            if (crank == 0 && ((km >> lane) & 1u) && pos < max_keep) keep[(int64_t)p * keep_ld + pos] = ol;
+            if ((km >> lane) & 1u) atomicOr(&keptw[jl >> 5], 1u << (jl & 31));
             if (lane == 0) {
                 keptmask_s = (int)km;
-                nk_s = min(nk + __popc(km), max_keep);
+                nk_s += __popc(km);
+                if (spec && __popc(km) * 4 < ng * 3) spec_s = 0;  // speculation does not pay on this problem
             }
         }
-        __syncthreads();
-        LZ_MARK(6)  // resolve
-        const unsigned km = (unsigned)keptmask_s;
-        if (split) cluster_wait();  // every peer has chosen its candidates of this pass: its bitmap may be touched now
-        // kill words: four threads per word, eight rows each
-        for (int wb = (g0 >> 5); wb < W; wb += NT / 4) {
-            const int w = wb + (tid >> 2), part = tid & 3;
-            unsigned kill = 0u;
-            if (w < W) {
+        if (spec) __syncthreads();
+        LZ_MARK(7)  // keep list (+ resolve)
+        if (split) cluster_wait();  // every peer is done reading its bitmap for this pass: it may be touched now
+        // ---- the marked boxes leave the alive bitmap
+        if (spec) {  // kill words from the kept candidates' rows: four threads per word, eight rows each
+            const unsigned km = (unsigned)keptmask_s;
+            for (int wb = (g0 >> 5); wb < W; wb += NT / 4) {
+                const int w = wb + (tid >> 2), part = tid & 3;
+                unsigned kill = 0u;
+                if (w < W) {
 #pragma unroll
-                for (int k = 0; k < G / 4; k++) {
-                    const int g = part * (G / 4) + k;
-                    if (g < ng) {
-                        if ((km >> g) & 1u) kill |= sup[g * SW + w];
-                        sup[g * SW + w] = 0u;
+                    for (int k = 0; k < G / 4; k++) {
+                        const int g = part * (G / 4) + k;
+                        if (g < ng) {
+                            if ((km >> g) & 1u) kill |= sup[g * SW + w];
+                            sup[g * SW + w] = 0u;
+                        }
+                    }
+                }
+                kill |= __shfl_xor_sync(FULL, kill, 1);
+                kill |= __shfl_xor_sync(FULL, kill, 2);
+                if (w < W && part == 0 && kill) {
+                    if (split) {  // peers update the same words: atomics everywhere
+                        for (int r = 0; r < C; r++) atomicAnd(cluster.map_shared_rank(&alive[w], r), ~kill);
+                    } else {
+                        alive[w] &= ~kill;
                     }
                 }
             }
-            kill |= __shfl_xor_sync(0xffffffffu, kill, 1);
-            kill |= __shfl_xor_sync(0xffffffffu, kill, 2);
-            if (w < W && part == 0 && kill) {
-                if (split) {  // peers update the same words: atomics everywhere
-                    for (int r = 0; r < C; r++) atomicAnd(cluster.map_shared_rank(&alive[w], r), ~kill);
-                } else {
-                    alive[w] &= ~kill;
+        } else {
+            for (int w = (g0 >> 5) + tid; w < W; w += NT) {
+                const unsigned kill = killw[w];
+                if (kill) {
+                    killw[w] = 0u;
+                    if (split) {
+                        for (int r = 0; r < C; r++) atomicAnd(cluster.map_shared_rank(&alive[w], r), ~kill);
+                    } else {
+                        alive[w] &= ~kill;
+                    }
                 }
             }
         }
-        cursor = glast + 1;
 #ifdef LG_LZ_TIMING
         npass++;
 #endif
-        if (split) cluster.sync();  // every CTA's kill words have landed everywhere before the next candidates are chosen
-        LZ_MARK(7)  // kill words (+ cluster sync)
+        if (split) cluster.sync();  // every CTA's kill words have landed everywhere before the next pass reads the bitmap
+        LZ_MARK(8)  // kill words (+ cluster sync)
     }
-    // all threads left the loop together
-    const int nk = nk_s;
+    // all threads left the loop together.  The keep list: the kept boxes in score order (= ascending position), the first
+    // max_keep of them, mapped through `order`; -1 beyond.
     if (crank == 0) {
+        if (warp == 0) {
+            int total = 0;
+            for (int w0 = 0; w0 < W; w0 += 32) {
+                const int w = w0 + lane;
+                const int c = w < W ? __popc(keptw[w]) : 0;
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (w < W) wprefix[w] = total + incl - c;
+                total += __shfl_sync(FULL, incl, 31);
+            }
+            if (lane == 0) nk_s = min(total, max_keep);
+        }
+        __syncthreads();
+        const int nk = nk_s;
         if (tid == 0) num_keep[p] = nk;
-        for (int i = nk + tid; i < max_keep; i += NT) keep[(int64_t)p * keep_ld + i] = -1;
+        int64_t* const krow = keep + (int64_t)p * keep_ld;
+        for (int wb = 0; wb < W; wb += NT / 4) {
+            const int w = wb + (tid >> 2), part = tid & 3;
+            if (w < W) {
+                const unsigned word = keptw[w];
+                unsigned bits = (word >> (8 * part)) & 0xffu;
+                int off = wprefix[w] + __popc(word & ((1u << (8 * part)) - 1u));
+                while (bits && off < max_keep) {
+                    const int j = w * 32 + 8 * part + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    krow[off++] = order ? __ldg(order + base + j) : (int64_t)j;
+                }
+            }
+        }
+        for (int i = nk + tid; i < max_keep; i += NT) krow[i] = -1;
     }
+    LZ_MARK(11)  // keep list emission
     if (stats) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) my_nonzero += __shfl_xor_sync(0xffffffffu, my_nonzero, d);
+        for (int d = 16; d > 0; d >>= 1) {
+            my_tested += __shfl_xor_sync(FULL, my_tested, d);
+            my_nonzero += __shfl_xor_sync(FULL, my_nonzero, d);
+        }
         if (lane == 0) {
             atomicAdd(stats, (unsigned long long)my_tested);
             atomicAdd(stats + 2, (unsigned long long)my_nonzero);
@@ -639,12 +804,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         if (tid == 0) atomicAdd(stats + 1, st_heavy);
 #ifdef LG_LZ_TIMING
         if (tid == 0) {
-            for (int ph = 0; ph < 8; ph++) atomicAdd(stats + 8 + ph, (unsigned long long)tacc[ph]);
-            atomicAdd(stats + 16, (unsigned long long)npass);
-            atomicMax(stats + 17, (unsigned long long)npass);
+            for (int ph = 0; ph < 12; ph++) atomicAdd(stats + 8 + ph, (unsigned long long)tacc[ph]);
+            atomicAdd(stats + 20, (unsigned long long)npass);
+            atomicMax(stats + 21, (unsigned long long)npass);
             unsigned long long tsum = 0ull;
-            for (int ph = 0; ph < 8; ph++) tsum += (unsigned long long)tacc[ph];
-            atomicMax(stats + 18, tsum);
+            for (int ph = 0; ph < 12; ph++) tsum += (unsigned long long)tacc[ph];
+            atomicMax(stats + 22, tsum);
         }
 #endif
     }

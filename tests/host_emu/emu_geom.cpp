@@ -187,3 +187,20 @@ extern "C" void emu_points_mask(const float* boxes, int T, const float* pts, lon
         }
     }
 }
+
+// sinf(-x) == -sinf(x) and cosf(-x) == cosf(x), bit for bit, in both flavors' implementations (make_record computes the
+// trigonometry of -heading from that of +heading): count of float bit patterns first, first + stride, ... that violate it
+extern "C" long long emu_trig_symmetry_sweep(unsigned first, unsigned stride, long long count, int flavor, unsigned* first_bad) {
+    long long bad = 0;
+    unsigned u = first;
+    for (long long i = 0; i < count; i++, u += stride) {
+        const float f = __uint_as_float(u & 0x7fffffffu);
+        if (!(f == f)) continue;
+        const float sp = flavor ? lgo_sinf(f, 1) : glibc_sincosf(f, 0), sn = flavor ? lgo_sinf(-f, 1) : glibc_sincosf(-f, 0);
+        const float cp = flavor ? lgo_cosf(f, 1) : glibc_sincosf(f, 1), cn = flavor ? lgo_cosf(-f, 1) : glibc_sincosf(-f, 1);
+        const bool ok = (__float_as_uint(sn) == (__float_as_uint(sp) ^ 0x80000000u) || (sp != sp && sn != sn)) &&
+                        (__float_as_uint(cn) == __float_as_uint(cp) || (cp != cp && cn != cn));
+        if (!ok && bad++ == 0 && first_bad) *first_bad = u;
+    }
+    return bad;
+}

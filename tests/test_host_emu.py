@@ -25,6 +25,8 @@ def emu():
     L.emu_glibc_sweep.restype = C.c_longlong
     L.emu_glibc_sweep.argtypes = [C.c_uint, C.c_uint, C.c_longlong, C.POINTER(C.c_uint)]
     L.emu_points_mask.argtypes = [fp, C.c_int, fp, C.c_longlong, ip, C.c_int]
+    L.emu_trig_symmetry_sweep.restype = C.c_longlong
+    L.emu_trig_symmetry_sweep.argtypes = [C.c_uint, C.c_uint, C.c_longlong, C.c_int, C.POINTER(C.c_uint)]
     return L
 
 
@@ -68,6 +70,16 @@ def test_device_restatement_of_glibc_sinf_cosf_matches_the_host_libm(emu):
     lo, hi = np.float32(0.78).view(np.uint32), np.float32(6.5).view(np.uint32)  # [0.78, 6.5]: pi/4 .. beyond 2 pi, every float
     for sign in (0, 1 << 31):
         assert emu.emu_glibc_sweep(int(lo) | sign, 1, int(hi - lo), C.byref(fb)) == 0, hex(fb.value)
+
+
+def test_trig_of_the_negated_heading(emu):
+    """make_record takes cosf(-th), sinf(-th) (check_in_box2d, kernel.cu:55-56) as cosf(th), -sinf(th): both trig implementations
+    (the oracle's restatement of libdevice, and glibc's restated for the device) are exactly even / odd.  Every 8th positive
+    float here; exhaustively: 0 violations for glibc, and only x = +0 for the libdevice restatement (sinf(-0) = +0 there; IEEE
+    and the device say -0, which is what the sign flip gives -- the sign of a zero sine never reaches a result)."""
+    fb = C.c_uint(0)
+    for flavor in (0, 1):
+        assert emu.emu_trig_symmetry_sweep(3, 8, 1 << 28, flavor, C.byref(fb)) == 0, (flavor, hex(fb.value))
 
 
 @pytest.mark.parametrize("name", sorted(SETS))

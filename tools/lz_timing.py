@@ -33,9 +33,10 @@ for _ in range(2):
 torch.cuda.synchronize()
 off = L.lg_nms_stats_offset(P, N)
 st = ws[off:off + 256].view(torch.int64).cpu().tolist()
-names = ["candidate search", "candidate records", "cull sweeps", "polygon rounds (thread 0)", "wait for last round", "deferred pairs", "resolve", "kill + cluster sync"]
-tot = sum(st[8:16])
+names = ["alive scan", "dense list + conflicts", "candidates + records", "cull sweeps", "polygon rounds (thread 0)", "wait for last round", "deferred pairs",
+         "keep list (+ resolve)", "kill + cluster sync", "prologue: records", "prologue: barrier", "epilogue: keep list"]
+tot = sum(st[8:20])
 print("pairs cull-tested", st[0], "polygon", st[1], "nonzero", st[2], "kept/frame", float(num.float().mean()))
-for n, v in zip(names, st[8:16]):
+for n, v in zip(names, st[8:20]):
     print(f"{n:28s} {v / max(tot, 1) * 100:5.1f} %   {v / 1.965e3 / (2 * P):8.1f} us per CTA")
-print("sum per CTA", tot / 1.965e3 / (2 * P), "us;  passes per CTA: mean", st[16] / (2 * P), "max", st[17], ";  slowest CTA", st[18] / 1.965e3, "us")
+print("sum per CTA", tot / 1.965e3 / (2 * P), "us;  passes per CTA: mean", st[20] / (2 * P), "max", st[21], ";  slowest CTA", st[22] / 1.965e3, "us")
