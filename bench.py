@@ -152,7 +152,7 @@ class Workload:
 class NmsWorkload(Workload):
     dtype = "f32"
 
-    def __init__(self, torch, which, rank):
+    def __init__(self, torch, which, rank, world=1):
         from lidardetection_b200 import synth
 
         self.torch = torch
@@ -161,36 +161,69 @@ class NmsWorkload(Workload):
             self.boxes_np, self.scores_np = synth.cfg2(64, 4096, seed=synth.SEEDS["cfg2"] + 1000 * rank)
             self.thresh, self.name = 0.01, "SECOND KITTI post-processing: rotated nms_gpu 4096 boxes/frame, thresh 0.01, 64 frames per GPU"
             self.metric, self.unit = "rotated NMS frames/s (4096 boxes/frame)", "frames/s"
+            self.post = 500  # NMS_POST_MAXSIZE of the config (second.yaml:94-99, "4096 -> 500"): keep comes back as (64, 500)
         else:
             b, s = synth.cfg5(256, 10, 1000, seed=synth.SEEDS["cfg5"] + 1000 * rank)
             self.boxes_np, self.scores_np = b.reshape(-1, 1000, 7), s.reshape(-1, 1000)
             self.thresh, self.name = 0.2, "NuScenes CBGS multi-head NMS: 10 classes x 1000 boxes x 256 frames per GPU, thresh 0.2"
             self.metric, self.unit = "rotated NMS problems/s (1000 boxes/problem)", "problems/s"
+            self.post = 83  # cbgs_second_multihead.yaml:196-206
+        self.world = world
+        self.multi_gpu_note = ("frames sharded by rank (weak scaling: every rank its own frames); keep lists + counts of all ranks gathered every "
+                               "step with ONE NCCL all_gather_into_tensor of a packed (frames, 1 + NMS_POST_MAXSIZE) int64 block per rank, inside "
+                               "the timed region (lidardetection_b200.sharded.nms_batched_sharded); `strong` = the config's fixed total split over N")
         self.units = self.boxes_np.shape[0]
         self.boxes = torch.from_numpy(self.boxes_np).cuda()
         self.scores = torch.from_numpy(self.scores_np).cuda()
         self.h_boxes = torch.from_numpy(self.boxes_np).pin_memory()
         self.h_scores = torch.from_numpy(self.scores_np).pin_memory()
-        # select_topk_kernel (the score sort; torch's segmented sort for batches of more than 296 problems), nms_prep_kernel, nms_lazy_kernel
-        self.launches_per_step = 3 if self.units <= 296 else 2
+        # select_topk_kernel (the score sort; torch's segmented sort for batches of more than 296 problems) + nms_lazy_kernel
+        self.launches_per_step = 2 if self.units <= 296 else 1
         self.h2d = self.h_boxes.numel() * 4 + self.h_scores.numel() * 4
         self.d2h = 0  # set by e2e_step from the tensors it copies
 
-    def step(self):
+    def _nms(self, boxes, scores):
+        """N = 1: the batched op.  N > 1: the same through lidardetection_b200.sharded -- every rank runs its own frames and
+        the truncated keep lists + counts of ALL ranks are all-gathered (one NCCL all_gather_into_tensor of a packed
+        (frames, 1 + NMS_POST_MAXSIZE) int64 block per rank) inside the timed region."""
+        if self.world > 1:
+            from lidardetection_b200 import sharded
+
+            return sharded.nms_batched_sharded(boxes, scores, self.thresh, max_keep=self.post, local_inputs=True)
         from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
 
-        return U.nms_gpu_batched(self.boxes, self.scores, self.thresh)
+        return U.nms_gpu_batched(boxes, scores, self.thresh, max_keep=self.post)
+
+    def step(self):
+        return self._nms(self.boxes, self.scores)
 
     def e2e_step(self):
-        from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
-
         b = self.h_boxes.cuda(non_blocking=True)
         s = self.h_scores.cuda(non_blocking=True)
-        keep, num = U.nms_gpu_batched(b, s, self.thresh)
+        keep, num = self._nms(b, s)
         num_h = num.cpu()  # the result a caller reads: the counts, then the kept indices (the padding stays on the device)
-        keep_h = keep[:, : int(num_h.max())].cpu()
+        keep_h = keep[:, : max(int(num_h.max()), 1)].cpu()
         self.d2h = num_h.numel() * 4 + keep_h.numel() * 8  # counted from the tensors copied
         return keep_h, num_h
+
+    def strong_setup(self):
+        """strong scaling: the config's own job size -- cfg2: 64 frames in total, cfg5: 256 frames x 10 classes in total --
+        replicated on every rank and split by sharded.nms_batched_sharded, results all-gathered"""
+        from lidardetection_b200 import synth
+
+        torch = self.torch
+        if self.which == "nms_cfg2":
+            b, s = synth.cfg2(64, 4096, seed=synth.SEEDS["cfg2"])
+        else:
+            b5, s5 = synth.cfg5(256, 10, 1000, seed=synth.SEEDS["cfg5"])
+            b, s = b5.reshape(-1, 1000, 7), s5.reshape(-1, 1000)
+        self.s_boxes, self.s_scores = torch.from_numpy(b).cuda(), torch.from_numpy(s).cuda()
+        return b.shape[0]
+
+    def strong_step(self):
+        from lidardetection_b200 import sharded
+
+        return sharded.nms_batched_sharded(self.s_boxes, self.s_scores, self.thresh, max_keep=self.post)
 
     def result_for_gather(self, out):
         return list(out)
@@ -278,7 +311,7 @@ class NmsWorkload(Workload):
 class IouWorkload(Workload):
     dtype = "f32"
 
-    def __init__(self, torch, which, rank, world):
+    def __init__(self, torch, which, rank, world, light=False):  # light: device-resident timing only, no pinned host copies
         from lidardetection_b200 import synth
 
         self.torch, self.which = torch, which
@@ -297,7 +330,8 @@ class IouWorkload(Workload):
             self.fn, self.name = "boxes_iou3d_gpu", "Waymo-scale evaluation IoU: boxes_iou3d 25,000-row shard x 200,000 boxes per GPU (200k x 200k over 8 shards)"
         self.a_np, self.b_np = a, b
         self.a, self.b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
-        self.h_a, self.h_b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+        if not light:
+            self.h_a, self.h_b = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
         self.pairs = a.shape[0] * b.shape[0]
         self.units = self.pairs / 1e9
         self.out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device="cuda")
@@ -306,7 +340,7 @@ class IouWorkload(Workload):
         self.h2d = (a.size + b.size) * 4
         self.e2e_d2h_full = self.pairs * 4 <= (1 << 30)
         self.d2h = self.pairs * 4 if self.e2e_d2h_full else a.shape[0] * 8
-        self.h_out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32).pin_memory() if self.e2e_d2h_full else None
+        self.h_out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32).pin_memory() if (self.e2e_d2h_full and not light) else None
 
     def _call(self, a, b):
         from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
@@ -356,8 +390,12 @@ class IouWorkload(Workload):
                     "algorithmic": {"pairs_per_launch": self.pairs, "nonzero_fraction": nz, "flops_per_pair": 307.0 * (1 - nz) + 818.0 * nz}}
         byts = 4.0 * n * m + 28.0 * (n + m)
         ach = byts / t / 1e9
-        return {"bound": "hbm", "kernel": "iou_strip_kernel / iou_flat_kernel (+prep_kernel)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "4*N*M + 28*(N+M)"}}
+        r = {"bound": "hbm", "kernel": "iou_strip_kernel / iou_flat_kernel (+prep_kernel)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+             "traffic": None, "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "4*N*M + 28*(N+M)"}}
+        if self.which == "iou_cfg1":
+            r["note"] = ("launch / tail bound, not bandwidth bound: one 35 us launch writes 26 MB, which is still in the 126 MB L2 when the "
+                         "kernel ends (DRAM traffic under ncu is a third of the algorithmic bytes); the fraction measures launch latency")
+        return r
 
     def cpu_sample(self, pool):
         rows = {"iou_dense": 2048, "iou_cfg1": 321408, "iou_cfg4": 2000}[self.which]
@@ -370,7 +408,7 @@ class IouWorkload(Workload):
 class PibWorkload(Workload):
     dtype = "f32"
 
-    def __init__(self, torch, rank):
+    def __init__(self, torch, rank, light=False):
         from lidardetection_b200 import synth
 
         self.torch = torch
@@ -382,7 +420,8 @@ class PibWorkload(Workload):
         self.metric, self.unit = "points-in-boxes frames/s (16,384 pts x 100 ROIs)", "frames/s"
         self.units = B
         self.pts, self.rois = torch.from_numpy(self.pts_np).cuda(), torch.from_numpy(self.rois_np).cuda()
-        self.h_pts, self.h_rois = torch.from_numpy(self.pts_np).pin_memory(), torch.from_numpy(self.rois_np).pin_memory()
+        if not light:
+            self.h_pts, self.h_rois = torch.from_numpy(self.pts_np).pin_memory(), torch.from_numpy(self.rois_np).pin_memory()
         self.launches_per_step = 1
         self.h2d = (self.pts_np.size + self.rois_np.size) * 4
         self.d2h = B * 16384 * 4
@@ -753,17 +792,119 @@ class IouMaxWorkload(Workload):
         return a.shape[0] * b.shape[0] / dt / 1e9, f"boxes_iou_bev_cpu on a {a.shape[0]} x {b.shape[0]} slice in row blocks (the reference has to build the matrix to take its max)"
 
 
-def make_workload(torch, which, rank, world):
+# ------------------------------------------------------------------------------------------------
+def timed_steps(torch, fn, steps, warmup, flush, world):
+    """CUDA-event time of `steps` calls of fn (L2 flushed before each, outside the events), summed, max over ranks -> ms"""
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        e.synchronize()
+        ms += s.elapsed_time(e)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_secondary(torch, which, rank, world, hbm_peak, hbm_src, fp32_peak, flush):
+    """the other halves of BASELINE.json's metric, measured in the same driver-run invocation: rotated-IoU Gpairs/s (dense =
+    FP32 roofline, cfg4 shard = HBM roofline) and points-in-boxes frames/s.  Every rank runs its own shard / replica (no
+    collective: SURVEY 8e, the matrices and index blocks stay with their owner); time = max over ranks."""
+    wl = make_workload(torch, which, rank, world, light=True)
+    steps = 5
+    ms = timed_steps(torch, wl.step, steps, 3, flush, world)
+    out = {"workload": wl.name, "metric": wl.metric, "unit": wl.unit, "value": wl.units * world * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+           "steps": steps, "warmup": 3, "gpu_launches_per_step": wl.launches_per_step, "dtype": wl.dtype}
+    if rank == 0:
+        r = wl.roofline(3, hbm_peak, hbm_src, fp32_peak)
+        tr, src = ncu_traffic(which)
+        if tr is not None:
+            r["traffic"], r["traffic_source"] = tr, src
+        out["roofline"] = r
+    del wl
+    torch.cuda.empty_cache()
+    return out
+
+
+def gpu_baseline(torch, wl):
+    """the reference's own CUDA kernels (oracle/_ref: the unmodified sources compiled for sm_100a) on this GPU, outside every timed
+    region: boxes_iou_bev_gpu on the dense 16384^2 microbenchmark (iou3d_nms_kernel.cu:251-265) and the per-frame nms_gpu of the
+    default workload (iou3d_nms.cpp:90-136: kernel, blocking D2H of the mask, host sweep), plus OUR per-frame nms_gpu -- the
+    reference's actual call pattern (detector3d_template.py:190-260) -- next to the batched call the headline times."""
+    from lidardetection_b200 import synth
+    from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+    from oracle import ref_loader as R
+
+    res = {}
+    frames = min(16, wl.boxes.shape[0])
+    for _ in range(2):
+        for f in range(frames):
+            U.nms_gpu(wl.boxes[f], wl.scores[f], wl.thresh)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(frames):
+        U.nms_gpu(wl.boxes[f], wl.scores[f], wl.thresh)  # one frame per call, the keep count read back per call, as the reference API forces
+    torch.cuda.synchronize()
+    res["ours_per_frame_nms_gpu_ms"] = 1e3 * (time.perf_counter() - t0) / frames
+    if not R.available():
+        res["reference_cuda"] = "oracle/_ref did not travel with this snapshot"
+        return res
+    ref = R.iou3d_nms_cuda()
+    a, b = synth.dense_overlap(16384, 16384, seed=synth.SEEDS["dense"])
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.zeros((16384, 16384), device="cuda")
+    ref.boxes_iou_bev_gpu(ta, tb, out)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(2):
+        ref.boxes_iou_bev_gpu(ta, tb, out)
+    e.record()
+    e.synchronize()
+    res["reference_boxes_iou_bev_gpu_dense_gpairs"] = 2 * 16384 * 16384 / (s.elapsed_time(e) * 1e-3) / 1e9
+    del out, ta, tb
+    order = wl.scores.sort(1, descending=True)[1]
+    sorted_boxes = [wl.boxes[f][order[f]].contiguous() for f in range(frames)]
+    keep = torch.LongTensor(wl.boxes.shape[1])
+    ref.nms_gpu(sorted_boxes[0], keep, wl.thresh)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(frames):
+        ref.nms_gpu(sorted_boxes[f], keep, wl.thresh)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / frames
+    res["reference_nms_gpu_per_frame_ms"] = 1e3 * dt
+    res["reference_nms_gpu_frames_per_s"] = 1.0 / dt
+    res["what"] = ("reference CUDA kernels recompiled unmodified for sm_100a (oracle/_ref), same GPU, outside the timed regions; nms_gpu timed on "
+                   f"{frames} pre-sorted frames of {wl.boxes.shape[1]} boxes, one call per frame (its API has no batch dimension)")
+    return res
+
+
+def make_workload(torch, which, rank, world, light=False):
     if which == "post_cfg2":
         return PostProcWorkload(torch, rank)
     if which == "iou_max_cfg4":
         return IouMaxWorkload(torch, rank, world)
     if which in ("nms_cfg2", "nms_cfg5"):
-        return NmsWorkload(torch, which, rank)
+        return NmsWorkload(torch, which, rank, world)
     if which in ("iou_dense", "iou_cfg1", "iou_cfg4"):
-        return IouWorkload(torch, which, rank, world)
+        return IouWorkload(torch, which, rank, world, light)
     if which == "pib_cfg3":
-        return PibWorkload(torch, rank)
+        return PibWorkload(torch, rank, light)
     if which in ("roiaware_partA2", "roipoint_pointrcnn"):
         return RoiPoolWorkload(torch, which, rank)
     if which == "kitti_eval":
@@ -884,6 +1025,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="nms_cfg2", choices=["nms_cfg2", "nms_cfg5", "iou_dense", "iou_cfg1", "iou_cfg4", "pib_cfg3", "post_cfg2", "iou_max_cfg4", "roiaware_partA2", "roipoint_pointrcnn", "kitti_eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary metrics and the GPU baseline of the default workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -928,15 +1070,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather(out):
-        # The path has no exchange step: every rank keeps the results of the frames / row blocks it
-        # owns, exactly as the reference's DDP evaluation does (eval_utils.py:54-57; results are merged once, at the end of
-        # the epoch, through pickle files: common_utils.py:206-227).  So there is no per-step collective to time.
-        return out
-
     # ---- device-resident timing -----------------------------------------------------------------
     for _ in range(args.warmup):
-        gather(wl.step())
+        wl.step()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -947,7 +1083,7 @@ def main():
         flush.zero_()  # L2 flush between timed iterations (outside the events)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        gather(wl.step())
+        wl.step()
         e.record()
         e.synchronize()
         dev_ms += s.elapsed_time(e)
@@ -979,11 +1115,29 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = float(tt[0]), float(tt[1])
 
+    # ---- strong scaling (N > 1, NMS workloads): the config's own total job split over the ranks, keep lists all-gathered
+    strong = None
+    if world > 1 and hasattr(wl, "strong_setup"):
+        total = wl.strong_setup()
+        ms = timed_steps(torch, wl.strong_step, args.steps, args.warmup, flush, world)
+        strong = {"value": total * args.steps / (ms * 1e-3), "unit": wl.unit, "ms_per_step": ms / args.steps, "units_total": total,
+                  "what": f"{total} problems in total, contiguous blocks of ceil({total} / {world}) per rank (sharded.nms_batched_sharded), one "
+                          "all_gather_into_tensor of the packed (block, 1 + NMS_POST_MAXSIZE) int64 results inside the timed region"}
+
     roofline = wl.roofline(args.steps, hbm_peak, hbm_src, fp32_peak) if rank == 0 else None
     if roofline is not None:
         tr, src = ncu_traffic(args.workload)
         if tr is not None:
             roofline["traffic"], roofline["traffic_source"] = tr, src
+    gbase = None
+    if rank == 0 and world == 1 and isinstance(wl, NmsWorkload) and not args.no_secondary:
+        gbase = gpu_baseline(torch, wl)
+    # ---- the other halves of the metric (default workload only): rotated-IoU Gpairs/s and points-in-boxes frames/s
+    secondary = None
+    if args.workload == "nms_cfg2" and not args.no_secondary:
+        del wl.boxes, wl.scores
+        torch.cuda.empty_cache()
+        secondary = {w: run_secondary(torch, w, rank, world, hbm_peak, hbm_src, fp32_peak, flush) for w in ("iou_dense", "iou_cfg4", "pib_cfg3")}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -996,12 +1150,13 @@ def main():
         "dtype": wl.dtype, "data": "synthetic (seeded, SURVEY.md 8d shapes; no datasets offline)",
         "config": {"workload": wl.name, "units_per_step_per_gpu": wl.units, "l2": "256 MB L2 flush between timed iterations",
                    "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
-                   "multi_gpu": "independent problems per rank, no data-path collective (results stay on the owning rank, as in the "
-                                "reference's DDP evaluation); NCCL only for the barrier and the max-over-ranks of the timings"
+                   "multi_gpu": (getattr(wl, "multi_gpu_note", None) or
+                                 "independent problems per rank, no data-path collective (results stay on the owning rank, as in the "
+                                 "reference's DDP evaluation); NCCL only for the barrier and the max-over-ranks of the timings")
                    if world > 1 else "single GPU"},
         "e2e": {"value": total_units * args.steps / e2e_s, "unit": wl.unit, "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h)},
         "gpu_launches": wl.launches_per_step * args.steps,
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "strong": strong, "secondary": secondary, "gpu_baseline": gbase,
         "fp32_peak_tflops_measured": fp32_peak, "hbm_peak_gbs": hbm_peak,
     }
     print(json.dumps(line), flush=True)

@@ -225,7 +225,7 @@ def nms_normal_gpu(boxes, scores, thresh, **kwargs):
     return _nms_single('lg_nms_normal_batched', boxes, scores, thresh, None)
 
 
-def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE, max_keep=None):
+def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE, max_keep=None, keep_out=None):
     assert boxes.dim() == 3 and boxes.shape[2] == 7 and scores.shape == boxes.shape[:2]
     b = boxes.contiguous().float()
     if counts is not None:
@@ -233,24 +233,28 @@ def _nms_batched(fn_name, boxes, scores, thresh, counts, flags=_lib.LG_FLAG_NONE
         idx = torch.arange(b.shape[1], device=b.device).unsqueeze(0)
         scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
         counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
-    buffers = _nms_buffers(fn_name, b.shape[0], b.shape[1], b.device, flags, max_keep)
+    keep, num, ws = _nms_buffers(fn_name, b.shape[0], b.shape[1], b.device, flags, max_keep)
+    if keep_out is not None:  # caller-owned keep (any row pitch, e.g. a slice of a send buffer): written in place
+        assert keep_out.dtype == torch.int64 and keep_out.shape == keep.shape and keep_out.stride(1) == 1 and keep_out.device == b.device
+        keep = keep_out
     order = _argsort_desc(scores)
-    return _nms_call(fn_name, b, order, counts, thresh, flags, buffers, max_keep)
+    return _nms_call(fn_name, b, order, counts, thresh, flags, (keep, num, ws), max_keep)
 
 
-def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False, max_keep=None):
+def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False, max_keep=None, keep_out=None):
     """P independent rotated-NMS problems in two launches (score sort, lazy NMS incl. its records) and no host sync.
     :param boxes: (P, N, 7), :param scores: (P, N), :param counts: optional (P,) valid boxes per problem
     :param full_mask: materialise the reference's N x N/64 suppression mask and sweep it (three launches)
         instead of evaluating kept rows only; the keep lists are identical
     :param max_keep: NMS_POST_MAXSIZE (model_nms_utils.py:20): only the first max_keep kept boxes are wanted; keep is then
         (P, min(max_keep, N)) and the kernel stops once a problem's row is full
+    :param keep_out: optional caller-owned int64 (P, K) tensor (unit column stride, any row pitch) to receive keep
     :return: keep (P, N) int64 indices into each problem's boxes, padded with -1; num_keep (P,) int32
     """
     flags = _lib.LG_FLAG_NMS_FULL_MASK if full_mask else _lib.LG_FLAG_NONE
-    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts, flags, max_keep)
+    return _nms_batched('lg_nms_rotated_batched', boxes, scores, thresh, counts, flags, max_keep, keep_out)
 
 
-def nms_normal_gpu_batched(boxes, scores, thresh, counts=None, max_keep=None):
+def nms_normal_gpu_batched(boxes, scores, thresh, counts=None, max_keep=None, keep_out=None):
     """Batched axis-aligned NMS; see nms_gpu_batched."""
-    return _nms_batched('lg_nms_normal_batched', boxes, scores, thresh, counts, max_keep=max_keep)
+    return _nms_batched('lg_nms_normal_batched', boxes, scores, thresh, counts, max_keep=max_keep, keep_out=keep_out)

@@ -61,10 +61,17 @@ def boxes_iou_sharded(boxes_a, boxes_b, kind="iou3d", gather=False, group=None, 
     return block, (start, stop)
 
 
-def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather=True, group=None, compute=None):
-    """Frame-sharded batched NMS.  boxes (P, N, 7), scores (P, N) replicated on every rank.
+def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather=True, group=None, compute=None, max_keep=None,
+                        local_inputs=False):
+    """Frame-sharded batched NMS.  boxes (P, N, 7), scores (P, N) replicated on every rank (local_inputs=False: every rank
+    works on its contiguous block of the P problems), or -- local_inputs=True, the data-parallel inference case -- already
+    this rank's own block of a global batch of world x P problems.
 
-    Returns keep (P, N) int64 (-1 padded) and num_keep (P,) int32 for all problems (gather=True), or this
+    max_keep: NMS_POST_MAXSIZE (model_nms_utils.py:20) -- only the first max_keep kept boxes of a problem are produced and
+    gathered (the reference merges the truncated per-frame results, common_utils.py:206-227, through pickle files and two
+    barriers; here it is ONE all_gather_into_tensor of a packed (block, 1 + max_keep) int64 tensor: column 0 the count, the
+    rest the kept indices, which the NMS kernel writes straight into the send buffer).
+    Returns keep (P_total, K) int64 (-1 padded) and num_keep (P_total,) int32 for all problems (gather=True), or this
     rank's block plus its (start, stop).
     """
     if compute is None:
@@ -72,13 +79,36 @@ def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather
 
         compute = U.nms_normal_gpu_batched if normal else U.nms_gpu_batched
     rank, world = _world(group)
-    P = boxes.shape[0]
-    start, stop = shard_range(P, rank, world)
-    c = None if counts is None else counts[start:stop]
-    keep, num = compute(boxes[start:stop], scores[start:stop], thresh, c)
-    if gather:
-        return _gather_rows(keep, P, group), _gather_rows(num, P, group)
-    return (keep, num), (start, stop)
+    if local_inputs:
+        P = boxes.shape[0] * world
+        start, stop = rank * boxes.shape[0], (rank + 1) * boxes.shape[0]
+        b, sc, c = boxes, scores, counts
+    else:
+        P = boxes.shape[0]
+        start, stop = shard_range(P, rank, world)
+        b, sc, c = boxes[start:stop], scores[start:stop], (None if counts is None else counts[start:stop])
+    kw = {} if max_keep is None else {"max_keep": max_keep}
+    if not gather or world == 1:
+        keep, num = compute(b, sc, thresh, c, **kw)
+        if gather:
+            return keep, num
+        return (keep, num), (start, stop)
+    per = boxes.shape[0] if local_inputs else (P + world - 1) // world
+    K = b.shape[1] if max_keep is None else min(int(max_keep), b.shape[1])
+    send = torch.empty((per, 1 + K), dtype=torch.int64, device=b.device)
+    if stop - start < per:  # a short (or empty) last block: pad rows, count 0
+        send[stop - start:, 0] = 0
+        send[stop - start:, 1:] = -1
+    if stop > start:
+        try:  # the CUDA op takes its keep buffer from the caller: the kernel writes into the send buffer
+            keep, num = compute(b, sc, thresh, c, keep_out=send[: stop - start, 1:], **kw)
+        except TypeError:  # an injected compute (CPU tests) without keep_out
+            keep, num = compute(b, sc, thresh, c, **kw)
+            send[: stop - start, 1:] = keep[:, :K]
+        send[: stop - start, 0] = num
+    recv = torch.empty((world * per, 1 + K), dtype=torch.int64, device=b.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:P, 1:], recv[:P, 0].to(torch.int32)
 
 
 def points_in_boxes_sharded(points, boxes, gather=True, group=None, compute=None):

@@ -23,12 +23,13 @@ def _iou_cpu(a, b):
     return torch.from_numpy(O.boxes_iou3d(a.numpy(), b.numpy(), O.FLAVOR_CUDA))
 
 
-def _nms_cpu(boxes, scores, thresh, counts):
+def _nms_cpu(boxes, scores, thresh, counts, max_keep=None):
     P, N = scores.shape
-    keep = torch.full((P, N), -1, dtype=torch.int64)
+    K = N if max_keep is None else min(max_keep, N)
+    keep = torch.full((P, K), -1, dtype=torch.int64)
     num = torch.zeros((P,), dtype=torch.int32)
     for p in range(P):
-        k = O.nms(boxes[p].numpy(), scores[p].numpy(), thresh)
+        k = O.nms(boxes[p].numpy(), scores[p].numpy(), thresh)[:K]
         keep[p, : len(k)] = torch.from_numpy(k)
         num[p] = len(k)
     return keep, num
@@ -62,6 +63,17 @@ def _worker(rank, world, port, ret):
         keep, num = sharded.nms_batched_sharded(torch.from_numpy(boxes), torch.from_numpy(scores), 0.1, compute=_nms_cpu)
         k1, n1 = _nms_cpu(torch.from_numpy(boxes), torch.from_numpy(scores), 0.1, None)
         ok = ok and torch.equal(keep, k1) and torch.equal(num, n1)
+        # NMS_POST_MAXSIZE: only the first 7 kept boxes are produced and gathered (one packed all-gather)
+        keep7, num7 = sharded.nms_batched_sharded(torch.from_numpy(boxes), torch.from_numpy(scores), 0.1, compute=_nms_cpu, max_keep=7)
+        ok = ok and torch.equal(keep7, k1[:, :7]) and torch.equal(num7, torch.clamp(n1, max=7)) and keep7.shape == (5, 7)
+        # data-parallel form: every rank brings its own frames; the result covers world x local frames in rank order
+        lb, ls = synth.nms_frames(3, 40, seed=20 + rank)
+        keepl, numl = sharded.nms_batched_sharded(torch.from_numpy(lb), torch.from_numpy(ls), 0.1, compute=_nms_cpu, max_keep=9, local_inputs=True)
+        ok = ok and keepl.shape == (3 * world, 9)
+        for r in range(world):
+            rb, rs = synth.nms_frames(3, 40, seed=20 + r)
+            kr, nr = _nms_cpu(torch.from_numpy(rb), torch.from_numpy(rs), 0.1, None, 9)
+            ok = ok and torch.equal(keepl[3 * r:3 * r + 3], kr) and torch.equal(numl[3 * r:3 * r + 3], nr)
         pts, rois = synth.cfg3(n_frames=3, n_points=200, n_rois=12, seed=4)
         idx = sharded.points_in_boxes_sharded(torch.from_numpy(pts), torch.from_numpy(rois), compute=_pib_cpu)
         ok = ok and torch.equal(idx, _pib_cpu(torch.from_numpy(pts), torch.from_numpy(rois)))
