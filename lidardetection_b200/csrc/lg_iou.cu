@@ -75,8 +75,11 @@ __device__ __forceinline__ unsigned long long max_key(float v, unsigned idx) {
 // DENSE = false: polygon path called out of line, 128 registers, 2 CTAs/SM, the sweep (cull + zero stores) stays in
 //                registers -- best for the usual, sparse matrix.  Both are launched; `dense_flag` (written by
 //                density_probe_kernel from a sample of the pairs, no host round trip) tells each whether it is its turn.
+#ifndef LG_SK_DENSE_MINB
+#define LG_SK_DENSE_MINB 3
+#endif
 template <int FL, bool REDUCE, bool DENSE>
-__global__ void __launch_bounds__(ST_THREADS, DENSE ? 3 : 2)
+__global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : 2)
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
                      const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
                      const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,

@@ -427,10 +427,6 @@ extern "C" int lg_points_in_boxes(const float* boxes, const float* pts, int32_t*
         set_error("num_boxes=%d exceeds LG_PIB_MAX_BOXES=%d", T, LG_PIB_MAX_BOXES);
         return LG_ERR_TOO_LARGE;
     }
-    if (B > 65535) {
-        set_error("batch=%d exceeds 65535; split the batch", B);
-        return LG_ERR_TOO_LARGE;
-    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // points per CTA: a whole frame when the batch alone fills the machine (the grid is built once per CTA),
     // otherwise split the frame, but never below 4 tiles, so that the build stays a small part of the work
@@ -447,16 +443,23 @@ extern "C" int lg_points_in_boxes(const float* boxes, const float* pts, int32_t*
         return LG_ERR_TOO_LARGE;
     }
     const size_t smem = PibSmem::total(T);
-    dim3 grid((unsigned)gx, B);
     int rc;
-    if (flags & LG_FLAG_STRICT_FP32) {
-        if ((rc = set_smem(pib_grid_kernel<0>, smem))) return rc;
-        pib_grid_kernel<0><<<grid, PIB_THREADS, smem, st>>>(boxes, pts, out, T, M, pts_per_cta);
-    } else {
-        if ((rc = set_smem(pib_grid_kernel<1>, smem))) return rc;
-        pib_grid_kernel<1><<<grid, PIB_THREADS, smem, st>>>(boxes, pts, out, T, M, pts_per_cta);
+    for (int b0 = 0; b0 < B; b0 += 65535) {  // grid.y holds at most 65,535 frames: larger batches go out in slices
+        const int bn = B - b0 < 65535 ? B - b0 : 65535;
+        dim3 grid((unsigned)gx, (unsigned)bn);
+        const float* bx = boxes + (size_t)b0 * T * 7;
+        const float* pp = pts + (size_t)b0 * M * 3;
+        int32_t* oo = out + (size_t)b0 * M;
+        if (flags & LG_FLAG_STRICT_FP32) {
+            if ((rc = set_smem(pib_grid_kernel<0>, smem))) return rc;
+            pib_grid_kernel<0><<<grid, PIB_THREADS, smem, st>>>(bx, pp, oo, T, M, pts_per_cta);
+        } else {
+            if ((rc = set_smem(pib_grid_kernel<1>, smem))) return rc;
+            pib_grid_kernel<1><<<grid, PIB_THREADS, smem, st>>>(bx, pp, oo, T, M, pts_per_cta);
+        }
+        if ((rc = check_launch("pib_grid_kernel"))) return rc;
     }
-    return check_launch("pib_grid_kernel");
+    return LG_OK;
 }
 
 extern "C" int lg_points_in_boxes_mask(const float* boxes, int64_t n, const float* pts, int64_t m, int32_t* out, float margin,

@@ -64,10 +64,25 @@ def points_in_boxes_gpu(points, boxes):
     if batch_size == 0 or num_points == 0:
         return box_idxs_of_pts
     L = _lib.lib()
-    with torch.cuda.device(p.device):
-        rc = L.lg_points_in_boxes(_lib.ptr(b), _lib.ptr(p), _lib.ptr(box_idxs_of_pts), batch_size, b.shape[1], num_points,
-                                  None, 0, _lib.LG_FLAG_NONE, _lib.stream_ptr(p.device))
-    _lib.check(rc, 'lg_points_in_boxes')
+    T = b.shape[1]
+
+    def call(boxes_chunk, out):
+        with torch.cuda.device(p.device):
+            rc = L.lg_points_in_boxes(_lib.ptr(boxes_chunk), _lib.ptr(p), _lib.ptr(out), batch_size, boxes_chunk.shape[1], num_points,
+                                      None, 0, _lib.LG_FLAG_NONE, _lib.stream_ptr(p.device))
+        _lib.check(rc, 'lg_points_in_boxes')
+
+    if T <= _lib.LG_PIB_MAX_BOXES:
+        call(b, box_idxs_of_pts)
+        return box_idxs_of_pts
+    # more boxes per frame than the kernel keeps in shared memory (the reference has no limit): chunks of LG_PIB_MAX_BOXES, the
+    # first (lowest-index) hit wins, as in the reference's `break` (roiaware_pool3d_kernel.cu:328-334)
+    box_idxs_of_pts.fill_(-1)
+    part = torch.empty_like(box_idxs_of_pts)
+    for t0 in range(0, T, _lib.LG_PIB_MAX_BOXES):
+        call(b[:, t0:t0 + _lib.LG_PIB_MAX_BOXES].contiguous(), part)
+        take = (box_idxs_of_pts < 0) & (part >= 0)
+        box_idxs_of_pts = torch.where(take, part + t0, box_idxs_of_pts)
     return box_idxs_of_pts
 
 

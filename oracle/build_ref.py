@@ -60,12 +60,12 @@ def build_py():
     out = os.path.join(OUT, "py")
     os.makedirs(out, exist_ok=True)
     for name, rel in PY_MODULES.items():
-        py_compile.compile(os.path.join(REF_ROOT, rel), cfile=os.path.join(out, name + ".pyc"), dfile=rel, doraise=True)
+        py_compile.compile(os.path.join(REF_ROOT, rel), cfile=os.path.join(out, name + ".pyc.bin"), dfile=rel, doraise=True)
     print(f"[build_ref] byte-compiled {sorted(PY_MODULES)} into {out}")
 
 
 def py_built():
-    return all(os.path.exists(os.path.join(OUT, "py", n + ".pyc")) for n in PY_MODULES)
+    return all(os.path.exists(os.path.join(OUT, "py", n + ".pyc.bin")) for n in PY_MODULES)
 
 
 def build(verbose=False):

@@ -51,7 +51,7 @@ def reference_python(module, ext, ext_name, package):
     import sys
     import types
 
-    path = os.path.join(_HERE, "_ref", "py", module + ".pyc")
+    path = os.path.join(_HERE, "_ref", "py", module + ".pyc.bin")
     if not os.path.exists(path):
         return None
     sub = {"iou3d_nms_utils": "iou3d_nms", "roiaware_pool3d_utils": "roiaware_pool3d"}[module]

@@ -330,6 +330,35 @@ def test_points_edge_cases():
     assert PU.points_in_boxes_gpu(cu(p), cu(box)).cpu().tolist() == [[0, 0, -1, 0, -1, -1]]
 
 
+def test_sizes_beyond_the_kernels_grid_and_shared_memory_limits():
+    """the reference entry points take any batch / box count; the library's limits (65,535 frames or problems per launch, 2048
+    boxes per frame in shared memory) are handled by slicing, not by raising"""
+    r = np.random.default_rng(12)
+    # 5000 boxes per frame: chunks of 2048, the lowest-index hit wins across chunks
+    boxes = synth.gt_boxes(5000, 3)[None]
+    k = r.integers(0, 5000, 6000)
+    pts = (boxes[0, k, 0:3] + r.normal(0, 0.4, (6000, 3))).astype(np.float32)[None]
+    got = PU.points_in_boxes_gpu(cu(pts), cu(boxes)).cpu().numpy()
+    assert np.array_equal(got, O.points_in_boxes_idx(pts, boxes, O.FLAVOR_CUDA)) and (got >= 2048).any() and (got >= 4096).any()
+    # 70,000 tiny frames
+    B = 70000
+    fb = np.tile(synth.gt_boxes(3, 5)[None], (B, 1, 1))
+    fb[:, :, 0] += r.normal(0, 0.5, (B, 3)).astype(np.float32)
+    fp = (fb[:, r.integers(0, 3, 8), 0:3] + r.normal(0, 0.8, (B, 8, 3))).astype(np.float32)
+    got = PU.points_in_boxes_gpu(cu(fp), cu(fb)).cpu().numpy()
+    rows = np.concatenate([np.arange(0, B, 997), np.arange(65500, 65600), [B - 1]])
+    assert np.array_equal(got[rows], O.points_in_boxes_idx(fp[rows], fb[rows], O.FLAVOR_CUDA))
+    # 70,000 NMS problems of 12 boxes, rotated and axis-aligned
+    nb, ns = synth.nms_frames(64, 12, seed=4)
+    nb, ns = np.tile(nb, (1100, 1, 1))[:B], np.tile(ns, (1100, 1))[:B]
+    for fn in (U.nms_gpu_batched, U.nms_normal_gpu_batched):
+        keep, num = fn(cu(nb), cu(ns), 0.1)
+        k64, n64 = fn(cu(nb[:64]), cu(ns[:64]), 0.1)
+        assert torch.equal(keep[:1093 * 64].view(1093, 64, 12), k64.unsqueeze(0).expand(1093, 64, 12))  # the batch repeats every 64 problems
+        assert torch.equal(num[:1093 * 64].view(1093, 64), n64.unsqueeze(0).expand(1093, 64))
+        assert torch.equal(keep[65536:65600], k64) and torch.equal(num[65536:65600], n64)  # 65536 = 1024 x 64: the tiling restarts there
+
+
 def test_cpu_named_functions_run_on_the_gpu_with_cpu_semantics():
     g = np.load(os.path.join(HERE, "golden", "golden_cpu.npz"))
     for f in range(2):
