@@ -169,9 +169,12 @@ class NmsWorkload(Workload):
             self.metric, self.unit = "rotated NMS problems/s (1000 boxes/problem)", "problems/s"
             self.post = 83  # cbgs_second_multihead.yaml:196-206
         self.world = world
-        self.multi_gpu_note = ("frames sharded by rank (weak scaling: every rank its own frames); keep lists + counts of all ranks gathered every "
-                               "step with ONE NCCL all_gather_into_tensor of a packed (frames, 1 + NMS_POST_MAXSIZE) int64 block per rank, inside "
-                               "the timed region (lidardetection_b200.sharded.nms_batched_sharded); `strong` = the config's fixed total split over N")
+        self.multi_gpu_note = ("frames sharded by rank (weak scaling: every rank its own frames); the truncated keep lists + counts of ALL ranks are "
+                               "gathered every step inside the timed region (lidardetection_b200.sharded.nms_batched_sharded): the NMS kernel's epilogue "
+                               "stores each problem's packed (count, kept indices) row into every rank's result buffer over NVLink peer memory "
+                               "(lg_nms_rotated_gather, torch symmetric memory) and one symmetric-memory barrier orders the ranks -- no NCCL launch on "
+                               "the data path (fused=False selects one NCCL all_gather_into_tensor instead; NCCL carries the timing barrier and the "
+                               "max-over-ranks); `strong` = the config's fixed total split over N")
         self.units = self.boxes_np.shape[0]
         self.boxes = torch.from_numpy(self.boxes_np).cuda()
         self.scores = torch.from_numpy(self.scores_np).cuda()
@@ -184,8 +187,8 @@ class NmsWorkload(Workload):
 
     def _nms(self, boxes, scores):
         """N = 1: the batched op.  N > 1: the same through lidardetection_b200.sharded -- every rank runs its own frames and
-        the truncated keep lists + counts of ALL ranks are all-gathered (one NCCL all_gather_into_tensor of a packed
-        (frames, 1 + NMS_POST_MAXSIZE) int64 block per rank) inside the timed region."""
+        the truncated keep lists + counts of ALL ranks are gathered inside the timed region (fused into the NMS kernel over
+        NVLink peer memory + one symmetric-memory barrier; see sharded.nms_batched_sharded)."""
         if self.world > 1:
             from lidardetection_b200 import sharded
 
@@ -1134,8 +1137,8 @@ def main():
         total = wl.strong_setup()
         ms = timed_steps(torch, wl.strong_step, args.steps, args.warmup, flush, world)
         strong = {"value": total * args.steps / (ms * 1e-3), "unit": wl.unit, "ms_per_step": ms / args.steps, "units_total": total,
-                  "what": f"{total} problems in total, contiguous blocks of ceil({total} / {world}) per rank (sharded.nms_batched_sharded), one "
-                          "all_gather_into_tensor of the packed (block, 1 + NMS_POST_MAXSIZE) int64 results inside the timed region"}
+                  "what": f"{total} problems in total, contiguous blocks of ceil({total} / {world}) per rank (sharded.nms_batched_sharded), the packed "
+                          "(block, 1 + NMS_POST_MAXSIZE) int64 results gathered on every rank inside the timed region (fused peer-memory gather)"}
 
     roofline = wl.roofline(args.steps, hbm_peak, hbm_src, fp32_peak) if rank == 0 else None
     if roofline is not None:

@@ -60,6 +60,7 @@ extern "C" {
 
 /* limits */
 #define LG_NMS_MAX_BOXES 65536 /* per NMS problem */
+#define LG_MAX_PEERS 8         /* ranks of one NVLink domain served by lg_nms_rotated_gather */
 #define LG_PIB_MAX_BOXES 2048  /* boxes per frame for lg_points_in_boxes (records are shared-memory resident);
                                   frames of up to 254 boxes take the grid-culled path, larger ones test every box */
 #define LG_ROIPOINT_MAX_SAMPLES 2048 /* sampled points per box for lg_roipoint_pool3d_forward (reference default: 512) */
@@ -142,6 +143,16 @@ LG_API int lg_nms_normal_batched(const float *boxes, const int64_t *order, const
 LG_API int lg_nms_batched_ex(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
                              float thresh, int normal, int max_keep, int64_t keep_ld, void *ws, size_t ws_bytes, int64_t *keep,
                              int32_t *num_keep, unsigned flags, void *stream);
+/* Rotated NMS fused with the gather of its results over NVLink peer memory (the reference merges per-rank results
+ * through pickle files and two barriers, pcdet/utils/common_utils.py:206-227).  peer_bufs[r], r < num_peers <= LG_MAX_PEERS, is
+ * the address IN THIS PROCESS of rank r's packed result buffer (rows, 1 + max_keep) int64 -- CUDA peer mappings, e.g. the
+ * buffer_ptrs of a torch symmetric-memory allocation; the own rank's buffer is one of them.  Problem p's row row0 + p of EVERY
+ * buffer receives (num_keep, kept indices ..., -1 ...), written by the NMS kernel's epilogue with plain stores; no keep tensor,
+ * no collective.  The caller orders the ranks (a barrier after the call, before anyone reads; a buffer is not rewritten while a
+ * peer may still read it: alternate two).  Lazy rotated NMS only (nmax up to ~12,000).  num_keep (P) may be NULL. */
+LG_API int lg_nms_rotated_gather(const float *boxes, const int64_t *order, const int32_t *counts, int num_problems, int nmax,
+                                 float thresh, int max_keep, void *ws, size_t ws_bytes, int64_t *const *peer_bufs, int num_peers,
+                                 int64_t row0, int32_t *num_keep, unsigned flags, void *stream);
 /* The same pipeline one phase at a time, for profiling (bench.py times the mask kernel alone for its
  * roofline line): phases is a bit-or of LG_NMS_PHASE_*; ws carries the records and the mask between calls.  The lazy rotated
  * NMS is ONE kernel (records included): it runs when LG_NMS_PHASE_SWEEP is set and ignores the other two bits. */

@@ -55,6 +55,8 @@ def lib():
         f.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp]
     L.lg_nms_batched_ex.restype = C.c_int
     L.lg_nms_batched_ex.argtypes = [vp, vp, vp, i32, i32, f32, i32, i32, i64, vp, sz, vp, vp, u32, vp]
+    L.lg_nms_rotated_gather.restype = C.c_int
+    L.lg_nms_rotated_gather.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp, sz, C.POINTER(C.c_void_p), i32, i64, vp, u32, vp]
     L.lg_nms_batched_phases.restype = C.c_int
     L.lg_nms_batched_phases.argtypes = [vp, vp, vp, i32, i32, f32, vp, sz, vp, vp, u32, vp, i32, u32]
     for name in ("lg_nms_rotated", "lg_nms_normal"):
@@ -94,7 +96,7 @@ def lib():
 EXPORTS = [
     "lg_version", "lg_last_error_string", "lg_check_device",
     "lg_iou_workspace_bytes", "lg_boxes_overlap_bev", "lg_boxes_iou_bev", "lg_boxes_iou3d", "lg_iou_reduce_workspace_bytes", "lg_boxes_iou_reduce",
-    "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_ex", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
+    "lg_nms_workspace_bytes", "lg_nms_workspace_bytes_ex", "lg_nms_stats_offset", "lg_nms_rotated_batched", "lg_nms_normal_batched", "lg_nms_batched_ex", "lg_nms_rotated_gather", "lg_nms_batched_phases", "lg_nms_rotated", "lg_nms_normal",
     "lg_points_in_boxes_workspace_bytes", "lg_points_in_boxes", "lg_points_in_boxes_mask",
     "lg_roiaware_pool3d_forward", "lg_roiaware_pool3d_backward", "lg_roipoint_pool3d_forward",
     "lg_kitti_workspace_bytes", "lg_rotate_iou_eval", "lg_d3_box_overlap", "lg_kitti_overlaps_parts",

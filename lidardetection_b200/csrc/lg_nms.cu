@@ -338,6 +338,15 @@ static inline int lazy_gcap(int nmax, int nt) {  // largest of 32 / 16 / 8 candi
     return 0;
 }
 
+// Fused gather (lg_nms_rotated_gather): the keep list of problem p goes, packed as (count, kept indices..., -1...), into row
+// row0 + p of a (rows, 1 + max_keep) int64 buffer on EVERY rank of the job -- plain stores through the NVLink peer mappings
+// (CUDA peer access / symmetric memory), straight from the kernel's epilogue, instead of a keep tensor + a collective.
+struct PeerRows {
+    int64_t* buf[LG_MAX_PEERS];
+    int n;         // 0: not a gather call
+    int64_t row0;  // this rank's first row in every buffer
+};
+
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -349,7 +358,7 @@ template <int FL, bool CL, int NT>
 __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     nms_lazy_kernel(const float* __restrict__ boxes, float4* rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
                     const int nmax, const float thresh, int64_t* __restrict__ keep, const int keep_ld, const int max_keep,
-                    int32_t* __restrict__ num_keep, unsigned long long* __restrict__ stats, const int gcap) {
+                    int32_t* __restrict__ num_keep, unsigned long long* __restrict__ stats, const int gcap, const PeerRows peers) {
     constexpr int G = LZ_G, GH = LZ_GH, NW = NT / 32, WG = NW / 2, STEP = WG * 32;  // columns per sweep step of the CTA's warps
     extern __shared__ float4 smem4[];
     const LazyLayout L(nmax, NT, gcap);
@@ -773,22 +782,27 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         }
         __syncthreads();
         const int nk = nk_s;
-        if (tid == 0) num_keep[p] = nk;
-        int64_t* const krow = keep + (int64_t)p * keep_ld;
-        for (int wb = 0; wb < W; wb += NT / 4) {
-            const int w = wb + (tid >> 2), part = tid & 3;
-            if (w < W) {
-                const unsigned word = keptw[w];
-                unsigned bits = (word >> (8 * part)) & 0xffu;
-                int off = wprefix[w] + __popc(word & ((1u << (8 * part)) - 1u));
-                while (bits && off < max_keep) {
-                    const int j = w * 32 + 8 * part + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    krow[off++] = order ? __ldg(order + base + j) : (int64_t)j;
+        if (tid == 0 && num_keep) num_keep[p] = nk;
+        // destinations: the caller's keep row, or (gather) the packed row of this problem in every peer's buffer
+        const int ndst = peers.n > 0 ? peers.n : 1;
+        for (int d = 0; d < ndst; d++) {
+            int64_t* const krow = peers.n > 0 ? peers.buf[d] + (peers.row0 + p) * (int64_t)keep_ld + 1 : keep + (int64_t)p * keep_ld;
+            if (peers.n > 0 && tid == 0) krow[-1] = nk;
+            for (int wb = 0; wb < W; wb += NT / 4) {
+                const int w = wb + (tid >> 2), part = tid & 3;
+                if (w < W) {
+                    const unsigned word = keptw[w];
+                    unsigned bits = (word >> (8 * part)) & 0xffu;
+                    int off = wprefix[w] + __popc(word & ((1u << (8 * part)) - 1u));
+                    while (bits && off < max_keep) {
+                        const int j = w * 32 + 8 * part + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        krow[off++] = order ? __ldg(order + base + j) : (int64_t)j;
+                    }
                 }
             }
+            for (int i = nk + tid; i < max_keep; i += NT) krow[i] = -1;
         }
-        for (int i = nk + tid; i < max_keep; i += NT) krow[i] = -1;
     }
     LZ_MARK(11)  // keep list emission
     if (stats) {
@@ -832,13 +846,13 @@ static int device_sm_count(int dev) {
 
 static int nms_entry(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax, float thresh, void* ws,
                      size_t ws_bytes, int64_t* keep, int keep_ld, int max_keep, int32_t* num_keep, unsigned flags, void* stream,
-                     bool normal, unsigned phases = PHASE_ALL) {
+                     bool normal, unsigned phases = PHASE_ALL, const PeerRows* peers = nullptr) {
     if (P < 0 || nmax < 0) {
         set_error("negative size num_problems=%d nmax=%d", P, nmax);
         return LG_ERR_INVALID_ARG;
     }
     if (P == 0) return LG_OK;
-    if (!num_keep || (nmax > 0 && (!boxes || !keep))) {
+    if (peers ? (nmax > 0 && !boxes) : (!num_keep || (nmax > 0 && (!boxes || !keep)))) {
         set_error("null pointer (boxes=%p keep=%p num_keep=%p)", (const void*)boxes, (void*)keep, (void*)num_keep);
         return LG_ERR_INVALID_ARG;
     }
@@ -852,6 +866,10 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
         return LG_ERR_TOO_LARGE;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (nmax == 0 && peers) {
+        set_error("gather call with nmax = 0");
+        return LG_ERR_INVALID_ARG;
+    }
     if (nmax == 0) {
         cudaError_t e = cudaMemsetAsync(num_keep, 0, sizeof(int32_t) * P, st);
         if (e != cudaSuccess) {
@@ -877,6 +895,10 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
     // takes over (same keep list)
     const int gcap512 = lazy_gcap(nmax, LZ_THREADS);
     const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0 || gcap512 == 0;
+    if (peers && (normal || full)) {
+        set_error("the fused gather exists for the lazy rotated NMS only (nmax=%d)", nmax);
+        return LG_ERR_INVALID_ARG;
+    }
     int rc;
     if (!normal && !full) {
         // lazy path: records, candidate rows and the greedy resolve in ONE launch; only the rows of kept boxes are ever evaluated
@@ -919,11 +941,16 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
             float4* rc4 = rec + (size_t)p0 * nmax * REC_F4;
             const int64_t* od = order ? order + (size_t)p0 * nmax : nullptr;
             const int32_t* cn = counts ? counts + p0 : nullptr;
-            int64_t* kp = keep + (size_t)p0 * keep_ld;
-            int32_t* nk = num_keep + p0;
+            int64_t* kp = keep ? keep + (size_t)p0 * keep_ld : nullptr;
+            int32_t* nk = num_keep ? num_keep + p0 : nullptr;
+            PeerRows pr = {};
+            if (peers) {
+                pr = *peers;
+                pr.row0 += p0;
+            }
             auto launch = [&](auto kern) -> cudaError_t {
                 if ((rc = set_smem(kern, L.total))) return cudaSuccess;
-                return cudaLaunchKernelEx(&lc, kern, bx, rc4, od, cn, nmax, thresh, kp, keep_ld, max_keep, nk, stats, gcap);
+                return cudaLaunchKernelEx(&lc, kern, bx, rc4, od, cn, nmax, thresh, kp, keep_ld, max_keep, nk, stats, gcap, pr);
             };
             rc = 0;
             if (strict) le = csize > 1 ? launch(nms_lazy_kernel<0, true, 512>) : (small ? launch(nms_lazy_kernel<0, false, 256>) : launch(nms_lazy_kernel<0, false, 512>));
@@ -1015,6 +1042,28 @@ extern "C" int lg_nms_batched_ex(const float* boxes, const int64_t* order, const
         return LG_ERR_INVALID_ARG;
     }
     return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, keep, (int)keep_ld, max_keep, num_keep, flags, stream, normal != 0);
+}
+
+extern "C" int lg_nms_rotated_gather(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax, float thresh,
+                                     int max_keep, void* ws, size_t ws_bytes, int64_t* const* peer_bufs, int num_peers, int64_t row0,
+                                     int32_t* num_keep, unsigned flags, void* stream) {
+    if (num_peers < 1 || num_peers > LG_MAX_PEERS || !peer_bufs || row0 < 0 || max_keep < 0) {
+        lg::set_error("bad gather arguments (num_peers=%d peer_bufs=%p row0=%lld max_keep=%d)", num_peers, (const void*)peer_bufs, (long long)row0, max_keep);
+        return LG_ERR_INVALID_ARG;
+    }
+    lg::PeerRows pr = {};
+    for (int r = 0; r < num_peers; r++) {
+        if (!peer_bufs[r]) {
+            lg::set_error("peer_bufs[%d] is NULL", r);
+            return LG_ERR_INVALID_ARG;
+        }
+        pr.buf[r] = peer_bufs[r];
+    }
+    pr.n = num_peers;
+    pr.row0 = row0;
+    const int mk = max_keep < nmax ? max_keep : nmax;
+    // the packed row pitch is 1 + max_keep as the CALLER defined it (not clamped to nmax)
+    return lg::nms_entry(boxes, order, counts, P, nmax, thresh, ws, ws_bytes, nullptr, 1 + max_keep, mk, num_keep, flags, stream, false, lg::PHASE_ALL, &pr);
 }
 
 extern "C" int lg_nms_batched_phases(const float* boxes, const int64_t* order, const int32_t* counts, int P, int nmax,

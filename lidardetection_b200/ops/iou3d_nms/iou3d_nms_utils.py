@@ -258,3 +258,30 @@ def nms_gpu_batched(boxes, scores, thresh, counts=None, full_mask=False, max_kee
 def nms_normal_gpu_batched(boxes, scores, thresh, counts=None, max_keep=None, keep_out=None):
     """Batched axis-aligned NMS; see nms_gpu_batched."""
     return _nms_batched('lg_nms_normal_batched', boxes, scores, thresh, counts, max_keep=max_keep, keep_out=keep_out)
+
+
+def nms_gpu_gather(boxes, scores, thresh, max_keep, peer_ptrs, row0, counts=None):
+    """Rotated NMS of this rank's P problems with the results written, by the NMS kernel itself, into row row0 + p of a packed
+    (rows, 1 + max_keep) int64 buffer on EVERY rank (lg_nms_rotated_gather): column 0 the count, then the kept indices, -1 padded.
+    peer_ptrs: sequence of the buffers' addresses in this process (torch symmetric memory `buffer_ptrs`), own rank included.
+    The caller synchronises the ranks afterwards (lidardetection_b200.sharded does: one symmetric-memory barrier)."""
+    import ctypes as C
+
+    assert boxes.dim() == 3 and boxes.shape[2] == 7 and scores.shape == boxes.shape[:2] and boxes.is_cuda
+    b = boxes.contiguous().float()
+    P, N = b.shape[0], b.shape[1]
+    if P == 0:
+        return
+    if counts is not None:
+        idx = torch.arange(N, device=b.device).unsqueeze(0)
+        scores = scores.masked_fill(idx >= counts.to(b.device).unsqueeze(1), float('-inf'))
+        counts = counts.to(device=b.device, dtype=torch.int32).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(b.device):
+        ws = _workspace(L.lg_nms_workspace_bytes_ex(P, N, 0, 0), b.device)
+    order = _argsort_desc(scores)
+    arr = (C.c_void_p * len(peer_ptrs))(*[int(x) for x in peer_ptrs])
+    with torch.cuda.device(b.device):
+        rc = L.lg_nms_rotated_gather(_lib.ptr(b), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), int(max_keep), _lib.ptr(ws), ws.numel(),
+                                     arr, len(peer_ptrs), int(row0), None, _lib.LG_FLAG_NONE, _lib.stream_ptr(b.device))
+    _lib.check(rc, 'lg_nms_rotated_gather')

@@ -61,8 +61,44 @@ def boxes_iou_sharded(boxes_a, boxes_b, kind="iou3d", gather=False, group=None, 
     return block, (start, stop)
 
 
+class _SymmRows:
+    """Two alternating symmetric-memory (rows, cols) int64 result buffers per (group, shape, device) for the fused NMS gather:
+    allocated and exchanged once (torch.distributed._symmetric_memory: CUDA peer mappings over NVLink), then reused.  A buffer
+    handed out by get() is rewritten by the call after next; the barrier of the call in between orders that write after
+    every rank's reads of it, provided those reads were enqueued on the stream the sharded call runs on."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, group, rows, cols, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        g = group if group is not None else dist.group.WORLD
+        key = (g.group_name, rows, cols, device.index)
+        if key not in cls._cache:
+            bufs, hdls = [], []
+            for _ in range(2):
+                t = symm_mem.empty((rows, cols), dtype=torch.int64, device=device)
+                hdls.append(symm_mem.rendezvous(t, g))
+                bufs.append(t)
+            cls._cache[key] = [bufs, hdls, 0]
+        e = cls._cache[key]
+        i = e[2]
+        e[2] ^= 1
+        return e[0][i], e[1][i]
+
+
+def _fused_gather_ok(boxes, world, normal, compute, blocks_equal):
+    """the fused path needs: NCCL world on CUDA tensors (one NVLink domain of <= 8 ranks), the CUDA op, rotated NMS, equal blocks"""
+    if compute is not None or normal or not boxes.is_cuda or not blocks_equal or world > 8:
+        return False
+    try:
+        return dist.get_backend() == "nccl"
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather=True, group=None, compute=None, max_keep=None,
-                        local_inputs=False):
+                        local_inputs=False, fused=None):
     """Frame-sharded batched NMS.  boxes (P, N, 7), scores (P, N) replicated on every rank (local_inputs=False: every rank
     works on its contiguous block of the P problems), or -- local_inputs=True, the data-parallel inference case -- already
     this rank's own block of a global batch of world x P problems.
@@ -71,9 +107,13 @@ def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather
     gathered (the reference merges the truncated per-frame results, common_utils.py:206-227, through pickle files and two
     barriers; here it is ONE all_gather_into_tensor of a packed (block, 1 + max_keep) int64 tensor: column 0 the count, the
     rest the kept indices, which the NMS kernel writes straight into the send buffer).
+    fused (default: on where it applies -- NCCL job, rotated NMS, equal blocks, <= 8 ranks of one NVLink domain): the NMS kernel
+    writes its results into every rank's buffer itself and a symmetric-memory barrier replaces the collective (see below);
+    keep / num_keep are then views into a reused buffer, valid until the call after next.  fused=False: the NCCL all-gather.
     Returns keep (P_total, K) int64 (-1 padded) and num_keep (P_total,) int32 for all problems (gather=True), or this
     rank's block plus its (start, stop).
     """
+    user_compute = compute
     if compute is None:
         from .ops.iou3d_nms import iou3d_nms_utils as U
 
@@ -88,6 +128,20 @@ def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather
         start, stop = shard_range(P, rank, world)
         b, sc, c = boxes[start:stop], scores[start:stop], (None if counts is None else counts[start:stop])
     kw = {} if max_keep is None else {"max_keep": max_keep}
+    if fused is None:
+        fused = True
+    if gather and world > 1 and fused and _fused_gather_ok(boxes, world, normal, user_compute, local_inputs or P % world == 0):
+        # ONE kernel does the NMS and the gather: its epilogue stores every problem's packed (count, kept indices) row into the
+        # result buffer of every rank through the NVLink peer mappings; a symmetric-memory barrier (signal pads, no NCCL launch)
+        # then tells every rank that all rows have landed.  The result is a view into the (reused) symmetric buffer.
+        from .ops.iou3d_nms import iou3d_nms_utils as U
+
+        per = stop - start
+        K = b.shape[1] if max_keep is None else min(int(max_keep), b.shape[1])
+        buf, hdl = _SymmRows.get(group, world * per, 1 + K, b.device)
+        U.nms_gpu_gather(b, sc, thresh, K, hdl.buffer_ptrs, rank * per, c)
+        hdl.barrier(channel=0)
+        return buf[:, 1:], buf[:, 0].to(torch.int32)
     if not gather or world == 1:
         keep, num = compute(b, sc, thresh, c, **kw)
         if gather:
