@@ -283,9 +283,12 @@ __global__ void __launch_bounds__(32)
 // A problem is a chain of dependent passes, each of them a handful of latency-bound phases (one polygon round is a
 // ~1500-instruction dependency chain per lane), so the kernel is as fast as it has few passes and few rounds per pass.
 constexpr int LZ_THREADS = 512;  // one problem is latency-bound: 16 warps hide the polygon path's dependency chains
-constexpr int LZ_G = 32;         // candidates per pass (one lane each in the resolve)
-constexpr int LZ_GH = 16;        // candidates per warp in a sweep: two warp groups share every 32 columns
-constexpr int LZ_WIN = 4 * LZ_G; // window: the first alive boxes among which the candidates are chosen
+constexpr int LZ_G = 32;         // speculative candidates per pass (one lane each in the resolve, one suppression row each)
+constexpr int LZ_GI = 32;        // independent candidates per pass (they need no rows and no resolve).  64 (window 256) was measured: the
+                                 // window of the best-scored alive boxes holds ~35 mutually separated ones, so the number of passes barely
+                                 // moves (4.3 -> 4.1 on nms_cfg2) while the window's conflict tests quadruple (kernel 0.153 -> 0.170 ms)
+constexpr int LZ_GH = 16;        // candidates per warp in a sweep: the warps form ceil(candidates / 16) groups that share every 32 columns
+constexpr int LZ_WIN = 4 * LZ_GI; // window: the first alive boxes among which the candidates are chosen
 constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
 constexpr int LZ_MAX_CLUSTER = 8;     // portable cluster size limit
 constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared memory per CTA on sm_100a, minus the static part
@@ -301,9 +304,9 @@ struct LazyLayout {
         qcap = 16 * nt + 512;
         rarecap = qcap + 1024;
         gcap = gcap_;
-        size_t o = (size_t)LZ_G * REC_F4 * sizeof(float4);  // candidate records first
+        size_t o = (size_t)LZ_GI * REC_F4 * sizeof(float4);  // candidate records first
         off_cand = o;
-        o += (size_t)LZ_G * sizeof(float4);
+        o += (size_t)LZ_GI * sizeof(float4);
         off_cull = o;
         o += (size_t)(nmax < LZ_CACHE ? nmax : LZ_CACHE) * sizeof(float4);
         off_slab = o;
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     nms_lazy_kernel(const float* __restrict__ boxes, float4* rec, const int64_t* __restrict__ order, const int32_t* __restrict__ counts,
                     const int nmax, const float thresh, int64_t* __restrict__ keep, const int keep_ld, const int max_keep,
                     int32_t* __restrict__ num_keep, unsigned long long* __restrict__ stats, const int gcap, const PeerRows peers) {
-    constexpr int G = LZ_G, GH = LZ_GH, NW = NT / 32, WG = NW / 2, STEP = WG * 32;  // columns per sweep step of the CTA's warps
+    constexpr int G = LZ_G, GH = LZ_GH, NW = NT / 32;
     extern __shared__ float4 smem4[];
     const LazyLayout L(nmax, NT, gcap);
     char* sm = reinterpret_cast<char*>(smem4);
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     uint16_t* dlist = reinterpret_cast<uint16_t*>(sm + L.off_dlist);
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     const int SW = L.sstride, QCAP = L.qcap, RARECAP = L.rarecap;
-    __shared__ int qcount, rcount, group[G], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s, nwin_s, nalive_s, cursor_s, spec_s;
+    __shared__ int qcount, rcount, group[LZ_GI], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s, nwin_s, nalive_s, cursor_s, spec_s;
     __shared__ unsigned long long st_heavy;
 
     // A problem may be spread over a thread-block cluster of C CTAs (C SMs): they keep identical copies of the alive bitmap
@@ -478,7 +481,8 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         __syncthreads();
         const int cursor = cursor_s;  // every box below it is decided
         const bool spec = spec_s != 0;
-        const int wincap = spec ? gcap : min(LZ_WIN, 4 * gcap);
+        const int gmax = spec ? gcap : min(LZ_GI, 2 * gcap);  // candidates of this pass at most
+        const int wincap = spec ? gcap : 4 * gmax;
         // ---- (warp 0) alive boxes at and after the cursor: per-word offsets of the dense list, and the window
         if (warp == 0) {
             int total = 0;
@@ -572,14 +576,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 const bool f = inw && (spec || wconf[b] == 0);
                 const unsigned m = __ballot_sync(FULL, f);
                 const int slot = cnt + __popc(m & lt);
-                const bool sel = f && slot < gcap;
+                const bool sel = f && slot < gmax;
                 if (sel) group[slot] = window[b];
                 const unsigned un = __ballot_sync(FULL, inw && !sel);
                 if (firstskip < 0 && un) firstskip = c0 + __ffs(un) - 1;
                 cnt += __popc(m);
             }
             if (lane == 0) {
-                ng_s = min(cnt, gcap);  // >= 1: the first window box has no earlier one
+                ng_s = min(cnt, gmax);  // >= 1: the first window box has no earlier one
                 // next cursor: the first window box that is not a candidate, else the first alive box after the window
                 cursor_s = firstskip >= 0 ? window[firstskip] : (nwin < nal ? (int)dlist[nwin] : n);
             }
@@ -602,10 +606,12 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
             my_nonzero += ov > 0.f ? 1u : 0u;
             if (iou > thresh) atomicOr(spec ? &sup[g * SW + (j >> 5)] : &killw[j >> 5], 1u << (j & 31));
         };
-        // ---- rows of the candidates against every later alive box.  Warp group `half` tests its GH candidates against 32
-        // entries of the dense list per step; the steps of a pass are interleaved over the CTAs of a cluster.
+        // ---- rows of the candidates against every later alive box.  The warps form ceil(ng / GH) groups; warp group `half` tests
+        // its GH candidates against 32 entries of the dense list per step (a step of the CTA: STEP columns x all candidates, at
+        // most NW x 512 pairs -- the queue's capacity); the steps of a pass are interleaved over the CTAs of a cluster.
+        const int ngr = (ng + GH - 1) / GH, WG = NW / ngr, STEP = WG * 32;
         const int half = warp / WG, wcol = warp % WG;
-        const int kmax = min(GH, ng - GH * half);  // candidates of this warp group in this pass (<= 0: none)
+        const int kmax = half < ngr ? min(GH, ng - GH * half) : 0;  // candidates of this warp group in this pass (0: an idle warp)
         const int ghi = kmax > 0 ? group[GH * half + kmax - 1] : 0;  // the last of them
         const int nsteps = (nal + C * STEP - 1) / (C * STEP);  // per CTA
         int s0 = 0;          // first step not yet swept
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         // ---- (warp 0, lane g = candidate g) keep list; in speculative mode first resolve the speculation in score order
         if (warp == 0) {
             const int jl = lane < ng ? group[lane] : 0;
-            unsigned km = ng >= 32 ? FULL : ((1u << ng) - 1u);
+            unsigned km = 0u;
             if (spec) {
                 // colm: the earlier candidates h whose row suppresses this lane's candidate (a column of the rows: SW is odd and
                 // the candidates sit in a few neighbouring words, so the loads are broadcasts or conflict-free)
@@ -706,10 +712,14 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                     if (g < ng && (cg_ & km) == 0u) km |= 1u << g;
                 }
             }
-            if ((km >> lane) & 1u) atomicOr(&keptw[jl >> 5], 1u << (jl & 31));
+            if (spec) {
+                if ((km >> lane) & 1u) atomicOr(&keptw[jl >> 5], 1u << (jl & 31));
+            } else {  // independent candidates (up to LZ_GI) are all kept
+                for (int g = lane; g < ng; g += 32) atomicOr(&keptw[group[g] >> 5], 1u << (group[g] & 31));
+            }
             if (lane == 0) {
                 keptmask_s = (int)km;
-                nk_s += __popc(km);
+                nk_s += spec ? __popc(km) : ng;
                 if (spec && __popc(km) * 4 < ng * 3) spec_s = 0;  // speculation does not pay on this problem
             }
         }
