@@ -31,9 +31,6 @@
 // re-points LG_SINF / LG_COSF at the oracle's restatement of libdevice when it compiles this header for the host,
 // tests/host_emu/), FL = 0 glibc's double-precision algorithm restated for the device
 #include "lg_trig.cuh"
-#ifndef LG_ATAN2F
-#define LG_ATAN2F(y, x) atan2f((y), (x))
-#endif
 
 namespace lg {
 
@@ -535,7 +532,7 @@ __device__ __noinline__ float overlap_area_slow(const float4* __restrict__ A, co
     const float mx = __fdiv_rn(sx, (float)cnt), my = __fdiv_rn(sy, (float)cnt);
     for (int k = 0; k < m; k++) {
         const float2 p = slab16(k);
-        ang16(k) = LG_ATAN2F(__fsub_rn(p.y, my), __fsub_rn(p.x, mx));
+        ang16(k) = trig_atan2<FL>(__fsub_rn(p.y, my), __fsub_rn(p.x, mx));
     }
     // order: 4 bits per rank = index of the vertex with that rank (stable: equal angles keep insertion order)
     unsigned long long order = 0ull;

@@ -22,6 +22,9 @@
 #define LG_SINF(x) sinf(x)
 #define LG_COSF(x) cosf(x)
 #endif
+#ifndef LG_ATAN2F
+#define LG_ATAN2F(y, x) atan2f((y), (x))
+#endif
 
 namespace lg {
 
@@ -86,6 +89,71 @@ static __device__ __noinline__ float glibc_sincosf(const float y, const int want
     return flip ? -r : r;  // round-to-nearest is symmetric: negating every coefficient negates the result exactly
 }
 
+// glibc's atan2f / atanf (2.39: sysdeps/ieee754/flt-32/e_atan2f.c, s_atanf.c -- the fdlibm single-precision code, every
+// operation individually rounded; no FMA variant exists for it), restated for the device: the literal vertex ordering of the
+// reference CPU build (iou3d_cpu.cpp:196-211) hangs on its last bit when two polygon vertices are radially aligned.
+// Checked against the container's libm on 4e8 operand pairs (random bit patterns and coordinate-like values): 0 differences;
+// tests/test_host_emu.py repeats a shorter sweep.  Infinite operands are not special-cased (the callers pass finite differences).
+static __device__ __noinline__ float glibc_atanf(float x) {
+    const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    const int hx = (int)__float_as_uint(x), ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c000000) {  // |x| >= 2^25
+        if (ix > 0x7f800000) return __fadd_rn(x, x);
+        const float r = __fadd_rn(atanhi[3], atanlo[3]);
+        return hx > 0 ? r : -r;
+    }
+    if (ix < 0x3ee00000) {  // |x| < 0.4375
+        if (ix < 0x31000000) return x;  // |x| < 2^-29
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {      // |x| < 1.1875
+            if (ix < 0x3f300000) {  // 7/16 <= |x| < 11/16
+                id = 0;
+                x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x));
+            } else {
+                id = 1;
+                x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f));
+            }
+        } else if (ix < 0x401c0000) {  // |x| < 2.4375
+            id = 2;
+            x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x)));
+        } else {
+            id = 3;
+            x = __fdiv_rn(-1.0f, x);
+        }
+    }
+    const float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+    auto h = [](float a, float b, float c) { return __fadd_rn(a, __fmul_rn(b, c)); };  // a + b*c, two roundings
+    const float s1 = __fmul_rn(z, h(3.3333334327e-01f, w, h(1.4285714924e-01f, w, h(9.0908870101e-02f, w, h(6.6610731184e-02f, w, h(4.9768779427e-02f, w, 1.6285819933e-02f))))));
+    const float s2 = __fmul_rn(w, h(-2.0000000298e-01f, w, h(-1.1111110449e-01f, w, h(-7.6918758452e-02f, w, h(-5.8335702866e-02f, w, -3.6531571299e-02f)))));
+    const float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+    if (id < 0) return __fsub_rn(x, xs);
+    const float r = __fsub_rn(atanhi[id], __fsub_rn(__fsub_rn(xs, atanlo[id]), x));
+    return hx < 0 ? -r : r;
+}
+
+static __device__ __noinline__ float glibc_atan2f(const float y, const float x) {
+    const float tiny = 1.0e-30f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    const int hx = (int)__float_as_uint(x), hy = (int)__float_as_uint(y), ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+    if (hx == 0x3f800000) return glibc_atanf(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);  // 2 * sign(x) + sign(y)
+    if (iy == 0) return m < 2 ? y : (m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny));
+    if (ix == 0) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = glibc_atanf(fabsf(__fdiv_rn(y, x)));
+    if (m == 0) return z;
+    if (m == 1) return -z;
+    if (m == 2) return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+    return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+}
+
 template <int FL>
 __device__ __forceinline__ float trig_sin(const float x) {
     if (FL) return LG_SINF(x);
@@ -95,6 +163,12 @@ template <int FL>
 __device__ __forceinline__ float trig_cos(const float x) {
     if (FL) return LG_COSF(x);
     return glibc_sincosf(x, 1);
+}
+
+template <int FL>
+__device__ __forceinline__ float trig_atan2(const float y, const float x) {
+    if (FL) return LG_ATAN2F(y, x);
+    return glibc_atan2f(y, x);
 }
 
 }  // namespace lg

@@ -204,3 +204,13 @@ extern "C" long long emu_trig_symmetry_sweep(unsigned first, unsigned stride, lo
     }
     return bad;
 }
+
+// the device restatement of glibc's atan2f against the host libm: count of differing results over n operand pairs
+extern "C" long long emu_glibc_atan2f_check(const float* y, const float* x, long long n) {
+    long long bad = 0;
+    for (long long i = 0; i < n; i++) {
+        const float a = atan2f(y[i], x[i]), b = glibc_atan2f(y[i], x[i]);
+        if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) bad++;
+    }
+    return bad;
+}

@@ -178,3 +178,24 @@ def test_compact_cell_list_insert_is_order_independent():
             assert got == want + [0xFF] * (4 - len(ids))
         else:
             assert got == want[:3] + [0xFE]
+
+
+def test_cpu_named_entry_points_say_why_they_cannot_run_without_cuda():
+    """boxes_bev_iou_cpu / points_in_boxes_cpu are served by the GPU (no CPU fallback by contract): without a usable CUDA
+    context -- this container, or a DataLoader worker forked from a CUDA process -- they raise a LidarGeomError that names the
+    function and the remedy instead of failing inside the driver ("DataLoader workers")."""
+    import numpy as np
+    import pytest
+    import torch
+
+    from lidardetection_b200 import _lib
+    from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+    from lidardetection_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as PU
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the functions run")
+    a = np.array([[0, 0, 0, 4, 2, 1.5, 0.3]], np.float32)
+    with pytest.raises(_lib.LidarGeomError, match="boxes_bev_iou_cpu.*no CPU fallback"):
+        U.boxes_bev_iou_cpu(a, a)
+    with pytest.raises(_lib.LidarGeomError, match="points_in_boxes_cpu.*no CPU fallback"):
+        PU.points_in_boxes_cpu(np.zeros((3, 3), np.float32), a)

@@ -82,6 +82,24 @@ def test_trig_of_the_negated_heading(emu):
         assert emu.emu_trig_symmetry_sweep(3, 8, 1 << 28, flavor, C.byref(fb)) == 0, (flavor, hex(fb.value))
 
 
+def test_device_restatement_of_glibc_atan2f_matches_the_host_libm(emu):
+    """the literal vertex ordering of the strict (CPU-build) flavor: 4e6 operand pairs -- random bit patterns, coordinate-like
+    differences, axis cases -- bit for bit (a 4e8-pair sweep of the same code in C: 0 differences)"""
+    r = np.random.default_rng(17)
+    n = 2_000_000
+    y = np.concatenate([r.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32), r.normal(0, 3, n).astype(np.float32)])
+    x = np.concatenate([r.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32), r.normal(0, 3, n).astype(np.float32)])
+    y[:64], x[:64] = 0.0, r.normal(0, 1, 64)
+    y[64:128], x[64:128] = r.normal(0, 1, 64), 0.0
+    x[128:192] = 1.0
+    x[192:256] = -x[192:256].__abs__() * 1e-30
+    finite = np.isfinite(x) & np.isfinite(y)  # infinities are not special-cased in the device code
+    y, x = np.ascontiguousarray(y[finite]), np.ascontiguousarray(x[finite])
+    emu.emu_glibc_atan2f_check.restype = C.c_longlong
+    emu.emu_glibc_atan2f_check.argtypes = [fp, fp, C.c_longlong]
+    assert emu.emu_glibc_atan2f_check(y.ctypes.data_as(fp), x.ctypes.data_as(fp), len(y)) == 0
+
+
 @pytest.mark.parametrize("name", sorted(SETS))
 def test_strict_flavor_matches_the_reference_cpu_build_bit_for_bit(emu, name):
     """LG_FLAG_STRICT_FP32 (boxes_bev_iou_cpu): un-contracted arithmetic + glibc trigonometry == the oracle's CPU flavor, which
