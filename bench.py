@@ -102,13 +102,16 @@ def measured_peaks():
 
 def ncu_traffic(workload):
     """DRAM bytes (read + write) per launch of the workload's dominant kernel, from the committed `ncu --set full` capture at
-    the bench shape (profiles/r01_ncu_traffic.json, written by tools/make_profiles.py --traffic); None when there is none."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    try:
-        with open(path) as f:
-            rec = json.load(f).get(workload)
-    except (OSError, ValueError):
-        return None, None
+    the bench shape (profiles/rNN_ncu_traffic.json, written by tools/make_profiles.py --traffic); None when there is none."""
+    rec = None
+    for tag in ("r02", "r01"):  # the latest round's capture of the kernel, else the previous one's
+        try:
+            with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_traffic.json")) as f:
+                rec = json.load(f).get(workload)
+        except (OSError, ValueError):
+            rec = None
+        if rec:
+            break
     if not rec:
         return None, None
     return rec["dram_bytes_read"] + rec["dram_bytes_write"], f"{rec['kernel']}: dram__bytes_read.sum + dram__bytes_write.sum, {rec['how']} ({rec['report']})"

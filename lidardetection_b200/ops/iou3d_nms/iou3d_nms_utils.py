@@ -128,7 +128,7 @@ def _nms_buffers(fn_name, P, N, dev, flags=_lib.LG_FLAG_NONE, max_keep=None):
     """outputs + scratch of one batched NMS call (allocated before the first launch of a step so that the launches follow
     each other without host work in between)"""
     keep = torch.empty((P, N if max_keep is None else min(int(max_keep), N)), dtype=torch.int64, device=dev)
-    num = torch.zeros((P,), dtype=torch.int32, device=dev)
+    num = torch.empty((P,), dtype=torch.int32, device=dev)  # written for every problem by the kernels (no fill launch in the step)
     ws = None
     if P > 0 and N > 0:
         with torch.cuda.device(dev):
@@ -143,7 +143,7 @@ def _nms_call(fn_name, boxes, order, counts, thresh, flags=_lib.LG_FLAG_NONE, bu
     dev = boxes.device
     keep, num, ws = buffers if buffers is not None else _nms_buffers(fn_name, P, N, dev, flags, max_keep)
     if P == 0 or N == 0 or keep.shape[1] == 0:
-        return keep, num
+        return keep, num.zero_()
     L = _lib.lib()
     mk = keep.shape[1] if max_keep is None else min(int(max_keep), keep.shape[1])  # a wider keep keeps its pitch; columns >= mk stay unwritten
     with torch.cuda.device(dev):

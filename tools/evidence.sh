@@ -10,17 +10,22 @@ O=gpurun_out
 mkdir -p $O
 WHAT=${1:-all}
 if [ "$WHAT" != ncu ]; then
-timeout 600 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+timeout 600 python -m pytest tests -m gpu -q -rs > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 timeout 600 python tools/gpu_check.py > $O/gpu_check.log 2>&1; echo "gpu_check rc=$?"
 timeout 300 python tools/kitti_check.py > $O/kitti_check.log 2>&1; echo "kitti_check rc=$?"
 : > $O/bench_lines.jsonl
+timeout 300 python bench.py 2> $O/bench_default.err | tail -1 > $O/bench_default.json; echo "bench default (with secondary + gpu_baseline) rc=$?"
 for w in nms_cfg2 nms_cfg5 iou_dense iou_cfg1 iou_cfg4 pib_cfg3 post_cfg2 iou_max_cfg4 roiaware_partA2 roipoint_pointrcnn kitti_eval; do
-    timeout 300 python bench.py --workload $w 2> $O/bench_$w.err | tail -1 >> $O/bench_lines.jsonl; echo "bench $w rc=$?"
+    timeout 300 python bench.py --workload $w --no-secondary 2> $O/bench_$w.err | tail -1 >> $O/bench_lines.jsonl; echo "bench $w rc=$?"
 done
 timeout 400 python bench.py --impl reference 2> $O/bench_reference.err | tail -1 >> $O/bench_lines.jsonl; echo "bench reference rc=$?"
-if timeout 200 python bench.py --steps 2 --warmup 1 > $O/plain_bench.log 2>&1; then
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo "smoke rc=$?"
+LG_LIB_PATH=lidardetection_b200/liblidargeom_timing.so timeout 120 python tools/lz_timing.py > $O/nms_lazy_phase_timing.log 2>&1; echo "lz_timing rc=$?"
+# launch list of the default workload (the secondary metrics and the baselines of the default command are left out: their launches
+# would fill the 400-launch window before the timed region of the headline is reached)
+if timeout 200 python bench.py --steps 2 --warmup 1 --no-secondary --no-cpu-baseline > $O/plain_bench.log 2>&1; then
     timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_nms_cfg2.csv \
-        python bench.py --steps 2 --warmup 1 > $O/ncu_launch.log 2>&1; echo "launch list rc=$?"
+        python bench.py --steps 2 --warmup 1 --no-secondary --no-cpu-baseline > $O/ncu_launch.log 2>&1; echo "launch list rc=$?"
 fi
 fi
 if [ "$WHAT" != run ]; then
