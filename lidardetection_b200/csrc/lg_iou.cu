@@ -78,8 +78,11 @@ __device__ __forceinline__ unsigned long long max_key(float v, unsigned idx) {
 #ifndef LG_SK_DENSE_MINB
 #define LG_SK_DENSE_MINB 3
 #endif
+#ifndef LG_SK_SPARSE_MINB
+#define LG_SK_SPARSE_MINB 2
+#endif
 template <int FL, bool REDUCE, bool DENSE>
-__global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : 2)
+__global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_SPARSE_MINB)
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
                      const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
                      const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,
@@ -151,8 +154,9 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : 2)
             // survivors go straight onto the warp's list (a warp-uniform, rarely taken branch when the matrix is sparse)
             const unsigned lt = (1u << lane) - 1u;
             auto push2 = [&](const int row, const bool s0, const bool s1) {
+                if (!__any_sync(0xffffffffu, s0 | s1)) return;  // the usual case of a sparse matrix: one vote per row
                 const unsigned m0 = __ballot_sync(0xffffffffu, s0), m1 = __ballot_sync(0xffffffffu, s1);
-                if (m0 | m1) {
+                {
                     if (s0) q.list[q.count + __popc(m0 & lt)] = (uint32_t)((row << SK_SHIFT) | c);
                     q.count += __popc(m0);
                     if (s1) q.list[q.count + __popc(m1 & lt)] = (uint32_t)((row << SK_SHIFT) | (c + 1));
