@@ -839,6 +839,24 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     }
 }
 
+// thresh < 0: every IoU, the exact zeros of disjoint boxes included, exceeds it (kernel.cu:304 `iou > thresh`), so the first box
+// suppresses all the others.  The kernels above never evaluate a pair the circle test proves disjoint, so this case is answered
+// directly: the best-scored box of every non-empty problem is kept, nothing else.
+__global__ void __launch_bounds__(256) nms_first_only_kernel(const int64_t* __restrict__ order, const int32_t* __restrict__ counts, const int nmax,
+                                                             int64_t* __restrict__ keep, const int keep_ld, const int max_keep,
+                                                             int32_t* __restrict__ num_keep, const int P) {
+    const int p = blockIdx.x;
+    if (p >= P) return;
+    const int n = problem_count(counts, p, nmax);
+    const int nk = (n > 0 && max_keep > 0) ? 1 : 0;
+    for (int i = threadIdx.x; i < max_keep; i += blockDim.x) {
+        int64_t v = -1;
+        if (i == 0 && nk) v = order ? order[(int64_t)p * nmax] : 0;
+        keep[(int64_t)p * keep_ld + i] = v;
+    }
+    if (threadIdx.x == 0 && num_keep) num_keep[p] = nk;
+}
+
 enum { PHASE_RECORDS = 1, PHASE_MASK = 2, PHASE_SWEEP = 4, PHASE_ALL = 7 };
 
 // per-device facts, looked up once (the C ABI keeps no state that matters: these are caches of immutable properties)
@@ -903,8 +921,21 @@ static int nms_entry(const float* boxes, const int64_t* order, const int32_t* co
     // the lazy kernel keeps the alive bitmap and the suppression rows of its candidates in shared memory: 32 candidates per pass
     // up to ~8,000 boxes, 16 / 8 beyond; past ~50,000 boxes nothing fits next to the queues and the mask + sweep formulation
     // takes over (same keep list)
+    if (!normal && thresh < 0.f && !peers) {  // (the axis-aligned kernel evaluates every pair and needs no special case)
+        if (!(phases & PHASE_SWEEP)) return LG_OK;
+        for (int p0 = 0; p0 < P; p0 += 65535) {
+            const int pn = min(P - p0, 65535);
+            nms_first_only_kernel<<<pn, 256, 0, st>>>(order ? order + (size_t)p0 * nmax : nullptr, counts ? counts + p0 : nullptr, nmax,
+                                                      keep + (size_t)p0 * keep_ld, keep_ld, max_keep, num_keep + p0, pn);
+        }
+        return check_launch("nms_first_only_kernel");
+    }
     const int gcap512 = lazy_gcap(nmax, LZ_THREADS);
     const bool full = (flags & LG_FLAG_NMS_FULL_MASK) != 0 || gcap512 == 0;
+    if (peers && thresh < 0.f) {
+        set_error("the fused gather does not take negative thresholds (thresh=%g): use lg_nms_batched_ex", (double)thresh);
+        return LG_ERR_INVALID_ARG;
+    }
     if (peers && (normal || full)) {
         set_error("the fused gather exists for the lazy rotated NMS only (nmax=%d)", nmax);
         return LG_ERR_INVALID_ARG;

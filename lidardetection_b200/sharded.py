@@ -130,7 +130,7 @@ def nms_batched_sharded(boxes, scores, thresh, counts=None, normal=False, gather
     kw = {} if max_keep is None else {"max_keep": max_keep}
     if fused is None:
         fused = True
-    if gather and world > 1 and fused and _fused_gather_ok(boxes, world, normal, user_compute, local_inputs or P % world == 0):
+    if gather and world > 1 and fused and not thresh < 0 and _fused_gather_ok(boxes, world, normal, user_compute, local_inputs or P % world == 0):
         # ONE kernel does the NMS and the gather: its epilogue stores every problem's packed (count, kept indices) row into the
         # result buffer of every rank through the NVLink peer mappings; a symmetric-memory barrier (signal pads, no NCCL launch)
         # then tells every rank that all rows have landed.  The result is a view into the (reused) symmetric buffer.

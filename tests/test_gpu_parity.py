@@ -268,6 +268,29 @@ def test_nms_vs_golden_reference_cuda(ggpu):
             assert np.array_equal(U.nms_normal_gpu(tb, ts, thr)[0].cpu().numpy(), ggpu[f"nms_keep_{f}_{thr}_1"]), (f, thr)
 
 
+def test_nms_threshold_edge_values():
+    """thresh < 0: the exact-zero IoU of disjoint boxes exceeds it too (kernel.cu:304), so only the best box survives -- the
+    kernels' exact-zero cull must not change that; thresh = NaN: nothing is suppressed; thresh >= 1: only IoUs above 1"""
+    boxes, scores = synth.nms_frames(3, 300, seed=41)
+    tb, ts = cu(boxes), cu(scores)
+    counts = torch.tensor([300, 0, 17], dtype=torch.int32)
+    for thr in (-0.5, -1e-9):
+        for fn, normal in ((U.nms_gpu_batched, False), (U.nms_normal_gpu_batched, True)):
+            keep, num = fn(tb, ts, thr, counts)
+            for p in range(3):
+                c = int(counts[p])
+                order = ts[p, :c].sort(0, descending=True)[1].cpu().numpy()
+                want = O.nms(boxes[p, :c], scores[p, :c], thr, normal=normal, order=order) if c else np.zeros(0, np.int64)
+                assert len(want) == min(c, 1) and np.array_equal(keep[p, : int(num[p])].cpu().numpy(), want), (thr, normal, p)
+                assert bool((keep[p, int(num[p]):] == -1).all())
+        k1 = U.nms_gpu(tb[0], ts[0], thr)[0]
+        assert k1.numel() == 1 and int(k1[0]) == int(ts[0].argmax())
+    keep, num = U.nms_gpu_batched(tb, ts, float("nan"))
+    assert num.tolist() == [300, 300, 300]
+    keep, num = U.nms_gpu_batched(tb, ts, 1.5)
+    assert num.tolist() == [300, 300, 300]
+
+
 def test_nms_pre_maxsize_empty_and_duplicates():
     boxes, scores = synth.nms_frames(1, 500, seed=9)
     tb, ts = cu(boxes[0]), cu(scores[0])
