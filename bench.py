@@ -210,9 +210,15 @@ class NmsWorkload(Workload):
 
     def e2e_step(self):
         torch = self.torch
-        b = self.h_boxes.cuda(non_blocking=True)
-        s = self.h_scores.cuda(non_blocking=True)
-        keep, num = self._nms(b, s)
+        if self.world == 1:
+            # the public host-input entry point: score upload + sort overlap the box upload (second stream)
+            from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
+
+            keep, num = U.nms_gpu_batched_from_host(self.h_boxes, self.h_scores, self.thresh, max_keep=self.post)
+        else:
+            b = self.h_boxes.cuda(non_blocking=True)
+            s = self.h_scores.cuda(non_blocking=True)
+            keep, num = self._nms(b, s)
         # the result a caller reads: counts and the (frames, NMS_POST_MAXSIZE) keep lists, into pinned buffers, ONE synchronisation
         if getattr(self, "h_keep", None) is None or self.h_keep.shape != keep.shape:
             self.h_keep = torch.empty(keep.shape, dtype=keep.dtype).pin_memory()

@@ -285,3 +285,34 @@ def nms_gpu_gather(boxes, scores, thresh, max_keep, peer_ptrs, row0, counts=None
         rc = L.lg_nms_rotated_gather(_lib.ptr(b), _lib.ptr(order), _lib.ptr(counts), P, N, float(thresh), int(max_keep), _lib.ptr(ws), ws.numel(),
                                      arr, len(peer_ptrs), int(row0), None, _lib.LG_FLAG_NONE, _lib.stream_ptr(b.device))
     _lib.check(rc, 'lg_nms_rotated_gather')
+
+
+_SIDE_STREAMS = {}
+
+
+def nms_gpu_batched_from_host(h_boxes, h_scores, thresh, counts=None, max_keep=None, device=None):
+    """nms_gpu_batched for inputs that still live in (pinned) host memory -- the serving case: the scores (1/7 of the bytes) are
+    uploaded first and sorted while the boxes are still crossing PCIe on a second stream; the NMS kernel then waits for both.
+    Same results as nms_gpu_batched(h_boxes.cuda(), h_scores.cuda(), ...).
+    :return: keep, num_keep on the device (current stream)"""
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    cur = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(dev)
+    assert h_boxes.dim() == 3 and h_boxes.shape[2] == 7 and h_scores.shape == h_boxes.shape[:2]
+    sc = h_scores.to(dev, non_blocking=True)  # current stream: the scores go first ...
+    side.wait_stream(cur)                     # (the side stream only has to respect what was queued before this call)
+    with torch.cuda.stream(side):
+        b = h_boxes.to(dev, dtype=torch.float32, non_blocking=True)  # ... the boxes follow on the side stream
+    sc = sc.float()
+    if counts is not None:
+        idx = torch.arange(sc.shape[1], device=dev).unsqueeze(0)
+        sc = sc.masked_fill(idx >= counts.to(dev).unsqueeze(1), float('-inf'))
+        counts = counts.to(device=dev, dtype=torch.int32).contiguous()
+    fn = 'lg_nms_rotated_batched'
+    buffers = _nms_buffers(fn, b.shape[0], b.shape[1], dev, _lib.LG_FLAG_NONE, max_keep)
+    order = _argsort_desc(sc)                 # overlaps the box upload
+    cur.wait_stream(side)
+    b.record_stream(cur)
+    return _nms_call(fn, b.contiguous(), order, counts, thresh, _lib.LG_FLAG_NONE, buffers, max_keep)

@@ -268,6 +268,18 @@ def test_nms_vs_golden_reference_cuda(ggpu):
             assert np.array_equal(U.nms_normal_gpu(tb, ts, thr)[0].cpu().numpy(), ggpu[f"nms_keep_{f}_{thr}_1"]), (f, thr)
 
 
+def test_nms_from_pinned_host_inputs_equals_the_device_call():
+    boxes, scores = synth.nms_frames(6, 900, seed=61)
+    hb, hs = torch.from_numpy(boxes).pin_memory(), torch.from_numpy(scores).pin_memory()
+    counts = torch.tensor([900, 1, 0, 64, 65, 333], dtype=torch.int32)
+    for c in (None, counts):
+        for mk in (None, 50):
+            k0, n0 = U.nms_gpu_batched(cu(boxes), cu(scores), 0.1, c, max_keep=mk)
+            for _ in range(3):  # the side stream and its buffers are reused across calls
+                k1, n1 = U.nms_gpu_batched_from_host(hb, hs, 0.1, c, max_keep=mk)
+                assert torch.equal(k0, k1) and torch.equal(n0, n1)
+
+
 def test_nms_threshold_edge_values():
     """thresh < 0: the exact-zero IoU of disjoint boxes exceeds it too (kernel.cu:304), so only the best box survives -- the
     kernels' exact-zero cull must not change that; thresh = NaN: nothing is suppressed; thresh >= 1: only IoUs above 1"""
