@@ -92,6 +92,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
+def workload_config(name):
+    """the `config` of a line: the workload and the cache discipline of the GPU arm; the same dict in both arms"""
+    return {"workload": name, "l2": "256 MB L2 flush between timed iterations of the GPU arm (outside the events)"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -1035,7 +1040,7 @@ def run_reference(args, rank):
     val = tot_u / tot_t
     line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (seeded, SURVEY.md 8d shapes)", "config": {"workload": name},
+            "data": "synthetic (seeded, SURVEY.md 8d shapes)", "config": workload_config(name),
             "cpu_baseline": {"value": val, "unit": unit, "cores": pool.workers, "kind": kind_override or pool.kind, "sample": sample},
             "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -1179,12 +1184,15 @@ def main():
         "metric": wl.metric, "value": total_units * args.steps / (dev_ms * 1e-3), "unit": wl.unit, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": wl.dtype, "data": "synthetic (seeded, SURVEY.md 8d shapes; no datasets offline)",
-        "config": {"workload": wl.name, "units_per_step_per_gpu": wl.units, "l2": "256 MB L2 flush between timed iterations",
-                   "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
-                   "multi_gpu": (getattr(wl, "multi_gpu_note", None) or
-                                 "independent problems per rank, no data-path collective (results stay on the owning rank, as in the "
-                                 "reference's DDP evaluation); NCCL only for the barrier and the max-over-ranks of the timings")
-                   if world > 1 else "single GPU"},
+        # `config` is the workload and nothing else, identical in both arms (the driver compares them); how THIS arm measures it is
+        # in `measurement`
+        "config": workload_config(wl.name),
+        "measurement": {"units_per_step_per_gpu": wl.units,
+                        "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
+                        "multi_gpu": (getattr(wl, "multi_gpu_note", None) or
+                                      "independent problems per rank, no data-path collective (results stay on the owning rank, as in the "
+                                      "reference's DDP evaluation); NCCL only for the barrier and the max-over-ranks of the timings")
+                        if world > 1 else "single GPU"},
         "e2e": {"value": total_units * args.steps / e2e_s, "unit": wl.unit, "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h)},
         "gpu_launches": wl.launches_per_step * args.steps,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "strong": strong, "secondary": secondary, "gpu_baseline": gbase,
