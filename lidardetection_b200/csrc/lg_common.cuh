@@ -67,6 +67,9 @@ inline int set_smem(K kernel, size_t bytes) {
         set_error("cudaFuncSetAttribute(%zu B dynamic smem): %s", bytes, cudaGetErrorString(e));
         return (int)e;
     }
+#ifdef LG_CARVEOUT_MAX
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+#endif
     smem_attr_cached(fn, dev, bytes, true);
     return LG_OK;
 }
