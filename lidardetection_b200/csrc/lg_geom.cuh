@@ -223,13 +223,28 @@ __device__ __forceinline__ uint32_t or_if_inside(uint32_t m, const uint32_t bit,
 //                           the ones s1 of the next B edge and s5 use; ptxas keeps them unfused)
 //   s3 = cross(p0,q1,q0) = fma(-Dx[i][j], f_j.y,  f_j.x * Dy[i][j])
 //   s4 = cross(q1,p1,q0) = fma(f_j.x, -Dy[i+1][j], Dx[i+1][j] * f_j.y)
+// A column record that lives in global memory (STAGE): the records are the only re-used global data of the sweeps, while the
+// result matrix streams through the L2 once -- ask the L2 to keep them (evict_last) so that the polygon path of a late survivor does
+// not find its record evicted by gigabytes of zeros.  (volatile: the lazy NMS reads records its own prologue wrote.)
+__device__ __forceinline__ float4 ld_keep(const float4* p) {
+#if defined(__CUDA_ARCH__) && !defined(LG_NO_EVICT_LAST)
+    float4 v;
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 template <int FL, bool STAGE = false>
 __device__ __forceinline__ void pair_masks(const float4* __restrict__ A, const float4* __restrict__ B, uint32_t& xmask,
                                            uint32_t& cmask, float2* __restrict__ slab = nullptr, const int sstride = 0) {
     float px[4], py[4], ex[4], ey[4], qx[4], qy[4], fx[4], fy[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const float4 a = A[k], b = B[k];
+        const float4 a = A[k], b = STAGE ? ld_keep(B + k) : B[k];
         px[k] = a.x; py[k] = a.y; ex[k] = a.z; ey[k] = a.w;
         qx[k] = b.x; qy[k] = b.y; fx[k] = b.z; fy[k] = b.w;
         if (STAGE) slab[(SLAB_BCORNER + k) * sstride] = make_float2(b.x, b.y);
@@ -237,7 +252,7 @@ __device__ __forceinline__ void pair_masks(const float4* __restrict__ A, const f
     // corner margin tests first (their operands die early): kernel.cu:51-61
     uint32_t cm = 0;
     {
-        const float4 am = A[REC_CULL], at = A[REC_TRIG], bm = B[REC_CULL], bt = B[REC_TRIG];
+        const float4 am = A[REC_CULL], at = A[REC_TRIG], bm = STAGE ? ld_keep(B + REC_CULL) : B[REC_CULL], bt = STAGE ? ld_keep(B + REC_TRIG) : B[REC_TRIG];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             {

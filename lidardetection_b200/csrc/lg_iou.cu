@@ -133,8 +133,94 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_S
     q.rcount = 0;
     float2* const slab_warp = slab + warp * 32;
 
-    const int rsub = warp >> 1, cbase = (warp & 1) * 64 + 2 * lane;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (!DENSE) {
+        // ---- sparse build (the usual matrix: < 6 % of the pairs survive the cull): the sweep is a stream of zeros, so it is laid
+        // out for the store -- FOUR adjacent columns per lane (one 16-byte st.global.cs per lane and row: a warp writes 512
+        // contiguous bytes), four consecutive rows per warp and trip.  The zeros are stored UNCONDITIONALLY, straight after the
+        // packed cull (no predicate, no branch); the few survivors go onto the warp's list and their results overwrite the zero
+        // after the __syncwarp that closes the trip (same warp, ordered by the barrier).  ~13 instructions per 64 pairs.
+        const int cl = 4 * lane;
+        const unsigned lt = (1u << lane) - 1u;
+        const bool vec4_ok = REDUCE || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(outb) & 15) == 0));
+        float4 bn[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) bn[u] = cl + u < nb ? ld_keep(gcull + cl + u) : zero4;
+        for (int t = 0;; t++) {  // one extra trip flushes the list (a single call site of the polygon path keeps the code small)
+            const bool last = t >= ntiles;
+            if (!last) {
+                const int ct = (t >> 1) * SK_TCOLS, c = ct + cl;  // this lane's first column, relative to col0
+                float4 b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) b[u] = bn[u];
+                if (t & 1) {  // both row halves of this column tile use b; fetch the next tile's quads now
+                    const int cn = c + SK_TCOLS;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) bn[u] = cn + u < nb ? ld_keep(gcull + cn + u) : zero4;
+                }
+                const int rbase = (t & 1) * SK_TROWS + warp * 4;  // this warp's four rows of the trip
+                if (rbase < na) {
+                    float* outp = outb + (int64_t)rbase * ld + c;
+                    auto push4 = [&](const int row, const bool s0, const bool s1, const bool s2, const bool s3) {
+                        if (!__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) return;  // the usual case: one vote per row
+                        const bool sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const unsigned mu = __ballot_sync(0xffffffffu, sv[u]);
+                            if (sv[u]) q.list[q.count + __popc(mu & lt)] = (uint32_t)((row << SK_SHIFT) | (c + u));
+                            q.count += __popc(mu);
+                        }
+                    };
+                    if (vec4_ok && rbase + 4 <= na && ct + SK_TCOLS <= nb) {  // full rows x full column tile: packed cull, no bounds tests
+                        const f32x2 bx01 = pack2(b[0].x, b[1].x), by01 = pack2(b[0].y, b[1].y), br01 = pack2(b[0].z, b[1].z);
+                        const f32x2 bx23 = pack2(b[2].x, b[3].x), by23 = pack2(b[2].y, b[3].y), br23 = pack2(b[2].z, b[3].z);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const ulonglong2 axy = *reinterpret_cast<const ulonglong2*>(sDup + 2 * (rbase + k));  // (cx,cx), (cy,cy)
+                            const f32x2 ar = *reinterpret_cast<const f32x2*>(sDup + 2 * (rbase + k) + 1);         // (rad,rad)
+                            const f32x2 dxa = sub2(axy.x, bx01), dya = sub2(axy.y, by01), rra = add2(ar, br01);
+                            const f32x2 dxb = sub2(axy.x, bx23), dyb = sub2(axy.y, by23), rrb = add2(ar, br23);
+                            const f32x2 d2a = fma2(dxa, dxa, mul2(dya, dya)), r2a = mul2(rra, rra);
+                            const f32x2 d2b = fma2(dxb, dxb, mul2(dyb, dyb)), r2b = mul2(rrb, rrb);
+                            float d0, d1, d2, d3, r0, r1, r2, r3;
+                            unpack2(d2a, d0, d1);
+                            unpack2(r2a, r0, r1);
+                            unpack2(d2b, d2, d3);
+                            unpack2(r2b, r2, r3);
+                            if (!REDUCE) {
+                                __stcs(reinterpret_cast<float4*>(outp), zero4);  // culled or not: exactly +0.0 first
+                                outp += ld;
+                            }
+                            push4(rbase + k, !(d0 > r0), !(d1 > r1), !(d2 > r2), !(d3 > r3));  // NaN => keep: the polygon path decides
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int k = 0; k < 4; k++) {
+                            const int r = rbase + k;
+                            bool sv[4] = {false, false, false, false};
+                            if (r < na) {
+                                const float4 ac = sA[r * REC_F4 + REC_CULL];
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (c + u < nb) {
+                                        sv[u] = cull_survives(ac, b[u]);
+                                        if (!REDUCE && !sv[u]) __stcs(outp + u, 0.f);
+                                    }
+                            }
+                            outp += ld;
+                            push4(r, sv[0], sv[1], sv[2], sv[3]);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            while (q.count >= (last ? 1 : 32)) warp_round<FL, SK_SHIFT, false>(q, sA, gB, slab_warp, NT, lane, emit);
+            if (last) break;
+        }
+        if (q.rcount > 0) warp_drain_rare<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
+        return;
+    }
+    const int rsub = warp >> 1, cbase = (warp & 1) * 64 + 2 * lane;
     float4 bn0 = cbase < nb ? __ldg(gcull + cbase) : zero4, bn1 = cbase + 1 < nb ? __ldg(gcull + cbase + 1) : zero4;
     for (int t = 0;; t++) {  // one extra trip flushes the list (a single call site of the polygon path keeps the code small)
         const bool last = t >= ntiles;

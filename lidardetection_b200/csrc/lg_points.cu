@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
     __shared__ float red[8][6];
     __shared__ PibGrid sgrid;
     __shared__ int s_use_grid, s_nvalid, s_total;
+    __shared__ int s_done[PIB_STAGES];  // warps that have finished with the stage's current tile
 
     const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t p_begin = (int64_t)blockIdx.x * pts_per_cta;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
         }
     };
     if (tid == 0) {
+        for (int s = 0; s < PIB_STAGES; s++) s_done[s] = 0;
         for (int s = 0; s < PIB_STAGES; s++) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -366,17 +368,30 @@ __global__ void __launch_bounds__(PIB_THREADS, LG_PIB_MINB)
         if (tma_ok && (bytes & 15) == 0) {
             mbar_wait(&bars[s], (unsigned)((t / PIB_STAGES) & 1));
         } else {
+            __syncthreads();  // (rare path) every warp is done with the tile this stage held
             const float* src = gp + (int64_t)t * PIB_TILE * 3;
             for (int i = tid; i < np * 3; i += NT) sp[i] = __ldg(src + i);
             __syncthreads();
         }
         const int wbase = warp * PIB_WPTS;       // this warp's first point within the tile
         process(sp + wbase * 3, np - wbase, t * PIB_TILE + wbase);
-        __syncwarp();  // orders the fill above, and the list writes, before the rounds
+        __syncwarp();  // orders the fill above, and the list writes, before the rounds; the warp has read its points
+        // No CTA barrier per tile: a warp that is done with the stage signs off, and the LAST one to do so refills it (tile
+        // t + PIB_STAGES) -- nobody waits for the slowest warp except through the data it needs next.  The work-list items carry
+        // their coordinates, so the rounds below no longer touch the stage.
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&s_done[s], 1) == PIB_WARPS - 1) {
+                s_done[s] = 0;  // the next sign-off for this stage comes after the refill issued here has landed
+                __threadfence_block();
+                if (t + PIB_STAGES < ntiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(t + PIB_STAGES);
+                }
+            }
+        }
         if (use_grid)
             while (wcount >= 32) round(32);
-        __syncthreads();  // everyone is done with this stage: refill it
-        if (tid == 0 && t + PIB_STAGES < ntiles) issue(t + PIB_STAGES);
     }
     if (use_grid && wcount > 0) round(wcount);
 }

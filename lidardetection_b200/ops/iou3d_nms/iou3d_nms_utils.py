@@ -316,3 +316,68 @@ def nms_gpu_batched_from_host(h_boxes, h_scores, thresh, counts=None, max_keep=N
     cur.wait_stream(side)
     b.record_stream(cur)
     return _nms_call(fn, b.contiguous(), order, counts, thresh, _lib.LG_FLAG_NONE, buffers, max_keep)
+
+
+class HostNmsPipeline:
+    """Serving loop for batches of frames that arrive in (pinned) host memory, one batch after the other
+    (post-processing of a detector that runs elsewhere, or offline evaluation from saved predictions).
+
+    submit() queues  upload -> score sort -> rotated NMS -> download  of one batch on the pipeline's own streams and returns at
+    once; result(ticket) waits for that batch only.  `depth` batches are in flight, each with its own device and pinned result
+    buffers: the boxes of batch k + 1 cross PCIe while batch k is in the kernels (on nms_cfg2 the upload, 8.4 MB, takes about as
+    long as the kernels do).  Every batch is copied host -> device and its result device -> host; nothing is cached between
+    batches.  Results are those of nms_gpu_batched(h_boxes.cuda(), h_scores.cuda(), thresh, max_keep=max_keep).
+
+        pipe = HostNmsPipeline(64, 4096, 0.01, max_keep=500)
+        t = pipe.submit(h_boxes, h_scores)       # returns immediately
+        ...
+        h_keep, h_num = pipe.result(t)           # pinned (P, max_keep) int64 / (P,) int32; valid until `depth` more submits
+    """
+
+    def __init__(self, num_problems, num_boxes, thresh, max_keep=None, depth=2, device=None):
+        assert depth >= 1 and num_problems > 0 and num_boxes > 0
+        self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.P, self.N, self.thresh, self.depth = int(num_problems), int(num_boxes), float(thresh), int(depth)
+        self.K = self.N if max_keep is None else min(int(max_keep), self.N)
+        self.up, self.comp = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                'boxes': torch.empty((self.P, self.N, 7), dtype=torch.float32, device=self.dev),
+                'scores': torch.empty((self.P, self.N), dtype=torch.float32, device=self.dev),
+                'keep': torch.empty((self.P, self.K), dtype=torch.int64, device=self.dev),
+                'h_keep': torch.empty((self.P, self.K), dtype=torch.int64).pin_memory(),
+                'h_num': torch.empty((self.P,), dtype=torch.int32).pin_memory(),
+                'ev_up': torch.cuda.Event(), 'ev_done': torch.cuda.Event(), 'ticket': -1, 'pending': False,
+            })
+        self.next_ticket = 0
+
+    def submit(self, h_boxes, h_scores):
+        assert tuple(h_boxes.shape) == (self.P, self.N, 7) and tuple(h_scores.shape) == (self.P, self.N)
+        assert h_boxes.dtype == torch.float32 and h_scores.dtype == torch.float32 and not h_boxes.is_cuda
+        t = self.next_ticket
+        s = self.slots[t % self.depth]
+        if s['pending']:
+            raise RuntimeError('HostNmsPipeline: result() of ticket %d has not been collected (depth %d)' % (s['ticket'], self.depth))
+        with torch.cuda.stream(self.up):
+            # the slot's previous batch has left the kernels (its result() synchronised on ev_done): the buffers are free
+            s['scores'].copy_(h_scores, non_blocking=True)
+            s['boxes'].copy_(h_boxes, non_blocking=True)
+            s['ev_up'].record(self.up)
+        with torch.cuda.stream(self.comp):
+            self.comp.wait_event(s['ev_up'])
+            keep, num = nms_gpu_batched(s['boxes'], s['scores'], self.thresh, max_keep=self.K, keep_out=s['keep'])
+            s['h_keep'].copy_(keep, non_blocking=True)
+            s['h_num'].copy_(num, non_blocking=True)
+            s['ev_done'].record(self.comp)
+        s['ticket'], s['pending'] = t, True
+        self.next_ticket += 1
+        return t
+
+    def result(self, ticket):
+        s = self.slots[ticket % self.depth]
+        if s['ticket'] != ticket or not s['pending']:
+            raise RuntimeError('HostNmsPipeline: ticket %d is not in flight' % ticket)
+        s['ev_done'].synchronize()
+        s['pending'] = False
+        return s['h_keep'], s['h_num']

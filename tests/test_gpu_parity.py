@@ -280,6 +280,32 @@ def test_nms_from_pinned_host_inputs_equals_the_device_call():
                 assert torch.equal(k0, k1) and torch.equal(n0, n1)
 
 
+def test_host_nms_pipeline_equals_the_device_call_batch_by_batch():
+    """HostNmsPipeline: batches in flight share nothing -- every ticket returns the keep lists of ITS batch, in any collection
+    order the depth allows, and a slot is not reused before its result was collected"""
+    batches = [synth.nms_frames(5, 700, seed=70 + k) for k in range(5)]
+    host = [(torch.from_numpy(b).pin_memory(), torch.from_numpy(s).pin_memory()) for b, s in batches]
+    want = [U.nms_gpu_batched(cu(b), cu(s), 0.1, max_keep=40) for b, s in batches]
+    for depth in (1, 2, 3):
+        pipe = U.HostNmsPipeline(5, 700, 0.1, max_keep=40, depth=depth)
+        tickets = []
+        for k, (hb, hs) in enumerate(host):
+            if len(tickets) == depth:  # collect the oldest before its slot is needed again
+                t = tickets.pop(0)
+                hk, hn = pipe.result(t)
+                assert torch.equal(hk, want[t][0].cpu()) and torch.equal(hn, want[t][1].cpu()), (depth, t)
+            tickets.append(pipe.submit(hb, hs))
+        for t in tickets:
+            hk, hn = pipe.result(t)
+            assert torch.equal(hk, want[t][0].cpu()) and torch.equal(hn, want[t][1].cpu()), (depth, t)
+    pipe = U.HostNmsPipeline(5, 700, 0.1, max_keep=40, depth=1)
+    pipe.submit(*host[0])
+    with pytest.raises(RuntimeError):
+        pipe.submit(*host[1])  # depth 1: the first result has not been collected
+    with pytest.raises(RuntimeError):
+        pipe.result(7)
+
+
 def test_nms_threshold_edge_values():
     """thresh < 0: the exact-zero IoU of disjoint boxes exceeds it too (kernel.cu:304), so only the best box survives -- the
     kernels' exact-zero cull must not change that; thresh = NaN: nothing is suppressed; thresh >= 1: only IoUs above 1"""
