@@ -55,6 +55,8 @@ extern "C" {
 #define LG_FLAG_STRICT_FP32 1u /* un-contracted FP32 (reference CPU build's rounding) instead of the reference CUDA build's */
 #define LG_FLAG_NMS_NO_CLUSTER 4u /* lazy rotated NMS: one CTA per problem even when the batch is small enough to give every
                                     problem a thread-block cluster of 2-8 SMs (the default); same keep list either way */
+#define LG_FLAG_IOU_SMALL_LIST 8u /* (testing) N x M IoU, two-phase sweep: shrink the survivor list to 1024 entries so that the
+                                     overflow path (the complete one-kernel sweep on the flagged strips) is exercised */
 #define LG_FLAG_NMS_FULL_MASK 2u /* rotated NMS: materialise the reference's N x N/64 suppression mask (upper triangle) and sweep
                                     it, instead of the default lazy evaluation of kept rows only; same keep list either way */
 

@@ -27,6 +27,27 @@
 
 namespace lg {
 
+// records of both box sets + the column cull quads + the density flag (16 B) + 16 B of slack, a multiple of 16 bytes
+static inline size_t lg_iou_workspace_bytes_base(int64_t n, int64_t m) {
+    return (size_t)(n + m) * REC_F4 * sizeof(float4) + (size_t)m * sizeof(float4) + 16 /* density flag */ + 16;
+}
+
+static inline unsigned pairs_grid() {  // iou_pairs_kernel: a grid-stride loop, three CTAs per SM
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    static std::atomic<int> cache[64];
+    if (dev >= 0 && dev < 64) {
+        int v = cache[dev].load(std::memory_order_relaxed);
+        if (v == 0) {
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cache[dev].store(sms, std::memory_order_relaxed);
+        } else {
+            sms = v;
+        }
+    }
+    return (unsigned)(3 * sms);
+}
+
 template <int FL>
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ a, int64_t n, const float* __restrict__ b,
                                                    int64_t m, float4* __restrict__ rec_a, float4* __restrict__ rec_b,
@@ -86,9 +107,10 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_S
     iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
                      const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
                      const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,
-                     unsigned long long* __restrict__ colkey, const int* __restrict__ dense_flag) {
+                     unsigned long long* __restrict__ colkey, const int* __restrict__ dense_flag, const int* __restrict__ cta_only) {
     constexpr int NT = ST_THREADS;
     if (dense_flag && (*dense_flag != 0) != DENSE) return;
+    if (cta_only && cta_only[blockIdx.x] == 0) return;  // two-phase path: only the strips whose survivors did not fit the list
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
     float4* sDup = sA + SK_ROWS * REC_F4;  // per row: (cx, cx, cy, cy), (rad, rad, -, -)
@@ -301,6 +323,222 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_S
     if (q.rcount > 0) warp_drain_rare<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Two-phase form of the sparse sweep (large matrices): the matrix is a stream of zeros with a few survivors, so the sweep
+// and the polygon path are separate kernels with the resources each needs.
+//   iou_sweep_kernel   cull + unconditional 16-byte zero stores + the survivors' (row, column) pairs appended to ONE global list;
+//                      no records, no polygon code: few registers, a full SM of warps -- it runs at the speed of the store stream;
+//   iou_pairs_kernel   the polygon path on the list, one pair per lane, always on full warps (the dense build's inlined path);
+//                      results overwrite the zeros (a later launch of the same stream).
+// The list has a fixed capacity (SweepPlan).  A strip whose survivors do not fit raises its flag in cta_over and stops; the
+// complete one-kernel sweep (iou_strip_kernel<., ., false>) then redoes exactly the flagged strips -- any density is handled,
+// the usual one (< 1 % survivors) never gets there.  list entry: row << 32 | column (global indices); ~0 = hole left by a
+// reservation that straddled the capacity.
+constexpr int SW_LIST = 31 + 512;        // per-warp staging: leftover + one trip (4 rows x 128 columns)
+constexpr int SW_FLUSH = 128;            // staged survivors that trigger a flush (one global atomicAdd per flush)
+constexpr unsigned long long SW_HOLE = ~0ull;
+struct SweepCtrl {
+    unsigned long long count;  // list entries reserved so far (may exceed the capacity)
+    unsigned long long pad;
+};
+
+template <bool REDUCE>
+__global__ void __launch_bounds__(ST_THREADS)
+    iou_sweep_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ cull_b, const int64_t m,
+                     float* __restrict__ out, const int64_t ld, const int cols_per_cta, const int64_t strips_m,
+                     const int* __restrict__ dense_flag, SweepCtrl* __restrict__ ctrl, int* __restrict__ cta_over,
+                     unsigned long long* __restrict__ list, const unsigned long long cap) {
+    if (dense_flag && *dense_flag != 0) return;
+    __shared__ float4 sDup[SK_ROWS * 2];  // per row: (cx, cx, cy, cy), (rad, rad, -, -)
+    __shared__ uint32_t lists[(ST_THREADS / 32) * SW_LIST];
+    __shared__ int s_over;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t strip = blockIdx.x;
+    const int64_t sn = strip / strips_m, sm = strip - sn * strips_m;
+    const int64_t row0 = sn * SK_ROWS, col0 = sm * cols_per_cta;
+    const int na = (int)min((int64_t)SK_ROWS, n - row0), nb = (int)min((int64_t)cols_per_cta, m - col0);
+    const int ntc = (nb + SK_TCOLS - 1) / SK_TCOLS;  // column tiles
+    if (tid < SK_ROWS) {
+        const float4 c = tid < na ? __ldg(rec_a + (row0 + tid) * REC_F4 + REC_CULL) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sDup[2 * tid] = make_float4(c.x, c.x, c.y, c.y);
+        sDup[2 * tid + 1] = make_float4(c.z, c.z, 0.f, 0.f);
+    }
+    if (tid == 0) s_over = 0;
+    __syncthreads();  // the only CTA barrier
+    const float4* const gcull = cull_b + col0;
+    float* const outb = REDUCE ? nullptr : out + row0 * ld + col0;
+    const bool vec4_ok = REDUCE || (((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(outb) & 15) == 0));
+    uint32_t* const wl = lists + warp * SW_LIST;
+    int count = 0;  // warp-uniform
+    const unsigned lt = (1u << lane) - 1u;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cl = 4 * lane;
+    auto flush = [&]() {  // the staged survivors go to the global list: one reservation per flush
+        __syncwarp();
+        unsigned long long base = 0ull;
+        if (lane == 0) base = atomicAdd(&ctrl->count, (unsigned long long)count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + (unsigned long long)count <= cap) {
+            for (int i = lane; i < count; i += 32) {
+                const uint32_t e = wl[i];
+                list[base + i] = ((unsigned long long)(row0 + (e >> SK_SHIFT)) << 32) | (unsigned long long)(col0 + (e & (SK_MAX_COLS - 1)));
+            }
+        } else {
+            for (unsigned long long i = base + lane; i < cap; i += 32) list[i] = SW_HOLE;  // the part of the reservation below the capacity
+            if (lane == 0) {
+                cta_over[blockIdx.x] = 1;
+                s_over = 1;
+            }
+        }
+        count = 0;
+        __syncwarp();
+    };
+    float4 bn[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) bn[u] = cl + u < nb ? ld_keep(gcull + cl + u) : zero4;
+    for (int tc = 0; tc < ntc; tc++) {
+        if (*(volatile int*)&s_over) break;  // this strip goes to the complete sweep: stop producing
+        const int ct = tc * SK_TCOLS, c = ct + cl;  // this lane's first column, relative to col0
+        float4 b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) b[u] = bn[u];
+        {
+            const int cn = c + SK_TCOLS;  // the next tile's quads: in flight during this tile's 8 rows
+#pragma unroll
+            for (int u = 0; u < 4; u++) bn[u] = cn + u < nb ? ld_keep(gcull + cn + u) : zero4;
+        }
+        const f32x2 bx01 = pack2(b[0].x, b[1].x), by01 = pack2(b[0].y, b[1].y), br01 = pack2(b[0].z, b[1].z);
+        const f32x2 bx23 = pack2(b[2].x, b[3].x), by23 = pack2(b[2].y, b[3].y), br23 = pack2(b[2].z, b[3].z);
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            const int rbase = half * SK_TROWS + warp * 4;  // this warp's four rows of the half
+            if (rbase >= na) break;
+            auto push4 = [&](const int row, const bool s0, const bool s1, const bool s2, const bool s3) {
+                if (!__any_sync(0xffffffffu, s0 | s1 | s2 | s3)) return;  // the usual case: one vote per row
+                const bool sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const unsigned mu = __ballot_sync(0xffffffffu, sv[u]);
+                    if (sv[u]) wl[count + __popc(mu & lt)] = (uint32_t)((row << SK_SHIFT) | (c + u));
+                    count += __popc(mu);
+                }
+            };
+            if (vec4_ok && rbase + 4 <= na && ct + SK_TCOLS <= nb) {  // full rows x full column tile: packed cull, no bounds tests
+                float* outp = REDUCE ? nullptr : outb + (int64_t)rbase * ld + c;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const ulonglong2 axy = *reinterpret_cast<const ulonglong2*>(sDup + 2 * (rbase + k));  // (cx,cx), (cy,cy)
+                    const f32x2 ar = *reinterpret_cast<const f32x2*>(sDup + 2 * (rbase + k) + 1);         // (rad,rad)
+                    const f32x2 dxa = sub2(axy.x, bx01), dya = sub2(axy.y, by01), rra = add2(ar, br01);
+                    const f32x2 dxb = sub2(axy.x, bx23), dyb = sub2(axy.y, by23), rrb = add2(ar, br23);
+                    const f32x2 d2a = fma2(dxa, dxa, mul2(dya, dya)), r2a = mul2(rra, rra);
+                    const f32x2 d2b = fma2(dxb, dxb, mul2(dyb, dyb)), r2b = mul2(rrb, rrb);
+                    float d0, d1, d2, d3, r0, r1, r2, r3;
+                    unpack2(d2a, d0, d1);
+                    unpack2(r2a, r0, r1);
+                    unpack2(d2b, d2, d3);
+                    unpack2(r2b, r2, r3);
+                    if (!REDUCE) {
+                        __stcs(reinterpret_cast<float4*>(outp), zero4);  // survivor or not: exactly +0.0 first
+                        outp += ld;
+                    }
+                    push4(rbase + k, !(d0 > r0), !(d1 > r1), !(d2 > r2), !(d3 > r3));  // NaN => keep: the polygon path decides
+                }
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) {
+                    const int r = rbase + k;
+                    bool sv[4] = {false, false, false, false};
+                    if (r < na) {
+                        const float4 ac = make_float4(sDup[2 * r].x, sDup[2 * r].z, sDup[2 * r + 1].x, 0.f);
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (c + u < nb) {
+                                sv[u] = cull_survives(ac, b[u]);
+                                if (!REDUCE) __stcs(outb + (int64_t)r * ld + c + u, 0.f);
+                            }
+                    }
+                    push4(r, sv[0], sv[1], sv[2], sv[3]);
+                }
+            }
+            if (count >= SW_FLUSH) flush();
+        }
+    }
+    if (count > 0) flush();
+}
+
+// The polygon path on the survivor list: a grid-stride loop, 32 consecutive entries per warp and trip.
+template <int FL, bool REDUCE>
+__global__ void __launch_bounds__(ST_THREADS, 3)
+    iou_pairs_kernel(const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const unsigned long long* __restrict__ list,
+                     const SweepCtrl* __restrict__ ctrl, const unsigned long long cap, float* __restrict__ out, const int64_t ld,
+                     const int mode, unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
+                     const int* __restrict__ dense_flag) {
+    if (dense_flag && *dense_flag != 0) return;
+    constexpr int NT = ST_THREADS, NW = NT / 32, RARE = 64;
+    __shared__ float2 slab[SLAB_ROWS * NT];
+    __shared__ unsigned long long rare[NW * RARE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long total = min(ctrl->count, cap);
+    float2* const slab_warp = slab + warp * 32;
+    unsigned long long* const wr = rare + warp * RARE;
+    int rcount = 0;  // warp-uniform
+    auto emit = [&](const unsigned long long e, const float ov, const float4* A, const float4* B) {
+        const float v = finish_pair(mode, ov, A, B);
+        const unsigned r = (unsigned)(e >> 32), c = (unsigned)e;
+        if (REDUCE) {
+            if (v > 0.f) {  // zeros never beat the initial key (0.0, index 0)
+                if (rowkey) atomicMax(rowkey + r, max_key(v, c));
+                if (colkey) atomicMax(colkey + c, max_key(v, r));
+            }
+        } else {
+            __stcs(out + (int64_t)r * ld + c, v);
+        }
+    };
+    // the deferred pairs of this warp (> 8 vertices, angular near-ties): lanes 0..7, 16 vertex + 16 angle slots each
+    auto drain_rare_list = [&]() {
+        __syncwarp();
+        if (lane < 8) {
+            auto slab16 = [&](int k) -> float2& { return slab_warp[(k & 7) * NT + lane + ((k >> 3) << 3)]; };
+            auto ang16 = [&](int k) -> float& { return reinterpret_cast<float*>(slab_warp + (k >> 1) * NT + 16 + lane)[k & 1]; };
+            for (int i = lane; i < rcount; i += 8) {
+                const unsigned long long e = wr[i];
+                const float4* A = rec_a + (int64_t)(e >> 32) * REC_F4;
+                const float4* B = rec_b + (int64_t)(e & 0xFFFFFFFFull) * REC_F4;
+                float ov = overlap_area16<FL>(A, B, slab16);
+                if (ov < 0.f) ov = overlap_area_slow<FL>(A, B, slab16, ang16);
+                emit(e, ov, A, B);
+            }
+        }
+        rcount = 0;
+        __syncwarp();
+    };
+    const unsigned long long stride = (unsigned long long)gridDim.x * NW * 32;
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * NW + warp) * 32; base < total; base += stride) {
+        const unsigned long long idx = base + lane;
+        unsigned long long e = SW_HOLE;
+        if (idx < total) e = __ldg(list + idx);
+        const bool act = e != SW_HOLE;
+        const unsigned wm = __ballot_sync(0xffffffffu, act);
+        bool defer = false;
+        if (act) {
+            const float4* A = rec_a + (int64_t)(e >> 32) * REC_F4;
+            const float4* B = rec_b + (int64_t)(e & 0xFFFFFFFFull) * REC_F4;
+            const float ov = overlap_area<FL, true>(A, B, slab_warp + lane, NT, wm);
+            if (ov < 0.f) defer = true;
+            else emit(e, ov, A, B);
+        }
+        const unsigned dm = __ballot_sync(0xffffffffu, defer);
+        if (dm) {
+            if (defer) wr[rcount + __popc(dm & ((1u << lane) - 1u))] = e;
+            rcount += __popc(dm);
+            if (rcount > RARE - 32) drain_rare_list();
+        }
+        __syncwarp();
+    }
+    if (rcount > 0) drain_rare_list();
+}
+
 // Survivor density of the exact-zero cull, estimated from 8192 pseudo-random pairs: flag = 1 when more than ~6 % survive.
 __global__ void __launch_bounds__(256) density_probe_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ cull_b,
                                                              const int64_t m, int* __restrict__ flag) {
@@ -415,6 +653,43 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
     }
 }
 
+// strip decomposition of an N x M sweep and, for large matrices, the two-phase plan (survivor list in the workspace)
+struct SweepPlan {
+    int64_t cols, strips_m, strips;
+    bool two_phase;
+    unsigned long long cap;  // list entries
+    size_t extra_bytes;      // control block + per-strip flags + list, appended to the workspace
+    size_t flags_bytes;
+};
+static SweepPlan sweep_plan(int64_t n, int64_t m, unsigned flags) {
+    SweepPlan p = {};
+    if (n <= 0 || m <= 0) return p;
+    // columns per CTA: as long a run as still leaves >= ~16 CTAs per SM-slot for load balance (148 SMs x 3 CTAs)
+    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS;
+    int64_t want_m = (16 * 444 + strips_n - 1) / strips_n;  // column splits wanted
+    if (want_m < 1) want_m = 1;
+    int64_t cols = (m + want_m - 1) / want_m;
+    cols = (cols + SK_TCOLS - 1) / SK_TCOLS * SK_TCOLS;
+    if (cols < 2 * SK_TCOLS) cols = 2 * SK_TCOLS;
+    if (cols > SK_MAX_COLS) cols = SK_MAX_COLS;
+    p.cols = cols;
+    p.strips_m = (m + cols - 1) / cols;
+    p.strips = strips_n * p.strips_m;
+    // two-phase from 2^24 pairs on (below that the extra launches cost more than the sweep); indices are packed in 32 bits
+    const double pairs = (double)n * (double)m;
+    p.two_phase = m > FLAT_COLS && pairs >= 16777216.0 && n < 0xFFFFFFFFLL && m < 0xFFFFFFFFLL && p.strips <= 0x7fffffffLL;
+    if (p.two_phase) {
+        double cap = pairs / 32.0;  // ~3 % survivors; the usual matrix has < 1 %
+        if (cap < 65536.0) cap = 65536.0;
+        if (cap > 33554432.0) cap = 33554432.0;  // 256 MB
+        p.cap = (unsigned long long)cap;
+        p.flags_bytes = align_up((size_t)p.strips * sizeof(int), 16);
+        p.extra_bytes = sizeof(SweepCtrl) + p.flags_bytes + (size_t)p.cap * sizeof(unsigned long long);
+        if (flags & LG_FLAG_IOU_SMALL_LIST) p.cap = 1024;  // (testing) same layout, tiny capacity: the overflow path
+    }
+    return p;
+}
+
 static int check_args(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, size_t ws_bytes) {
     if (n < 0 || m < 0) {
         set_error("negative size n=%lld m=%lld", (long long)n, (long long)m);
@@ -438,7 +713,7 @@ static int check_args(const float* a, int64_t n, const float* b, int64_t m, floa
 
 template <int FL>
 static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws, int mode,
-                   cudaStream_t st) {
+                   cudaStream_t st, unsigned flags) {
     int rc;
     if (m <= FLAT_COLS) {
         const int64_t ctas = (n + FLAT_ROWS - 1) / FLAT_ROWS;
@@ -458,16 +733,8 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
     const int64_t total = n + m;
     prep_kernel<FL><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, n, b, m, ra, rb, cb);
     if ((rc = check_launch("prep_kernel"))) return rc;
-    // columns per CTA: as long a run as still leaves >= ~16 CTAs per SM-slot for load balance (148 SMs x 3 CTAs)
-    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS;
-    int64_t want_m = (16 * 444 + strips_n - 1) / strips_n;  // column splits wanted
-    if (want_m < 1) want_m = 1;
-    int64_t cols = (m + want_m - 1) / want_m;
-    cols = (cols + SK_TCOLS - 1) / SK_TCOLS * SK_TCOLS;
-    if (cols < 2 * SK_TCOLS) cols = 2 * SK_TCOLS;
-    if (cols > SK_MAX_COLS) cols = SK_MAX_COLS;
-    const int64_t strips_m = (m + cols - 1) / cols;
-    const int64_t strips = strips_n * strips_m;
+    const SweepPlan pl = sweep_plan(n, m, flags);
+    const int64_t cols = pl.cols, strips_m = pl.strips_m, strips = pl.strips;
     if (strips > 0x7fffffffLL) {
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
         return LG_ERR_TOO_LARGE;
@@ -479,8 +746,27 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
     auto kd = iou_strip_kernel<FL, false, true>;
     if ((rc = set_smem(ks, StripSmem::total))) return rc;
     if ((rc = set_smem(kd, StripSmem::total))) return rc;
-    ks<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag);
-    kd<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag);
+    const int* only = nullptr;
+    if (pl.two_phase) {
+        // sparse matrices: zeros + survivor list, then the polygon path on the list; the complete sweep below redoes only the strips
+        // whose survivors did not fit (none, normally)
+        char* extra = reinterpret_cast<char*>(ws) + lg_iou_workspace_bytes_base(n, m);
+        SweepCtrl* ctrl = reinterpret_cast<SweepCtrl*>(extra);
+        int* over = reinterpret_cast<int*>(extra + sizeof(SweepCtrl));
+        unsigned long long* list = reinterpret_cast<unsigned long long*>(extra + sizeof(SweepCtrl) + pl.flags_bytes);
+        cudaError_t e = cudaMemsetAsync(extra, 0, sizeof(SweepCtrl) + pl.flags_bytes, st);
+        if (e != cudaSuccess) {
+            set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        iou_sweep_kernel<false><<<(unsigned)strips, ST_THREADS, 0, st>>>(ra, n, cb, m, out, ld, (int)cols, strips_m, flag, ctrl, over, list, pl.cap);
+        if ((rc = check_launch("iou_sweep_kernel"))) return rc;
+        iou_pairs_kernel<FL, false><<<pairs_grid(), ST_THREADS, 0, st>>>(ra, rb, list, ctrl, pl.cap, out, ld, mode, nullptr, nullptr, flag);
+        if ((rc = check_launch("iou_pairs_kernel"))) return rc;
+        only = over;
+    }
+    ks<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag, only);
+    kd<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag, nullptr);
     return check_launch("iou_strip_kernel");
 }
 
@@ -501,7 +787,7 @@ __global__ void __launch_bounds__(256) key_unpack_kernel(const unsigned long lon
 
 template <int FL>
 static int run_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, void* ws, int mode, float* row_max, int64_t* row_arg,
-                          float* col_max, int64_t* col_arg, cudaStream_t st) {
+                          float* col_max, int64_t* col_arg, cudaStream_t st, unsigned flags) {
     float4* ra = reinterpret_cast<float4*>(ws);
     float4* rb = ra + n * REC_F4;
     float4* cb = rb + m * REC_F4;
@@ -514,22 +800,32 @@ static int run_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, 
     if ((rc = check_launch("prep_kernel"))) return rc;
     key_init_kernel<<<(unsigned)((n + m + 255) / 256), 256, 0, st>>>(keys, n + m);
     if ((rc = check_launch("key_init_kernel"))) return rc;
-    const int64_t strips_n = (n + SK_ROWS - 1) / SK_ROWS;
-    int64_t want_m = (16 * 444 + strips_n - 1) / strips_n;
-    if (want_m < 1) want_m = 1;
-    int64_t cols = (m + want_m - 1) / want_m;
-    cols = (cols + SK_TCOLS - 1) / SK_TCOLS * SK_TCOLS;
-    if (cols < 2 * SK_TCOLS) cols = 2 * SK_TCOLS;
-    if (cols > SK_MAX_COLS) cols = SK_MAX_COLS;
-    const int64_t strips_m = (m + cols - 1) / cols;
-    const int64_t strips = strips_n * strips_m;
+    const SweepPlan pl = sweep_plan(n, m, flags);
+    const int64_t cols = pl.cols, strips_m = pl.strips_m, strips = pl.strips;
     if (strips > 0x7fffffffLL) {
         set_error("%lld strips exceed the 1-D grid limit; split the call by row blocks", (long long)strips);
         return LG_ERR_TOO_LARGE;
     }
     auto kern = iou_strip_kernel<FL, true, false>;
     if ((rc = set_smem(kern, StripSmem::total))) return rc;
-    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey, nullptr);
+    const int* only = nullptr;
+    if (pl.two_phase) {  // see run_iou; there is no density probe here: a dense matrix overflows the list at once and every strip falls back
+        char* extra = reinterpret_cast<char*>(ws) + lg_iou_workspace_bytes_base(n, m) + (size_t)(n + m) * sizeof(unsigned long long);
+        SweepCtrl* ctrl = reinterpret_cast<SweepCtrl*>(extra);
+        int* over = reinterpret_cast<int*>(extra + sizeof(SweepCtrl));
+        unsigned long long* list = reinterpret_cast<unsigned long long*>(extra + sizeof(SweepCtrl) + pl.flags_bytes);
+        cudaError_t e = cudaMemsetAsync(extra, 0, sizeof(SweepCtrl) + pl.flags_bytes, st);
+        if (e != cudaSuccess) {
+            set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        iou_sweep_kernel<true><<<(unsigned)strips, ST_THREADS, 0, st>>>(ra, n, cb, m, nullptr, 0, (int)cols, strips_m, nullptr, ctrl, over, list, pl.cap);
+        if ((rc = check_launch("iou_sweep_kernel<reduce>"))) return rc;
+        iou_pairs_kernel<FL, true><<<pairs_grid(), ST_THREADS, 0, st>>>(ra, rb, list, ctrl, pl.cap, nullptr, 0, mode, rowkey, colkey, nullptr);
+        if ((rc = check_launch("iou_pairs_kernel<reduce>"))) return rc;
+        only = over;
+    }
+    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey, nullptr, only);
     if ((rc = check_launch("iou_strip_kernel<reduce>"))) return rc;
     if (want_rows) key_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowkey, n, row_max, row_arg);
     if (want_cols) key_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(colkey, m, col_max, col_arg);
@@ -541,20 +837,20 @@ static int iou_entry(const float* a, int64_t n, const float* b, int64_t m, float
     int rc = check_args(a, n, b, m, out, ld, ws, ws_bytes);
     if (rc || n == 0 || m == 0) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (flags & LG_FLAG_STRICT_FP32) return run_iou<0>(a, n, b, m, out, ld, ws, mode, st);
-    return run_iou<1>(a, n, b, m, out, ld, ws, mode, st);
+    if (flags & LG_FLAG_STRICT_FP32) return run_iou<0>(a, n, b, m, out, ld, ws, mode, st, flags);
+    return run_iou<1>(a, n, b, m, out, ld, ws, mode, st, flags);
 }
 
 }  // namespace lg
 
 extern "C" size_t lg_iou_workspace_bytes(int64_t n, int64_t m) {
     if (n < 0 || m < 0) return 0;
-    return (size_t)(n + m) * lg::REC_F4 * sizeof(float4) + (size_t)m * sizeof(float4) + 16 /* density flag */ + 16;
+    return lg::lg_iou_workspace_bytes_base(n, m) + lg::sweep_plan(n, m, 0).extra_bytes;
 }
 
 extern "C" size_t lg_iou_reduce_workspace_bytes(int64_t n, int64_t m) {
     if (n < 0 || m < 0) return 0;
-    return lg_iou_workspace_bytes(n, m) + (size_t)(n + m) * sizeof(unsigned long long);
+    return lg::lg_iou_workspace_bytes_base(n, m) + (size_t)(n + m) * sizeof(unsigned long long) + lg::sweep_plan(n, m, 0).extra_bytes;
 }
 
 extern "C" int lg_boxes_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, int kind, float* row_max, int64_t* row_argmax,
@@ -584,8 +880,8 @@ extern "C" int lg_boxes_iou_reduce(const float* a, int64_t n, const float* b, in
         set_error("workspace %p of %zu B; need %zu B, 16-byte aligned", ws, ws_bytes, lg_iou_reduce_workspace_bytes(n, m));
         return LG_ERR_WORKSPACE;
     }
-    if (flags & LG_FLAG_STRICT_FP32) return run_iou_reduce<0>(a, n, b, m, ws, kind, row_max, row_argmax, col_max, col_argmax, st);
-    return run_iou_reduce<1>(a, n, b, m, ws, kind, row_max, row_argmax, col_max, col_argmax, st);
+    if (flags & LG_FLAG_STRICT_FP32) return run_iou_reduce<0>(a, n, b, m, ws, kind, row_max, row_argmax, col_max, col_argmax, st, flags);
+    return run_iou_reduce<1>(a, n, b, m, ws, kind, row_max, row_argmax, col_max, col_argmax, st, flags);
 }
 
 extern "C" int lg_boxes_overlap_bev(const float* a, int64_t n, const float* b, int64_t m, float* out, int64_t ld, void* ws,

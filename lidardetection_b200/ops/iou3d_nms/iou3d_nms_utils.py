@@ -94,7 +94,7 @@ def boxes_iou3d_gpu(boxes_a, boxes_b):
 _REDUCE_KINDS = {'overlap_bev': 0, 'iou_bev': 1, 'iou3d': 2}
 
 
-def boxes_iou_max(boxes_a, boxes_b, kind='iou3d', rows=True, cols=False):
+def boxes_iou_max(boxes_a, boxes_b, kind='iou3d', rows=True, cols=False, flags=_lib.LG_FLAG_NONE):
     """Row / column (max, argmax) of the N x M matrix `kind` without materialising it.
 
     What the callers of boxes_iou3d_gpu go on to compute -- `torch.max(iou3d, dim=1)` (proposal_target_layer.py:107),
@@ -114,7 +114,7 @@ def boxes_iou_max(boxes_a, boxes_b, kind='iou3d', rows=True, cols=False):
     with torch.cuda.device(dev):
         ws = _workspace(L.lg_iou_reduce_workspace_bytes(n, m), dev)
         rc = L.lg_boxes_iou_reduce(_lib.ptr(a), n, _lib.ptr(b), m, _REDUCE_KINDS[kind], _lib.ptr(rmax), _lib.ptr(rarg), _lib.ptr(cmax),
-                                   _lib.ptr(carg), _lib.ptr(ws), ws.numel(), _lib.LG_FLAG_NONE, _lib.stream_ptr(dev))
+                                   _lib.ptr(carg), _lib.ptr(ws), ws.numel(), flags, _lib.stream_ptr(dev))
     _lib.check(rc, 'lg_boxes_iou_reduce')
     out = ()
     if rows:
