@@ -398,8 +398,9 @@ class IouWorkload(Workload):
         self.pairs = a.shape[0] * b.shape[0]
         self.units = self.pairs / 1e9
         self.out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device="cuda")
-        # iou_flat_kernel alone (M <= 64); else prep_kernel + density_probe_kernel + the two iou_strip_kernel variants (one of them exits at once)
-        self.launches_per_step = 1 if b.shape[0] <= 64 else 4
+        # iou_flat_kernel alone (M <= 64); else prep_kernel + density_probe_kernel + the two iou_strip_kernel variants (one of them exits at
+        # once); from 2^26 pairs on also iou_sweep_kernel + iou_pairs_kernel (two-phase sweep; the sparse strip kernel then only mops up)
+        self.launches_per_step = 1 if b.shape[0] <= 64 else (6 if self.pairs >= (1 << 26) else 4)
         self.h2d = (a.size + b.size) * 4
         self.e2e_d2h_full = self.pairs * 4 <= (1 << 30)
         self.d2h = self.pairs * 4 if self.e2e_d2h_full else a.shape[0] * 8
@@ -453,8 +454,12 @@ class IouWorkload(Workload):
                     "algorithmic": {"pairs_per_launch": self.pairs, "nonzero_fraction": nz, "flops_per_pair": 307.0 * (1 - nz) + 818.0 * nz}}
         byts = 4.0 * n * m + 28.0 * (n + m)
         ach = byts / t / 1e9
-        r = {"bound": "hbm", "kernel": "iou_strip_kernel / iou_flat_kernel (+prep_kernel)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-             "traffic": None, "peak_source": hbm_src, "algorithmic": {"bytes_per_launch": byts, "formula": "4*N*M + 28*(N+M)"}}
+        kern = ("iou_flat_kernel" if m <= 64 else
+                "iou_sweep_kernel (zeros + survivor list, ~80 % of the step) + iou_pairs_kernel (polygon path on the list) + prep / probe"
+                if self.pairs >= (1 << 26) else "iou_strip_kernel (+prep_kernel, density_probe_kernel)")
+        r = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+             "traffic": None, "peak_source": hbm_src,
+             "algorithmic": {"bytes_per_launch": byts, "formula": "4*N*M + 28*(N+M)", "time": "the whole call (every launch of the step), CUDA events"}}
         if self.which == "iou_cfg1":
             r["note"] = ("launch / tail bound, not bandwidth bound: one 35 us launch writes 26 MB, which is still in the 126 MB L2 when the "
                          "kernel ends (DRAM traffic under ncu is a third of the algorithmic bytes); the fraction measures launch latency")

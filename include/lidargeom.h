@@ -57,6 +57,8 @@ extern "C" {
                                     problem a thread-block cluster of 2-8 SMs (the default); same keep list either way */
 #define LG_FLAG_IOU_SMALL_LIST 8u /* (testing) N x M IoU, two-phase sweep: shrink the survivor list to 1024 entries so that the
                                      overflow path (the complete one-kernel sweep on the flagged strips) is exercised */
+#define LG_FLAG_IOU_ONE_KERNEL 16u /* N x M IoU: the complete one-kernel sweep whatever the size (the two-phase sweep is the default
+                                      from 2^26 pairs on; results are identical) */
 #define LG_FLAG_NMS_FULL_MASK 2u /* rotated NMS: materialise the reference's N x N/64 suppression mask (upper triangle) and sweep
                                     it, instead of the default lazy evaluation of kept rows only; same keep list either way */
 

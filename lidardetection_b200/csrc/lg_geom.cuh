@@ -348,6 +348,80 @@ __device__ __forceinline__ float2 crossing_point(const float4* __restrict__ A, c
     return make_float2(X, Y);
 }
 
+// The heavy part of the fast path: 3..8 polygon vertices, from the masks of phase A.  All lanes of `hm` call it together (it
+// re-converges them after each data-dependent loop).  Returns the overlap area, or -1 on an angular near-tie.
+template <int FL, bool STAGE = false>
+__device__ __forceinline__ float overlap_area_heavy(const float4* __restrict__ A, const float4* __restrict__ B, uint32_t xmask, uint32_t cmask,
+                                                    const int cnt, float2* __restrict__ slab, const int sstride, const unsigned hm) {
+    bool tie = false;
+    int n = 0;
+    float sx = 0.f, sy = 0.f;
+    // crossing points, ascending bit order == the reference's append order (i outer, j inner)
+    while (xmask) {
+        const int e = __ffs(xmask) - 1;
+        xmask &= xmask - 1;
+        const float2 v = crossing_point<FL, STAGE>(A, B, e >> 2, e & 3, slab, sstride);
+        slab[n * sstride] = v;
+        sx += v.x;
+        sy += v.y;
+        n++;
+    }
+    __syncwarp(hm);
+    // flagged corners (reference order: B corner k, then A corner k)
+    while (cmask) {
+        const int e = __ffs(cmask) - 1;
+        cmask &= cmask - 1;
+        float2 c;
+        if ((e & 1) || !STAGE) {
+            const float4 a = (e & 1) ? A[e >> 1] : B[e >> 1];
+            c = make_float2(a.x, a.y);
+        } else {
+            c = slab[(SLAB_BCORNER + (e >> 1)) * sstride];
+        }
+        slab[n * sstride] = c;
+        sx += c.x;
+        sy += c.y;
+        n++;
+    }
+    __syncwarp(hm);
+    const float inv = __fdividef(1.0f, (float)cnt);
+    const float mx = sx * inv, my = sy * inv;  // centroid: only orders the vertices
+    uint32_t key[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        key[k] = 0xFFFFFFF0u | k;
+        if (k < cnt) {
+            const float2 p = slab[k * sstride];
+            key[k] = angle_key(p.x, p.y, mx, my, k);
+        }
+    }
+    sort8(key);
+    // near-tie of two polar angles (coincident or radially aligned vertices): the reference's order then
+    // depends on atan2f's rounding -> hand the pair to the literal path.  64 key units = 1.9e-6 of the
+    // pseudo-angle, ~10x the rounding noise of either angle function.
+    uint32_t gap = 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+        if (k + 1 < cnt) gap = min(gap, (key[k + 1] >> 4) - (key[k] >> 4));  // padding keys sort last
+    tie = gap <= LG_TIE_UNITS;
+    // fan area from the first vertex in angular order (kernel.cu:219-224); term 0 is cross(0, u) == +-0
+    const float2 p0 = slab[(key[0] & 15) * sstride];
+    const float2 p1 = slab[(key[1] & 15) * sstride];
+    float ux = p1.x - p0.x, uy = p1.y - p0.y;
+    float area = 0.f;
+#pragma unroll
+    for (int k = 2; k < 8; k++) {
+        if (k < cnt) {
+            const float2 pn = slab[(key[k] & 15) * sstride];
+            const float vx = pn.x - p0.x, vy = pn.y - p0.y;
+            area = __fadd_rn(area, msub<FL>(ux, vy, uy, vx));
+            ux = vx;
+            uy = vy;
+        }
+    }
+    return tie ? -1.f : __fmul_rn(fabsf(area), 0.5f);
+}
+
 // ---- the pair, fast path (<= 8 polygon vertices) -------------------------------------------------
 // slab: this thread's vertex column, entry k at slab[k * sstride], 8 entries.
 // wmask: the lanes of this warp that call the function together (a __ballot_sync taken where the warp was
@@ -366,75 +440,7 @@ __device__ __forceinline__ float overlap_area(const float4* __restrict__ A, cons
     if (cnt > 8) res = -1.f;  // deferred
     const bool heavy = cnt > 2 && cnt <= 8;
     const unsigned hm = __ballot_sync(wmask, heavy);
-    bool tie = false;
-    if (heavy) {
-        int n = 0;
-        float sx = 0.f, sy = 0.f;
-        // crossing points, ascending bit order == the reference's append order (i outer, j inner)
-        while (xmask) {
-            const int e = __ffs(xmask) - 1;
-            xmask &= xmask - 1;
-            const float2 v = crossing_point<FL, STAGE>(A, B, e >> 2, e & 3, slab, sstride);
-            slab[n * sstride] = v;
-            sx += v.x;
-            sy += v.y;
-            n++;
-        }
-        __syncwarp(hm);
-        // flagged corners (reference order: B corner k, then A corner k)
-        while (cmask) {
-            const int e = __ffs(cmask) - 1;
-            cmask &= cmask - 1;
-            float2 c;
-            if ((e & 1) || !STAGE) {
-                const float4 a = (e & 1) ? A[e >> 1] : B[e >> 1];
-                c = make_float2(a.x, a.y);
-            } else {
-                c = slab[(SLAB_BCORNER + (e >> 1)) * sstride];
-            }
-            slab[n * sstride] = c;
-            sx += c.x;
-            sy += c.y;
-            n++;
-        }
-        __syncwarp(hm);
-        const float inv = __fdividef(1.0f, (float)cnt);
-        const float mx = sx * inv, my = sy * inv;  // centroid: only orders the vertices
-        uint32_t key[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            key[k] = 0xFFFFFFF0u | k;
-            if (k < cnt) {
-                const float2 p = slab[k * sstride];
-                key[k] = angle_key(p.x, p.y, mx, my, k);
-            }
-        }
-        sort8(key);
-        // near-tie of two polar angles (coincident or radially aligned vertices): the reference's order then
-        // depends on atan2f's rounding -> hand the pair to the literal path.  64 key units = 1.9e-6 of the
-        // pseudo-angle, ~10x the rounding noise of either angle function.
-        uint32_t gap = 0xFFFFFFFFu;
-#pragma unroll
-        for (int k = 0; k < 7; k++)
-            if (k + 1 < cnt) gap = min(gap, (key[k + 1] >> 4) - (key[k] >> 4));  // padding keys sort last
-        tie = gap <= LG_TIE_UNITS;
-        // fan area from the first vertex in angular order (kernel.cu:219-224); term 0 is cross(0, u) == +-0
-        const float2 p0 = slab[(key[0] & 15) * sstride];
-        const float2 p1 = slab[(key[1] & 15) * sstride];
-        float ux = p1.x - p0.x, uy = p1.y - p0.y;
-        float area = 0.f;
-#pragma unroll
-        for (int k = 2; k < 8; k++) {
-            if (k < cnt) {
-                const float2 pn = slab[(key[k] & 15) * sstride];
-                const float vx = pn.x - p0.x, vy = pn.y - p0.y;
-                area = __fadd_rn(area, msub<FL>(ux, vy, uy, vx));
-                ux = vx;
-                uy = vy;
-            }
-        }
-        res = tie ? -1.f : __fmul_rn(fabsf(area), 0.5f);
-    }
+    if (heavy) res = overlap_area_heavy<FL, STAGE>(A, B, xmask, cmask, cnt, slab, sstride, hm);
     __syncwarp(wmask);
     return res;
 }

@@ -103,14 +103,12 @@ __device__ __forceinline__ unsigned long long max_key(float v, unsigned idx) {
 #define LG_SK_SPARSE_MINB 2
 #endif
 template <int FL, bool REDUCE, bool DENSE>
-__global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_SPARSE_MINB)
-    iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
-                     const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
-                     const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,
-                     unsigned long long* __restrict__ colkey, const int* __restrict__ dense_flag, const int* __restrict__ cta_only) {
+__device__ __forceinline__ void strip_body(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
+                                           const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
+                                           const int mode, const int cols_per_cta, const int64_t strips_m,
+                                           unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
+                                           const int64_t strip) {
     constexpr int NT = ST_THREADS;
-    if (dense_flag && (*dense_flag != 0) != DENSE) return;
-    if (cta_only && cta_only[blockIdx.x] == 0) return;  // two-phase path: only the strips whose survivors did not fit the list
     extern __shared__ float4 smem4[];
     float4* sA = smem4;
     float4* sDup = sA + SK_ROWS * REC_F4;  // per row: (cx, cx, cy, cy), (rad, rad, -, -)
@@ -118,7 +116,6 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_S
     uint32_t* lists = reinterpret_cast<uint32_t*>(slab + SLAB_ROWS * NT);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t strip = blockIdx.x;
     const int64_t sn = strip / strips_m, sm = strip - sn * strips_m;
     const int64_t row0 = sn * SK_ROWS, col0 = sm * cols_per_cta;
     const int na = (int)min((int64_t)SK_ROWS, n - row0), nb = (int)min((int64_t)cols_per_cta, m - col0);
@@ -323,6 +320,27 @@ __global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_S
     if (q.rcount > 0) warp_drain_rare<FL, SK_SHIFT>(q, sA, gB, slab_warp, NT, lane, emit);
 }
 
+// cta_only == nullptr: one strip per CTA.  Otherwise (the two-phase path's complete sweep): a small persistent grid walks the
+// strips and redoes only those whose flag is raised -- normally none, so the launch must cost next to nothing.
+template <int FL, bool REDUCE, bool DENSE>
+__global__ void __launch_bounds__(ST_THREADS, DENSE ? LG_SK_DENSE_MINB : LG_SK_SPARSE_MINB)
+    iou_strip_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ rec_b,
+                     const float4* __restrict__ cull_b, const int64_t m, float* __restrict__ out, const int64_t ld,
+                     const int mode, const int cols_per_cta, const int64_t strips_m, unsigned long long* __restrict__ rowkey,
+                     unsigned long long* __restrict__ colkey, const int* __restrict__ dense_flag, const int* __restrict__ cta_only,
+                     const int64_t total_strips) {
+    if (dense_flag && (*dense_flag != 0) != DENSE) return;
+    if (!cta_only) {
+        strip_body<FL, REDUCE, DENSE>(rec_a, n, rec_b, cull_b, m, out, ld, mode, cols_per_cta, strips_m, rowkey, colkey, blockIdx.x);
+        return;
+    }
+    for (int64_t s = blockIdx.x; s < total_strips; s += gridDim.x) {
+        if (cta_only[s] == 0) continue;  // CTA-uniform
+        strip_body<FL, REDUCE, DENSE>(rec_a, n, rec_b, cull_b, m, out, ld, mode, cols_per_cta, strips_m, rowkey, colkey, s);
+        __syncthreads();  // the next strip re-uses the shared memory
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Two-phase form of the sparse sweep (large matrices): the matrix is a stream of zeros with a few survivors, so the sweep
 // and the polygon path are separate kernels with the resources each needs.
@@ -467,7 +485,11 @@ __global__ void __launch_bounds__(ST_THREADS)
     if (count > 0) flush();
 }
 
-// The polygon path on the survivor list: a grid-stride loop, 32 consecutive entries per warp and trip.
+// The polygon path on the survivor list: a grid-stride loop, 32 consecutive entries per warp and trip, in two stages.  Most
+// survivors of the circle test are near misses whose polygon is empty: stage 1 (phase A: the 16 straddle + 8 margin tests) settles
+// them.  The few pairs that do overlap (3..8 vertices) are queued -- pair + masks, 16 bytes -- and stage 2 (crossing points, order,
+// fan) runs whenever the warp's queue holds 32 of them, so the divergent code sees full warps instead of the one or two overlapping
+// pairs of a trip.
 template <int FL, bool REDUCE>
 __global__ void __launch_bounds__(ST_THREADS, 3)
     iou_pairs_kernel(const float4* __restrict__ rec_a, const float4* __restrict__ rec_b, const unsigned long long* __restrict__ list,
@@ -475,14 +497,17 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
                      const int mode, unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
                      const int* __restrict__ dense_flag) {
     if (dense_flag && *dense_flag != 0) return;
-    constexpr int NT = ST_THREADS, NW = NT / 32, RARE = 64;
-    __shared__ float2 slab[SLAB_ROWS * NT];
+    constexpr int NT = ST_THREADS, NW = NT / 32, RARE = 64, HEAVY = 64;
+    __shared__ float2 slab[SLAB_ROWS_SMEM_B * NT];
     __shared__ unsigned long long rare[NW * RARE];
+    __shared__ ulonglong2 heavyq[NW * HEAVY];  // (pair, xmask | cmask << 16)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long total = min(ctrl->count, cap);
     float2* const slab_warp = slab + warp * 32;
     unsigned long long* const wr = rare + warp * RARE;
-    int rcount = 0;  // warp-uniform
+    ulonglong2* const wh = heavyq + warp * HEAVY;
+    int rcount = 0, hcount = 0;  // warp-uniform
+    const unsigned lt = (1u << lane) - 1u;
     auto emit = [&](const unsigned long long e, const float ov, const float4* A, const float4* B) {
         const float v = finish_pair(mode, ov, A, B);
         const unsigned r = (unsigned)(e >> 32), c = (unsigned)e;
@@ -513,45 +538,102 @@ __global__ void __launch_bounds__(ST_THREADS, 3)
         rcount = 0;
         __syncwarp();
     };
-    const unsigned long long stride = (unsigned long long)gridDim.x * NW * 32;
-    for (unsigned long long base = ((unsigned long long)blockIdx.x * NW + warp) * 32; base < total; base += stride) {
-        const unsigned long long idx = base + lane;
-        unsigned long long e = SW_HOLE;
-        if (idx < total) e = __ldg(list + idx);
-        const bool act = e != SW_HOLE;
-        const unsigned wm = __ballot_sync(0xffffffffu, act);
-        bool defer = false;
-        if (act) {
-            const float4* A = rec_a + (int64_t)(e >> 32) * REC_F4;
-            const float4* B = rec_b + (int64_t)(e & 0xFFFFFFFFull) * REC_F4;
-            const float ov = overlap_area<FL, true>(A, B, slab_warp + lane, NT, wm);
-            if (ov < 0.f) defer = true;
-            else emit(e, ov, A, B);
-        }
+    auto defer_rare = [&](const bool defer, const unsigned long long e) {  // all lanes
         const unsigned dm = __ballot_sync(0xffffffffu, defer);
         if (dm) {
-            if (defer) wr[rcount + __popc(dm & ((1u << lane) - 1u))] = e;
+            if (defer) wr[rcount + __popc(dm & lt)] = e;
             rcount += __popc(dm);
             if (rcount > RARE - 32) drain_rare_list();
         }
+    };
+    // stage 2 on the top n (<= 32) entries of the warp's queue
+    auto heavy_round = [&](const int n) {
         __syncwarp();
+        const bool act = lane < n;
+        const unsigned hm = __ballot_sync(0xffffffffu, act);
+        bool defer = false;
+        unsigned long long e = 0ull;
+        if (act) {
+            const ulonglong2 h = wh[hcount - n + lane];
+            e = h.x;
+            const uint32_t xm = (uint32_t)h.y & 0xFFFFu, cm = ((uint32_t)h.y >> 16) & 0xFFu;
+            const float4* A = rec_a + (int64_t)(e >> 32) * REC_F4;
+            const float4* B = rec_b + (int64_t)(e & 0xFFFFFFFFull) * REC_F4;
+            const float ov = overlap_area_heavy<FL, false>(A, B, xm, cm, __popc(xm) + __popc(cm), slab_warp + lane, NT, hm);
+            if (ov < 0.f) defer = true;  // angular near-tie
+            else emit(e, ov, A, B);
+        }
+        hcount -= n;
+        defer_rare(defer, e);
+        __syncwarp();
+    };
+    const unsigned long long stride = (unsigned long long)gridDim.x * NW * 32;
+    // the kernel is bound by the latency of its gathers (list entry -> two 112-byte records somewhere in the L2): the entry of the
+    // NEXT trip is loaded one trip ahead and its records are requested into the L1 while this trip's pairs are worked on
+    auto fetch = [&](const unsigned long long idx) -> unsigned long long {
+        unsigned long long e = SW_HOLE;
+        if (idx < total) e = __ldg(list + idx);
+        if (e != SW_HOLE) {
+            const char* pa = reinterpret_cast<const char*>(rec_a + (int64_t)(e >> 32) * REC_F4);
+            const char* pb = reinterpret_cast<const char*>(rec_b + (int64_t)(e & 0xFFFFFFFFull) * REC_F4);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + 96));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pb));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + 96));
+        }
+        return e;
+    };
+    const unsigned long long base0 = ((unsigned long long)blockIdx.x * NW + warp) * 32;
+    unsigned long long e_next = fetch(base0 + lane);
+    for (unsigned long long base = base0; base < total; base += stride) {
+        const unsigned long long e = e_next;
+        e_next = fetch(base + stride + lane);
+        const bool act = e != SW_HOLE;
+        bool defer = false, heavy = false;
+        uint32_t xm = 0u, cm = 0u;
+        if (act) {
+            const float4* A = rec_a + (int64_t)(e >> 32) * REC_F4;
+            const float4* B = rec_b + (int64_t)(e & 0xFFFFFFFFull) * REC_F4;
+            pair_masks<FL, false>(A, B, xm, cm);
+            const int cnt = __popc(xm) + __popc(cm);
+            if (cnt <= 2) emit(e, 0.f, A, B);  // the fan sum is empty or a single zero term
+            else if (cnt > 8) defer = true;
+            else heavy = true;
+        }
+        const unsigned hv = __ballot_sync(0xffffffffu, heavy);
+        if (hv) {
+            if (heavy) wh[hcount + __popc(hv & lt)] = make_ulonglong2(e, (unsigned long long)(xm | (cm << 16)));
+            hcount += __popc(hv);
+        }
+        defer_rare(defer, e);
+        if (hcount >= 32) heavy_round(32);
     }
+    if (hcount > 0) heavy_round(hcount);
     if (rcount > 0) drain_rare_list();
 }
 
 // Survivor density of the exact-zero cull, estimated from 8192 pseudo-random pairs: flag = 1 when more than ~6 % survive.
-__global__ void __launch_bounds__(256) density_probe_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ cull_b,
-                                                             const int64_t m, int* __restrict__ flag) {
+__global__ void __launch_bounds__(1024) density_probe_kernel(const float4* __restrict__ rec_a, const int64_t n, const float4* __restrict__ cull_b,
+                                                              const int64_t m, int* __restrict__ flag) {
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
-    int mine = 0;
-    for (int s = threadIdx.x; s < 8192; s += 256) {
+    // 8 samples per thread, all 16 loads in flight at once (the probe is a chain of cache misses, nothing else)
+    float4 qa[8], qb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const int s = threadIdx.x + 1024 * u;
         const unsigned long long h = (unsigned long long)(s + 1) * 0x9E3779B97F4A7C15ull;
         const int64_t i = (int64_t)((h >> 33) % (unsigned long long)n), j = (int64_t)(((h * 0xD1B54A32D192ED03ull) >> 33) % (unsigned long long)m);
-        mine += cull_survives(__ldg(rec_a + i * REC_F4 + REC_CULL), __ldg(cull_b + j)) ? 1 : 0;
+        qa[u] = __ldg(rec_a + i * REC_F4 + REC_CULL);
+        qb[u] = __ldg(cull_b + j);
     }
-    atomicAdd(&cnt, mine);
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) mine += cull_survives(qa[u], qb[u]) ? 1 : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&cnt, mine);
     __syncthreads();
     if (threadIdx.x == 0) *flag = cnt > 512 ? 1 : 0;
 }
@@ -675,9 +757,9 @@ static SweepPlan sweep_plan(int64_t n, int64_t m, unsigned flags) {
     p.cols = cols;
     p.strips_m = (m + cols - 1) / cols;
     p.strips = strips_n * p.strips_m;
-    // two-phase from 2^24 pairs on (below that the extra launches cost more than the sweep); indices are packed in 32 bits
+    // two-phase from 2^26 pairs on (below that the extra launches cost more than the sweep saves: measured, tools/time_two_phase.py); indices are packed in 32 bits
     const double pairs = (double)n * (double)m;
-    p.two_phase = m > FLAT_COLS && pairs >= 16777216.0 && n < 0xFFFFFFFFLL && m < 0xFFFFFFFFLL && p.strips <= 0x7fffffffLL;
+    p.two_phase = !(flags & LG_FLAG_IOU_ONE_KERNEL) && m > FLAT_COLS && pairs >= 67108864.0 && n < 0xFFFFFFFFLL && m < 0xFFFFFFFFLL && p.strips <= 0x7fffffffLL;
     if (p.two_phase) {
         double cap = pairs / 32.0;  // ~3 % survivors; the usual matrix has < 1 %
         if (cap < 65536.0) cap = 65536.0;
@@ -740,7 +822,7 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         return LG_ERR_TOO_LARGE;
     }
     int* flag = reinterpret_cast<int*>(cb + m);
-    density_probe_kernel<<<1, 256, 0, st>>>(ra, n, cb, m, flag);
+    density_probe_kernel<<<1, 1024, 0, st>>>(ra, n, cb, m, flag);
     if ((rc = check_launch("density_probe_kernel"))) return rc;
     auto ks = iou_strip_kernel<FL, false, false>;
     auto kd = iou_strip_kernel<FL, false, true>;
@@ -765,8 +847,9 @@ static int run_iou(const float* a, int64_t n, const float* b, int64_t m, float* 
         if ((rc = check_launch("iou_pairs_kernel"))) return rc;
         only = over;
     }
-    ks<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag, only);
-    kd<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag, nullptr);
+    const unsigned gs = only ? (unsigned)min(strips, (int64_t)pairs_grid()) : (unsigned)strips;  // persistent when it only mops up
+    ks<<<gs, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag, only, strips);
+    kd<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, out, ld, mode, (int)cols, strips_m, nullptr, nullptr, flag, nullptr, strips);
     return check_launch("iou_strip_kernel");
 }
 
@@ -825,7 +908,8 @@ static int run_iou_reduce(const float* a, int64_t n, const float* b, int64_t m, 
         if ((rc = check_launch("iou_pairs_kernel<reduce>"))) return rc;
         only = over;
     }
-    kern<<<(unsigned)strips, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey, nullptr, only);
+    const unsigned gs = only ? (unsigned)min(strips, (int64_t)pairs_grid()) : (unsigned)strips;
+    kern<<<gs, ST_THREADS, StripSmem::total, st>>>(ra, n, rb, cb, m, nullptr, 0, mode, (int)cols, strips_m, rowkey, colkey, nullptr, only, strips);
     if ((rc = check_launch("iou_strip_kernel<reduce>"))) return rc;
     if (want_rows) key_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowkey, n, row_max, row_arg);
     if (want_cols) key_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(colkey, m, col_max, col_arg);

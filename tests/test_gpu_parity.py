@@ -633,37 +633,37 @@ def test_iou_row_col_max_equals_torch_max_of_the_matrix(kind, fn, n, m, sparse):
 
 
 def test_two_phase_sweep_and_its_overflow_path_equal_the_one_kernel_sweep():
-    """From 2^24 pairs on the matrix is swept in two phases (zeros + survivor list, then the polygon path on the list).  The same
-    matrix must come out (a) of the one-kernel sweep -- row blocks below the threshold -- and (b) when the list is far too small
+    """From 2^26 pairs on the matrix is swept in two phases (zeros + survivor list, then the polygon path on the list).  The same
+    matrix must come out (a) of the one-kernel sweep (LG_FLAG_IOU_ONE_KERNEL) and (b) when the list is far too small
     (LG_FLAG_IOU_SMALL_LIST: 1024 entries), where the flagged strips are redone by the one-kernel sweep; likewise the reductions."""
-    a, b = synth.cfg4(n=6000, seed=11)  # 3.6e7 pairs, a few 1e4 survivors
+    a, b = synth.cfg4(n=9000, seed=11)  # 8.1e7 pairs, some 1e5 survivors
     ta, tb = cu(a), cu(b)
+    ONE, SMALL = _lib.LG_FLAG_IOU_ONE_KERNEL, _lib.LG_FLAG_IOU_SMALL_LIST
     for fn in ("lg_boxes_iou3d", "lg_boxes_iou_bev", "lg_boxes_overlap_bev"):
         two = U._iou_call(fn, ta, tb)
-        assert int((two > 0).sum()) > 4096  # more survivors than the small list holds
-        one = torch.cat([U._iou_call(fn, ta[i:i + 2000], tb) for i in (0, 2000, 4000)], 0)  # 1.2e7 pairs per call: one kernel
+        assert int((two > 0).sum()) > 4096  # more overlapping pairs than the small list holds
+        one = U._iou_call(fn, ta, tb, flags=ONE)
         assert torch.equal(two, one), fn
-        small = U._iou_call(fn, ta, tb, flags=_lib.LG_FLAG_IOU_SMALL_LIST)
+        small = U._iou_call(fn, ta, tb, flags=SMALL)
         assert torch.equal(small, one), fn
     # ragged shapes: partial row strips, partial column tiles, a pitch that rules out the 16-byte stores
-    n, m = 5003, 4099
+    n, m = 8999, 8195
     wide = torch.full((n, m + 3), -7.0, dtype=torch.float32, device=ta.device)
     got = U._iou_call("lg_boxes_iou3d", ta[:n], tb[:m], out=wide[:, :m])
-    want = torch.cat([U._iou_call("lg_boxes_iou3d", ta[i:min(i + 2000, n)], tb[:m]) for i in (0, 2000, 4000)], 0)
+    want = U._iou_call("lg_boxes_iou3d", ta[:n], tb[:m], flags=ONE)
     assert torch.equal(got, want) and bool((wide[:, m:] == -7.0).all())
     # the reductions over the same pairs
-    w = U._iou_call("lg_boxes_iou3d", ta, tb)
-    for flags in (_lib.LG_FLAG_NONE, _lib.LG_FLAG_IOU_SMALL_LIST):
+    w = U._iou_call("lg_boxes_iou3d", ta, tb, flags=ONE)
+    for flags in (_lib.LG_FLAG_NONE, SMALL, ONE):
         rmax, rarg, cmax, carg = U.boxes_iou_max(ta, tb, kind="iou3d", rows=True, cols=True, flags=flags)
         assert torch.equal(rmax, w.max(1).values) and torch.equal(cmax, w.max(0).values)
         assert torch.equal(rarg, (w == w.max(1).values.unsqueeze(1)).int().argmax(1))
         assert torch.equal(carg, (w == w.max(0).values.unsqueeze(0)).int().argmax(0))
     # a dense matrix above the threshold: the density probe routes it to the dense build, the two-phase kernels stand down
-    da, db = synth.clustered_pairs(4200, 4200, seed=5)
+    da, db = synth.clustered_pairs(8200, 8200, seed=5)
     tda, tdb = cu(da), cu(db)
     dense = U._iou_call("lg_boxes_iou_bev", tda, tdb)
-    parts = torch.cat([U._iou_call("lg_boxes_iou_bev", tda[i:i + 1400], tdb) for i in (0, 1400, 2800)], 0)
-    assert torch.equal(dense, parts)
+    assert torch.equal(dense, U._iou_call("lg_boxes_iou_bev", tda, tdb, flags=ONE))
     rmax, rarg = U.boxes_iou_max(tda, tdb, kind="iou_bev")  # no probe on this path: the list overflows, every strip falls back
     assert torch.equal(rmax, dense.max(1).values)
 

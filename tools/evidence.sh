@@ -29,11 +29,11 @@ if timeout 200 python bench.py --steps 2 --warmup 1 --no-secondary --no-cpu-base
 fi
 fi
 if [ "$WHAT" != run ]; then
-for tk in nms64:nms_lazy_kernel nms_cfg5:nms_lazy_kernel nms_full:nms_mask_kernel iou_dense16k:iou_strip_kernel:2 iou_cfg4:iou_strip_kernel:2 iou_cfg1:iou_flat_kernel pib4096:pib_grid_kernel kitti:kitti_pair_kernel roiaware:roiaware_collect_pool_kernel roipoint:roipoint_pool_kernel; do
-    IFS=: read -r t k c <<< "$tk"; c=${c:-1}   # target : kernel regex : launches to capture (the strip kernel is launched in two builds)
-    if timeout 120 python tools/prof_target.py $t 3 > $O/plain_$t.log 2>&1; then
-        timeout 500 ncu --set full --clock-control none --import-source on -k regex:$k -c $c -f -o $O/final_$t \
-            python tools/prof_target.py $t 2 > $O/ncu_$t.log 2>&1; echo "ncu $t rc=$?"
+for tk in nms64:nms_lazy_kernel nms_cfg5:nms_lazy_kernel nms_full:nms_mask_kernel iou_dense16k:iou_strip_kernel:2 iou_cfg4:iou_sweep_kernel:1 iou_cfg4:iou_pairs_kernel:1:iou_cfg4_pairs iou_cfg1:iou_flat_kernel pib4096:pib_grid_kernel kitti:kitti_pair_kernel roiaware:roiaware_collect_pool_kernel roipoint:roipoint_pool_kernel; do
+    IFS=: read -r t k c nm <<< "$tk"; c=${c:-1}; nm=${nm:-$t}   # target : kernel regex : launches to capture (the strip kernel is launched in two builds) : report name
+    if timeout 120 python tools/prof_target.py $t 3 > $O/plain_$nm.log 2>&1; then
+        timeout 500 ncu --set full --clock-control none --import-source on -k regex:$k -c $c -f -o $O/final_$nm \
+            python tools/prof_target.py $t 2 > $O/ncu_$nm.log 2>&1; echo "ncu $nm rc=$?"
     else
         echo "plain $t failed"
     fi
