@@ -19,9 +19,11 @@
 //                  survivor density (0.3 % for anchors x GT, 100 % for the dense microbench); column
 //                  records are read through L1/L2 (they are 112 B x M, L2 resident); results are stored directly.
 //      DRAM traffic == algorithmic bytes 4*N*M + 28*(N+M) (+ the 128*(N+M)-byte record round trip).
-//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.  63 KB smem and <= 80 registers
-//      per thread keep 3 CTAs (24 warps) resident per SM.
-//   3. 64-bit output offsets (the reference's int32 index overflows at 2^31 pairs).
+//      Sparse workloads are HBM-write bound, dense ones FP32-issue bound.  52 KB smem and <= 80 registers
+//      per thread keep 3 CTAs (24 warps) of the dense build resident per SM.
+//   3. large sparse matrices (>= 2^26 pairs): a two-phase sweep -- iou_sweep_kernel (cull, zero stores, survivor list) at the speed
+//      of the store stream, then iou_pairs_kernel (the polygon path on the list); see the comment above iou_sweep_kernel.
+//   4. 64-bit output offsets (the reference's int32 index overflows at 2^31 pairs).
 #include "lg_common.cuh"
 #include "lg_strip.cuh"
 
