@@ -291,7 +291,7 @@ constexpr int LZ_GH = 16;        // candidates per warp in a sweep: the warps fo
 constexpr int LZ_WIN = 4 * LZ_GI; // window: the first alive boxes among which the candidates are chosen
 constexpr int LZ_CACHE = 4096;   // cull quads cached in smem; boxes beyond read theirs from the records (L2)
 constexpr int LZ_MAX_CLUSTER = 8;     // portable cluster size limit
-constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 1024;  // opt-in dynamic shared memory per CTA on sm_100a, minus the static part
+constexpr size_t LZ_SMEM_LIMIT = 227 * 1024 - 2048;  // opt-in shared memory per CTA on sm_100a (227 KB), minus the kernel's static part (1.6 KB)
 
 struct LazyLayout {
     int words, sstride;  // alive words; pitch of a suppression row (odd: the resolve reads a column of the rows conflict-free)
@@ -382,6 +382,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     uint32_t* sup = reinterpret_cast<uint32_t*>(sm + L.off_sup);
     const int SW = L.sstride, QCAP = L.qcap, RARECAP = L.rarecap;
     __shared__ int qcount, rcount, group[LZ_GI], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s, nwin_s, nalive_s, cursor_s, spec_s;
+    // the candidates' cull quads once more, two candidates side by side: (x0, x1, y0, y1) and (r0, r1) -- the operand pairs of the
+    // packed FP32 instructions of the sweeps
+    __shared__ float4 sc2xy[LZ_GI / 2];
+    __shared__ float2 sc2r[LZ_GI / 2];
     __shared__ unsigned long long st_heavy;
 
     // A problem may be spread over a thread-block cluster of C CTAs (C SMs): they keep identical copies of the alive bitmap
@@ -639,7 +643,11 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         for (int e = tid; e < ng * REC_F4; e += NT) sA[e] = __ldcg(grec + (int64_t)group[e / REC_F4] * REC_F4 + (e % REC_F4));
         if (tid < ng) {
             const int j = group[tid];
-            scand[tid] = quad(j);
+            const float4 qj = quad(j);
+            scand[tid] = qj;
+            reinterpret_cast<float*>(&sc2xy[tid >> 1])[tid & 1] = qj.x;
+            reinterpret_cast<float*>(&sc2xy[tid >> 1])[2 + (tid & 1)] = qj.y;
+            reinterpret_cast<float*>(&sc2r[tid >> 1])[tid & 1] = qj.z;
             // the candidates are decided in this pass: they leave the alive bitmap now (every CTA of a cluster clears its own
             // copy), so the column sweeps below never see them -- candidate-vs-candidate pairs are queued separately
             atomicAnd(&alive[j >> 5], ~(1u << (j & 31)));
@@ -689,10 +697,24 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                     const float4 cj = a ? quad(j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     unsigned mk[GH];
                     if (__all_sync(FULL, !a || j > ghi)) {  // the usual case: every column lies after all of this group's candidates
+                        // two candidates per packed instruction (FADD2 / FMUL2 / FFMA2); the circle test is conservative, so how its
+                        // products are contracted does not matter
+                        const f32x2 bx = pack2(cj.x, cj.x), by = pack2(cj.y, cj.y), br = pack2(cj.z, cj.z);
 #pragma unroll
-                        for (int k = 0; k < GH; k++) {
+                        for (int k = 0; k < GH; k += 2) {
                             mk[k] = 0u;
-                            if (k < kmax) mk[k] = __ballot_sync(FULL, a && cull_survives(scand[GH * half + k], cj));  // warp-uniform guard
+                            mk[k + 1] = 0u;
+                            if (k < kmax) {  // warp-uniform guard
+                                const ulonglong2 axy = *reinterpret_cast<const ulonglong2*>(&sc2xy[(GH * half + k) >> 1]);
+                                const f32x2 ar = *reinterpret_cast<const f32x2*>(&sc2r[(GH * half + k) >> 1]);
+                                const f32x2 dx = sub2(axy.x, bx), dy = sub2(axy.y, by), rr = add2(ar, br);
+                                const f32x2 d2 = fma2(dx, dx, mul2(dy, dy)), r2 = mul2(rr, rr);
+                                float d0, d1, r0, r1;
+                                unpack2(d2, d0, d1);
+                                unpack2(r2, r0, r1);
+                                mk[k] = __ballot_sync(FULL, a && !(d0 > r0));  // NaN => keep: the polygon path decides
+                                if (k + 1 < kmax) mk[k + 1] = __ballot_sync(FULL, a && !(d1 > r1));
+                            }
                         }
                         my_tested += a ? (unsigned)kmax : 0u;
                     } else {  // window boxes that are not candidates sit between the candidates: only the earlier candidates test them
