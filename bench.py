@@ -43,12 +43,13 @@ L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
 
 
 def l2_flush(flush):
-    """Evict the L2 between timed iterations (outside the CUDA events).  Three passes over the 256 MB buffer: one evicts the cache; the
-    other two keep the GPU busy for ~0.1 ms, so that Python has queued the step's launches by the time the start event fires and
-    the events time the GPU's work on the step, not the host's launch latency (which a busy host core would otherwise add)."""
-    flush.zero_()
-    flush.zero_()
-    flush.zero_()
+    """Evict the L2 between timed iterations (outside the CUDA events).  Six passes over the 256 MB buffer: one evicts the cache; the
+    others keep the GPU busy for ~0.25 ms, so that Python has queued the step's launches by the time the start event fires and
+    the events time the GPU's work on the step, not the host's launch latency (a busy host core -- the clock sampler's thread on
+    rank 0, a neighbour's process -- otherwise adds it: seen as 0.23 instead of 0.18 ms on a step of two launches, and as
+    0.22 instead of 0.19 ms on the multi-GPU step, whose Python side is longer)."""
+    for _ in range(6):
+        flush.zero_()
 
 
 def log(*a):

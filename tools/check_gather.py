@@ -39,7 +39,18 @@ for it in range(5):  # buffer reuse
     ok = ok and torch.equal(k0, k2) and torch.equal(n0, n2)
 
 
+def local_only():
+    return sharded.nms_batched_sharded(tb, ts, 0.01, max_keep=500, local_inputs=True, gather=False)
+
+
 def timed(fused):
+    if fused is None:  # this rank's frames only, nothing gathered: what the gather costs is the difference
+        global run
+        run_saved, run = run, (lambda f: local_only())
+        try:
+            return timed(True)
+        finally:
+            run = run_saved
     for _ in range(5):
         run(fused)
     dist.barrier()
@@ -47,6 +58,8 @@ def timed(fused):
     ms = 0.0
     for _ in range(30):
         flush.zero_()
+        flush.zero_()
+        flush.zero_()  # (keeps the GPU busy while Python queues the step: the events time the device, not the launch latency)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         run(fused)
@@ -58,10 +71,10 @@ def timed(fused):
     return float(t[0])
 
 
-t_nccl, t_fused = timed(False), timed(True)
+t_nccl, t_fused, t_local = timed(False), timed(True), timed(None)
 okt = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(okt, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"world {world}: fused == nccl results: {bool(okt[0])};  ms/step (max over ranks, 64 frames x 4096 per rank): nccl all-gather {t_nccl:.4f}, fused peer-memory gather {t_fused:.4f}")
+    print(f"world {world}: fused == nccl results: {bool(okt[0])};  ms/step (max over ranks, 64 frames x 4096 per rank): nccl all-gather {t_nccl:.4f}, fused peer-memory gather {t_fused:.4f}, no gather {t_local:.4f}")
 dist.destroy_process_group()
 sys.exit(0 if bool(okt[0]) else 1)

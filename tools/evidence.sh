@@ -3,7 +3,7 @@
 # every bench workload + the reference arm, the ncu launch list of the default bench command, and one `ncu --set full`
 # report per dominant kernel (each only after the same command has exited 0 without ncu).  Everything lands in
 # gpurun_out/; tools/make_profiles.py turns the reports into profiles/rNN_*.txt afterwards.
-#   gpurun --timeout 1500 -- 'bash tools/evidence.sh [run|ncu|all]'
+#   gpurun --timeout 1500 -- 'bash tools/evidence.sh [run|ncu|all] [report names of the ncu part ...]'
 # gpurun brings back at most 64 MiB: every ncu capture is limited to its kernel (-k) and one launch (-c).
 set -u
 O=gpurun_out
@@ -30,7 +30,8 @@ fi
 fi
 if [ "$WHAT" != run ]; then
 for tk in nms64:nms_lazy_kernel nms_cfg5:nms_lazy_kernel nms_full:nms_mask_kernel iou_dense16k:iou_strip_kernel:2 iou_cfg4:iou_sweep_kernel:1 iou_cfg4:iou_pairs_kernel:1:iou_cfg4_pairs iou_cfg1:iou_flat_kernel pib4096:pib_grid_kernel kitti:kitti_pair_kernel roiaware:roiaware_collect_pool_kernel roipoint:roipoint_pool_kernel; do
-    IFS=: read -r t k c nm <<< "$tk"; c=${c:-1}; nm=${nm:-$t}   # target : kernel regex : launches to capture (the strip kernel is launched in two builds) : report name
+    IFS=: read -r t k c nm <<< "$tk"; c=${c:-1}; nm=${nm:-$t}
+    if [ $# -gt 1 ] && [[ " ${*:2} " != *" $nm "* ]]; then continue; fi   # `evidence.sh ncu name ...`: only these reports (64 MiB per call)   # target : kernel regex : launches to capture (the strip kernel is launched in two builds) : report name
     if timeout 120 python tools/prof_target.py $t 3 > $O/plain_$nm.log 2>&1; then
         timeout 500 ncu --set full --clock-control none --import-source on -k regex:$k -c $c -f -o $O/final_$nm \
             python tools/prof_target.py $t 2 > $O/ncu_$nm.log 2>&1; echo "ncu $nm rc=$?"
