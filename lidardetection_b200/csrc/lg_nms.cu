@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
     __shared__ int qcount, rcount, group[LZ_GI], ng_s, keptmask_s, nk_s, qvalid_s, sfail_s, nwin_s, nalive_s, cursor_s, spec_s;
     // the candidates' cull quads once more, two candidates side by side: (x0, x1, y0, y1) and (r0, r1) -- the operand pairs of the
     // packed FP32 instructions of the sweeps
+    __shared__ int wtot[NT / 32], full_s;  // the alive scan: totals of the warps' 32-word slices; NMS_POST_MAXSIZE reached
     __shared__ float4 sc2xy[LZ_GI / 2];
     __shared__ float2 sc2r[LZ_GI / 2];
     __shared__ unsigned long long st_heavy;
@@ -533,9 +534,10 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
         const bool spec = spec_s != 0;
         const int gmax = spec ? gcap : min(LZ_GI, 2 * gcap);  // candidates of this pass at most
         const int wincap = spec ? gcap : 4 * gmax;
-        // ---- (warp 0) alive boxes at and after the cursor: per-word offsets of the dense list, and the window
+        // ---- (all warps) alive boxes at and after the cursor: per-word offsets of the dense list, and the window.  Warp k takes the
+        // k-th 32 words of a round of NW x 32 (one round up to 16,384 boxes); the warps' totals meet in shared memory.  (One warp
+        // walking the bitmap 32 words at a time while fifteen waited cost 2 us of every 21-us pass.)
         if (warp == 0) {
-            int total = 0;
             // NMS_POST_MAXSIZE (model_nms_utils.py:20): the first max_keep kept boxes in score order are final once that many
             // are kept BELOW the cursor (independent candidates are kept out of order; everything below the cursor is decided)
             bool full = max_keep <= 0;
@@ -550,35 +552,46 @@ __global__ void __launch_bounds__(NT, NT == 512 ? 1 : 2)
                 for (int d = 16; d > 0; d >>= 1) kb += __shfl_xor_sync(FULL, kb, d);
                 full = kb >= max_keep;
             }
-            if (!full) {
-                for (int w0 = cursor >> 5; w0 < W; w0 += 32) {
-                    const int w = w0 + lane;
-                    unsigned word = w < W ? alive[w] : 0u;
-                    if (w == (cursor >> 5)) word &= FULL << (cursor & 31);
-                    const int c = __popc(word);
-                    int incl = c;
+            if (lane == 0) full_s = full ? 1 : 0;
+        }
+        int total = 0;  // the same in every thread
+        for (int g0 = cursor >> 5; g0 < W; g0 += NW * 32) {
+            const int w = g0 + warp * 32 + lane;
+            unsigned word = w < W ? alive[w] : 0u;
+            if (w == (cursor >> 5)) word &= FULL << (cursor & 31);
+            const int c = __popc(word);
+            int incl = c;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int v = __shfl_up_sync(FULL, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    int slot = total + incl - c;
-                    if (w < W) wprefix[w] = slot;
-                    while (word && slot < wincap) {  // the window: every lane lists the boxes of its own word (few, once the bitmap thins out)
-                        const int b = __ffs(word) - 1;
-                        word &= word - 1;
-                        window[slot++] = w * 32 + b;
-                    }
-                    total += __shfl_sync(FULL, incl, 31);
-                }
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
             }
-            if (lane == 0) {
-                nalive_s = total;
-                nwin_s = min(total, wincap);
-                qcount = 0;  // the queue of the previous pass is drained
-                qvalid_s = QCAP;
-                sfail_s = 0x7fffffff;
+            if (lane == 31) wtot[warp] = incl;
+            __syncthreads();
+            int ws = lane < NW ? wtot[lane] : 0;  // inclusive prefix of the warps' totals
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, ws, d);
+                if (lane >= d) ws += v;
             }
+            const int before = warp > 0 ? __shfl_sync(FULL, ws, warp - 1) : 0, round_total = __shfl_sync(FULL, ws, NW - 1);
+            int slot = total + before + incl - c;
+            if (w < W) wprefix[w] = slot;
+            while (word && slot < wincap) {  // the window: every lane lists the boxes of its own word (few, once the bitmap thins out)
+                const int b = __ffs(word) - 1;
+                word &= word - 1;
+                window[slot++] = w * 32 + b;
+            }
+            total += round_total;
+            if (g0 + NW * 32 < W) __syncthreads();  // wtot is written again in the next round
+        }
+        if (tid == 0) {
+            if (full_s) total = 0;  // (warp 0 wrote full_s before the round's barrier; a problem without a round has no boxes left)
+            nalive_s = total;
+            nwin_s = min(total, wincap);
+            qcount = 0;  // the queue of the previous pass is drained
+            qvalid_s = QCAP;
+            sfail_s = 0x7fffffff;
         }
         __syncthreads();
         LZ_MARK(0)  // alive scan
