@@ -63,7 +63,7 @@ extern "C" {
                                     it, instead of the default lazy evaluation of kept rows only; same keep list either way */
 
 /* limits */
-#define LG_NMS_MAX_BOXES 65536 /* per NMS problem */
+#define LG_NMS_MAX_BOXES 262144 /* per NMS problem (the mask + sweep formulation then needs nmax^2 / 8 bytes of workspace per problem) */
 #define LG_MAX_PEERS 8         /* ranks of one NVLink domain served by lg_nms_rotated_gather */
 #define LG_PIB_MAX_BOXES 2048  /* boxes per frame for lg_points_in_boxes (records are shared-memory resident);
                                   frames of up to 254 boxes take the grid-culled path, larger ones test every box */

@@ -11,7 +11,7 @@ LG_FLAG_NMS_FULL_MASK = 2
 LG_FLAG_NMS_NO_CLUSTER = 4
 LG_FLAG_IOU_SMALL_LIST = 8
 LG_FLAG_IOU_ONE_KERNEL = 16
-LG_NMS_MAX_BOXES = 65536
+LG_NMS_MAX_BOXES = 262144
 LG_PIB_MAX_BOXES = 2048
 
 _lib = None

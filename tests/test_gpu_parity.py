@@ -306,6 +306,18 @@ def test_host_nms_pipeline_equals_the_device_call_batch_by_batch():
         pipe.result(7)
 
 
+def test_nms_of_more_than_65536_boxes():
+    """no pre_maxsize, raw candidates: the reference takes any N (it allocates the N x N/64 mask); so does the mask + sweep
+    formulation here (rotated and axis-aligned), checked against the oracle's NMS"""
+    boxes, scores = synth.nms_frames(1, 70001, seed=77)
+    tb, ts = cu(boxes[0]), cu(scores[0])
+    order = ts.sort(dim=0, descending=True, stable=True)[1].cpu().numpy()
+    for fn, normal, thr in ((U.nms_gpu, False, 0.1), (U.nms_normal_gpu, True, 0.3)):
+        got = fn(tb, ts, thr)[0].cpu().numpy()
+        want = O.nms(boxes[0], scores[0], thr, normal=normal, order=order)
+        assert np.array_equal(got, want), (normal, len(got), len(want))
+
+
 def test_nms_threshold_edge_values():
     """thresh < 0: the exact-zero IoU of disjoint boxes exceeds it too (kernel.cu:304), so only the best box survives -- the
     kernels' exact-zero cull must not change that; thresh = NaN: nothing is suppressed; thresh >= 1: only IoUs above 1"""

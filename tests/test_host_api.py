@@ -61,7 +61,7 @@ def test_argument_validation_without_gpu():
     assert L.lg_boxes_iou_bev(None, 0, None, 7, None, 7, None, 0, 0, None) == 0
     assert L.lg_points_in_boxes(None, None, None, 0, 10, 100, None, 0, 0, None) == 0
     assert L.lg_points_in_boxes(dummy, dummy, dummy, 1, 5000, 100, None, 0, 0, None) == -3
-    assert L.lg_nms_rotated_batched(dummy, None, None, 1, 70000, 0.1, dummy, 1 << 30, dummy, dummy, 0, None) == -3
+    assert L.lg_nms_rotated_batched(dummy, None, None, 1, 300000, 0.1, dummy, 1 << 30, dummy, dummy, 0, None) == -3
     assert L.lg_nms_rotated_batched(dummy, None, None, 2, 128, 0.1, None, 0, dummy, dummy, 0, None) == -2
     assert L.lg_nms_normal_batched(dummy, None, None, -1, 128, 0.1, dummy, 1 << 20, dummy, dummy, 0, None) == -1
     assert L.lg_nms_rotated_batched(None, None, None, 0, 128, 0.1, None, 0, None, None, 0, None) == 0
