@@ -322,7 +322,7 @@ class HostNmsPipeline:
     """Serving loop for batches of frames that arrive in (pinned) host memory, one batch after the other
     (post-processing of a detector that runs elsewhere, or offline evaluation from saved predictions).
 
-    submit() queues  upload -> score sort -> rotated NMS -> download  of one batch on the pipeline's own streams and returns at
+    submit() queues  upload -> score sort -> rotated NMS -> download  of one batch on the pipeline's own three streams and returns at
     once; result(ticket) waits for that batch only.  `depth` batches are in flight, each with its own device and pinned result
     buffers: the boxes of batch k + 1 cross PCIe while batch k is in the kernels (on nms_cfg2 the upload, 8.4 MB, takes about as
     long as the kernels do).  Every batch is copied host -> device and its result device -> host; nothing is cached between
@@ -339,7 +339,7 @@ class HostNmsPipeline:
         self.dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.P, self.N, self.thresh, self.depth = int(num_problems), int(num_boxes), float(thresh), int(depth)
         self.K = self.N if max_keep is None else min(int(max_keep), self.N)
-        self.up, self.comp = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.up, self.comp, self.down = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
         self.slots = []
         for _ in range(self.depth):
             self.slots.append({
@@ -348,7 +348,7 @@ class HostNmsPipeline:
                 'keep': torch.empty((self.P, self.K), dtype=torch.int64, device=self.dev),
                 'h_keep': torch.empty((self.P, self.K), dtype=torch.int64).pin_memory(),
                 'h_num': torch.empty((self.P,), dtype=torch.int32).pin_memory(),
-                'ev_up': torch.cuda.Event(), 'ev_done': torch.cuda.Event(), 'ticket': -1, 'pending': False,
+                'ev_up': torch.cuda.Event(), 'ev_nms': torch.cuda.Event(), 'ev_done': torch.cuda.Event(), 'ticket': -1, 'pending': False,
             })
         self.next_ticket = 0
 
@@ -367,9 +367,13 @@ class HostNmsPipeline:
         with torch.cuda.stream(self.comp):
             self.comp.wait_event(s['ev_up'])
             keep, num = nms_gpu_batched(s['boxes'], s['scores'], self.thresh, max_keep=self.K, keep_out=s['keep'])
+            s['ev_nms'].record(self.comp)
+        with torch.cuda.stream(self.down):  # the download does not hold up the next batch's kernels
+            self.down.wait_event(s['ev_nms'])
             s['h_keep'].copy_(keep, non_blocking=True)
             s['h_num'].copy_(num, non_blocking=True)
-            s['ev_done'].record(self.comp)
+            num.record_stream(self.down)  # allocated on the compute stream, last read here
+            s['ev_done'].record(self.down)
         s['ticket'], s['pending'] = t, True
         self.next_ticket += 1
         return t
