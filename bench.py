@@ -436,6 +436,8 @@ class IouWorkload(Workload):
 
         n, m = self.a.shape[0], self.b.shape[0]
         flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        self.step()  # untimed: the caching allocator settles (the flush buffer above may have taken the block the workspace was using)
+        torch.cuda.synchronize()
         ts = []
         for _ in range(max(3, steps)):
             l2_flush(flush)
@@ -445,7 +447,7 @@ class IouWorkload(Workload):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        t = float(np.mean(ts)) * 1e-3
+        t = float(np.median(ts)) * 1e-3
         if self.which == "iou_dense":
             nz = float((self.out[:2048] > 0).float().mean())
             flops = self.pairs * (307.0 * (1 - nz) + 818.0 * nz)
@@ -510,6 +512,8 @@ class PibWorkload(Workload):
 
     def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
         torch = self.torch
+        self.step()  # untimed: the caching allocator settles (the flush buffer above may have taken the block the workspace was using)
+        torch.cuda.synchronize()
         ts = []
         for _ in range(max(3, steps)):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -518,7 +522,7 @@ class PibWorkload(Workload):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        t = float(np.mean(ts)) * 1e-3
+        t = float(np.median(ts)) * 1e-3
         byts = self.units * (12.0 * 16384 + 28.0 * 100 + 4.0 * 16384)
         ach = byts / t / 1e9
         return {"bound": "hbm", "kernel": "pib_grid_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
@@ -599,6 +603,8 @@ class RoiPoolWorkload(Workload):
 
     def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
         torch = self.torch
+        self.step()  # untimed: the caching allocator settles (the flush buffer above may have taken the block the workspace was using)
+        torch.cuda.synchronize()
         ts = []
         for _ in range(max(3, steps)):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -607,7 +613,7 @@ class RoiPoolWorkload(Workload):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        t = float(np.mean(ts)) * 1e-3
+        t = float(np.median(ts)) * 1e-3
         byts = self.units * self.bytes_per_frame
         ach = byts / t / 1e9
         return {"bound": "hbm", "kernel": self.kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
@@ -677,6 +683,8 @@ class KittiEvalWorkload(Workload):
     def roofline(self, steps, hbm_peak, hbm_src, fp32_peak):
         torch = self.torch
         flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        self.step()  # untimed: the caching allocator settles (the flush buffer above may have taken the block the workspace was using)
+        torch.cuda.synchronize()
         ts = []
         for _ in range(max(3, steps)):
             l2_flush(flush)
@@ -686,7 +694,7 @@ class KittiEvalWorkload(Workload):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        t = float(np.mean(ts)) * 1e-3
+        t = float(np.median(ts)) * 1e-3
         ach = self.bytes_per_step / t / 1e9
         return {"bound": "hbm", "kernel": "kitti_pair_kernel (+2 x kitti_prep_kernel), both metrics", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
@@ -758,6 +766,8 @@ class PostProcWorkload(Workload):
         algorithmic bytes = scores + boxes read once + results."""
         torch = self.torch
         flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        self.step()  # untimed: the caching allocator settles (the flush buffer above may have taken the block the workspace was using)
+        torch.cuda.synchronize()
         ts = []
         for _ in range(max(3, steps)):
             l2_flush(flush)
@@ -767,7 +777,7 @@ class PostProcWorkload(Workload):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        t = float(np.mean(ts)) * 1e-3
+        t = float(np.median(ts)) * 1e-3
         byts = float(self.boxes_np.size * 4 + self.scores_np.size * 4 + self.units * 500 * 12)
         ach = byts / t / 1e9
         return {"bound": "hbm", "kernel": "select_topk_kernel + nms_prep_kernel + nms_lazy_kernel + select_finish_kernel (whole step)", "achieved": ach, "peak": hbm_peak,
@@ -842,6 +852,8 @@ class IouMaxWorkload(Workload):
         from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
 
         flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        self.step()  # untimed: the caching allocator settles (the flush buffer above may have taken the block the workspace was using)
+        torch.cuda.synchronize()
         ts = []
         for _ in range(max(3, steps)):
             l2_flush(flush)
@@ -851,7 +863,7 @@ class IouMaxWorkload(Workload):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        t = float(np.mean(ts)) * 1e-3
+        t = float(np.median(ts)) * 1e-3
         nz = int((U.boxes_iou3d_gpu(self.a[:2000], self.b) > 0).sum()) * (self.a.shape[0] / 2000.0)
         flops = 8.0 * (self.pairs - nz) + 818.0 * nz
         ach, peak = flops / t / 1e12, (fp32_peak or 74.4)
