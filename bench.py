@@ -253,6 +253,8 @@ class NmsWorkload(Workload):
         from lidardetection_b200.ops.iou3d_nms import iou3d_nms_utils as U
 
         torch = self.torch
+        if self.world > 1:
+            return self._e2e_pipelined_sharded(steps)
         pipe = U.HostNmsPipeline(self.units, self.boxes_np.shape[1], self.thresh, max_keep=self.post, depth=depth)
         for _ in range(3):  # warm-up: buffers, streams, allocator
             pipe.result(pipe.submit(self.h_boxes, self.h_scores))
@@ -265,6 +267,60 @@ class NmsWorkload(Workload):
             inflight.append(pipe.submit(self.h_boxes, self.h_scores))
         for t in inflight:
             hk, hn = pipe.result(t)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        self.d2h = hk.numel() * 8 + hn.numel() * 4
+        return dt
+
+    def _e2e_pipelined_sharded(self, steps):
+        """N > 1: the same serving loop around sharded.nms_batched_sharded (every rank uploads its own frames, runs the NMS whose epilogue
+        gathers all ranks' keep lists, downloads the gathered lists).  Two streams, two steps in flight: the upload of step k + 1
+        crosses PCIe while step k is in the kernels; the download of step k stays on the kernels' stream, BEFORE step k + 1 -- the
+        gathered result lives in one of two alternating symmetric buffers that the peers' kernels of step k + 2 write, and a peer
+        gets there only after this rank has passed the barrier of step k + 1."""
+        import time
+
+        torch = self.torch
+        dev = self.boxes.device
+        up, comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        slots = [{"boxes": torch.empty_like(self.boxes), "scores": torch.empty_like(self.scores), "ev_up": torch.cuda.Event(),
+                  "ev_done": torch.cuda.Event(), "h_keep": None, "h_num": None} for _ in range(2)]
+
+        def submit(k):
+            sl = slots[k % 2]
+            with torch.cuda.stream(up):  # (the slot's previous step was collected by result(k - 2): its device inputs are free)
+                sl["scores"].copy_(self.h_scores, non_blocking=True)
+                sl["boxes"].copy_(self.h_boxes, non_blocking=True)
+                sl["ev_up"].record(up)
+            with torch.cuda.stream(comp):
+                comp.wait_event(sl["ev_up"])
+                keep, num = self._nms(sl["boxes"], sl["scores"])
+                if sl["h_keep"] is None:
+                    sl["h_keep"] = torch.empty(keep.shape, dtype=keep.dtype).pin_memory()
+                    sl["h_num"] = torch.empty(num.shape, dtype=num.dtype).pin_memory()
+                sl["h_keep"].copy_(keep, non_blocking=True)
+                sl["h_num"].copy_(num, non_blocking=True)
+                sl["ev_done"].record(comp)
+
+        def result(k):
+            sl = slots[k % 2]
+            sl["ev_done"].synchronize()
+            return sl["h_keep"], sl["h_num"]
+
+        want_keep, want_num = self._nms(self.boxes, self.scores)  # the device-resident call on the same frames
+        want_keep, want_num = want_keep.cpu(), want_num.cpu()
+        for k in range(4):  # warm-up: buffers, streams, both symmetric buffers; and the loop returns what the plain call returns
+            submit(k)
+            hk, hn = result(k)
+            assert torch.equal(hk, want_keep) and torch.equal(hn, want_num), "pipelined multi-GPU step != plain step"
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            if k >= 2:
+                hk, hn = result(k - 2)  # frees the slot step k is about to use
+            submit(k)
+        for k in range(max(0, steps - 2), steps):
+            hk, hn = result(k)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         self.d2h = hk.numel() * 8 + hn.numel() * 4
@@ -1202,9 +1258,11 @@ def main():
     # N = 1, NMS workloads: the same steps through the serving loop of the public API (four steps in flight); the per-call figure
     # above stays in the line as e2e_sync
     e2e_sync_s, e2e_depth = e2e_s, 1
-    if world == 1 and hasattr(wl, "e2e_pipelined"):
-        e2e_depth = 4
+    if hasattr(wl, "e2e_pipelined"):
+        e2e_depth = 4 if world == 1 else 2
+        barrier()
         e2e_s = wl.e2e_pipelined(args.steps, e2e_depth)
+        barrier()
     tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -1248,7 +1306,8 @@ def main():
         "config": workload_config(wl.name),
         "measurement": {"units_per_step_per_gpu": wl.units,
                         "timing": "CUDA events per step on the launching stream, summed over steps, max over ranks",
-                        "e2e": ("HostNmsPipeline (public API): every step uploads its inputs from pinned host memory and downloads its result; "
+                        "e2e": (("HostNmsPipeline (public API)" if world == 1 else "the same serving loop around sharded.nms_batched_sharded (upload on one stream; kernels + gather + download of the gathered lists on another)") +
+                                ": every step uploads its inputs from pinned host memory and downloads its result; "
                                 f"{e2e_depth} steps in flight (upload of step k + 1 overlaps the kernels of step k); wall clock over all steps"
                                 if e2e_depth > 1 else "one blocking call of the public API per step from pinned host memory, result read back; wall clock"),
                         "multi_gpu": (getattr(wl, "multi_gpu_note", None) or
